@@ -1,0 +1,192 @@
+"""ctypes doors to the parity checkers (TEST INFRASTRUCTURE ONLY -- see oracle/sdf_oracle.c header).
+
+``oracle.port``  -> oracle/liboracle.so, the plain-C restatement (always buildable: gcc only).
+``oracle.ref``   -> oracle/_ref/libsdfgen_ref.so, the unmodified reference CPU code compiled in place
+                    from /root/reference (present wherever it was built; it travels to the GPU box
+                    as a prebuilt file).  ``oracle.have_ref()`` says whether it can be loaded.
+
+Only tests/, __graft_entry__ (build/smoke) and bench.py's CPU-baseline legs may import this package.
+Nothing under sdfgen_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT_SO = os.path.join(_HERE, "liboracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libsdfgen_ref.so")
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """(Re)build the checkers with oracle/Makefile (the _ref target is a no-op without /root/reference)."""
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+class _Outputs(C.Structure):
+    _fields_ = [("phi_band", C.POINTER(C.c_float)), ("tri_band", C.POINTER(C.c_int32)),
+                ("counts", C.POINTER(C.c_int32)), ("phi_swept", C.POINTER(C.c_float)),
+                ("tri_final", C.POINTER(C.c_int32)), ("stats", C.POINTER(C.c_int64))]
+
+
+@dataclass
+class Staged:
+    """All arrays are flat, i fastest (index i + ni*(j + nj*k)), like the reference's Array3."""
+    phi: np.ndarray          # signed result
+    phi_band: np.ndarray     # |phi| after the exact band
+    tri_band: np.ndarray     # closest_tri after the exact band
+    counts: np.ndarray       # intersection_count
+    phi_swept: np.ndarray    # |phi| after the sweeps
+    tri_final: np.ndarray    # closest_tri after the sweeps
+    stats: np.ndarray | None = None
+
+
+def _prep(vertices, triangles, origin):
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    o = np.ascontiguousarray(origin, dtype=np.float32).reshape(3)
+    return v, t, o
+
+
+class _Port:
+    _lib = None
+
+    def lib(self):
+        if self._lib is None:
+            if not os.path.exists(_PORT_SO) or os.path.getmtime(_PORT_SO) < os.path.getmtime(
+                    os.path.join(_HERE, "sdf_oracle.c")):
+                build()
+            L = C.CDLL(_PORT_SO)
+            L.sdfo_make_level_set3.restype = C.c_int
+            L.sdfo_make_level_set3.argtypes = [_u32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_float,
+                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p,
+                                               C.POINTER(_Outputs)]
+            L.sdfo_band_counts_slab.restype = C.c_int
+            L.sdfo_band_counts_slab.argtypes = [_u32p, C.c_uint64, _f32p, _f32p, C.c_float,
+                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                _f32p, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32)]
+            L.sdfo_point_triangle_distance.restype = C.c_float
+            L.sdfo_point_triangle_distance.argtypes = [_f32p, _f32p, _f32p, _f32p]
+            self._lib = L
+        return self._lib
+
+    def make_level_set3(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1):
+        """Signed phi only (flat, i fastest)."""
+        v, t, o = _prep(vertices, triangles, origin)
+        phi = np.empty(ni * nj * nk, dtype=np.float32)
+        rc = self.lib().sdfo_make_level_set3(t, t.shape[0], v, v.shape[0], o, dx, ni, nj, nk, exact_band,
+                                             16, phi, None)
+        if rc != 0:
+            raise RuntimeError(f"oracle port failed rc={rc}")
+        return phi
+
+    def staged(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1, nsweeps=16, stats=False) -> Staged:
+        v, t, o = _prep(vertices, triangles, origin)
+        V = ni * nj * nk
+        s = Staged(np.empty(V, np.float32), np.empty(V, np.float32), np.empty(V, np.int32),
+                   np.empty(V, np.int32), np.empty(V, np.float32), np.empty(V, np.int32),
+                   np.zeros(80, np.int64) if stats else None)
+        out = _Outputs(_ptr(s.phi_band, C.c_float), _ptr(s.tri_band, C.c_int32), _ptr(s.counts, C.c_int32),
+                       _ptr(s.phi_swept, C.c_float), _ptr(s.tri_final, C.c_int32), _ptr(s.stats, C.c_int64))
+        rc = self.lib().sdfo_make_level_set3(t, t.shape[0], v, v.shape[0], o, dx, ni, nj, nk, exact_band,
+                                             nsweeps, s.phi, C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"oracle port failed rc={rc}")
+        return s
+
+    def band_counts_slab(self, vertices, triangles, origin, dx, ni, nj, nk, k_lo, k_hi, exact_band=1):
+        v, t, o = _prep(vertices, triangles, origin)
+        V = ni * nj * (k_hi - k_lo)
+        phi, tri, cnt = np.empty(V, np.float32), np.empty(V, np.int32), np.empty(V, np.int32)
+        rc = self.lib().sdfo_band_counts_slab(t, t.shape[0], v, o, dx, ni, nj, nk, k_lo, k_hi, exact_band,
+                                              phi, tri, cnt)
+        if rc != 0:
+            raise RuntimeError(f"oracle slab failed rc={rc}")
+        return phi, tri, cnt
+
+    def point_triangle_distance(self, x0, x1, x2, x3) -> float:
+        a = [np.ascontiguousarray(x, dtype=np.float32).reshape(3) for x in (x0, x1, x2, x3)]
+        return float(self.lib().sdfo_point_triangle_distance(*a))
+
+
+class _Ref:
+    _lib = None
+
+    def available(self) -> bool:
+        return os.path.exists(_REF_SO)
+
+    def lib(self):
+        if self._lib is None:
+            if not self.available():
+                build()
+            if not self.available():
+                raise RuntimeError("oracle/_ref/libsdfgen_ref.so is absent and /root/reference is not here to build it")
+            L = C.CDLL(_REF_SO)
+            L.ref_make_level_set3.restype = C.c_int
+            L.ref_make_level_set3.argtypes = [_u32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_float,
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+            L.ref_make_level_set3_staged.restype = C.c_int
+            L.ref_make_level_set3_staged.argtypes = [_u32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_float,
+                                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+            L.ref_point_triangle_distance.restype = C.c_float
+            L.ref_point_triangle_distance.argtypes = [_f32p, _f32p, _f32p, _f32p]
+            L.ref_hardware_concurrency.restype = C.c_int
+            self._lib = L
+        return self._lib
+
+    def hardware_concurrency(self) -> int:
+        return int(self.lib().ref_hardware_concurrency())
+
+    def make_level_set3(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1, num_threads=1):
+        """sdfgen::cpu::make_level_set3 itself; num_threads=1 is the parity oracle (the threaded
+        path is racy), num_threads=0 is the reference's auto-threaded timing baseline."""
+        v, t, o = _prep(vertices, triangles, origin)
+        phi = np.empty(ni * nj * nk, dtype=np.float32)
+        rc = self.lib().ref_make_level_set3(t, t.shape[0], v, v.shape[0], o, dx, ni, nj, nk, exact_band,
+                                            num_threads, phi)
+        if rc != 0:
+            raise RuntimeError(f"reference failed rc={rc}")
+        return phi
+
+    def staged(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1, nsweeps=16) -> Staged:
+        v, t, o = _prep(vertices, triangles, origin)
+        V = ni * nj * nk
+        s = Staged(np.empty(V, np.float32), np.empty(V, np.float32), np.empty(V, np.int32),
+                   np.empty(V, np.int32), np.empty(V, np.float32), np.empty(V, np.int32))
+        rc = self.lib().ref_make_level_set3_staged(
+            t, t.shape[0], v, v.shape[0], o, dx, ni, nj, nk, exact_band, nsweeps,
+            s.phi_band.ctypes.data, s.tri_band.ctypes.data, s.counts.ctypes.data,
+            s.phi_swept.ctypes.data, s.tri_final.ctypes.data, s.phi.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"reference staged failed rc={rc}")
+        return s
+
+    def point_triangle_distance(self, x0, x1, x2, x3) -> float:
+        a = [np.ascontiguousarray(x, dtype=np.float32).reshape(3) for x in (x0, x1, x2, x3)]
+        return float(self.lib().ref_point_triangle_distance(*a))
+
+
+port = _Port()
+ref = _Ref()
+
+
+def have_ref() -> bool:
+    return ref.available() or os.path.exists("/root/reference/cpu_lib/makelevelset3.cpp")
+
+
+def best():
+    """The strongest available checker: the compiled reference if present, else the C port."""
+    return ref if have_ref() else port
