@@ -1,0 +1,128 @@
+/*
+ * sdfb.h -- C ABI of the B200-native make_level_set3 (libsdfb.so, sm_100a only).
+ *
+ * This is the drop-in boundary for ONE hot path of SDFGenFast: triangle mesh -> signed distance
+ * grid.  The reference has no C ABI for it; the slot it fills is the C++ symbol
+ *     sdfgen::gpu::make_level_set3          /root/reference/gpu_lib/makelevelset3_gpu.h:40-42
+ * reached through
+ *     sdfgen::make_level_set3 (dispatch)    /root/reference/common/sdfgen_unified.cpp:30-71
+ *     sdfgen::is_gpu_available              /root/reference/common/sdfgen_unified.cpp:19-28
+ *     Python sdfgen_ext.generate_sdf        /root/reference/python/sdfgen_py.cpp:160-218
+ * include/sdfgen_b200.hpp is the C++ shim with the reference's signatures on top of this file and
+ * sdfgen_b200/__init__.py is the Python mirror; INTEGRATION.md shows the reference-side edits.
+ *
+ * Semantics are those of the reference's single-threaded CPU path
+ * (/root/reference/cpu_lib/makelevelset3.cpp:192-304): exact band with lowest-triangle-index
+ * tie-break, SOS-robust x-ray crossing counts, 2 x 8 Gauss-Seidel closest-triangle sweeps in the
+ * reference's order, parity sign.  There is no CPU fallback: every entry point fails with
+ * SDFB_ERR_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Conventions: plain pointers and sizes only; all functions return 0 (SDFB_OK) or a negative
+ * SDFB_ERR_* code and leave a message for sdfb_last_error() (thread-local).  Grids are dense,
+ * "i fastest" (index i + ni*(j + nj*k), /root/reference/common/array3.h:111-115) unless
+ * SDFB_OUT_KFASTEST is given.  Triangles are uint32[ntri][3], vertices float[nvert][3]
+ * (Vec3ui / Vec3f PODs, /root/reference/common/vec.h:25-29,180-181).
+ */
+#ifndef SDFB_H
+#define SDFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFB_OK                 0
+#define SDFB_ERR_INVALID       -1   /* bad argument (null pointer, non-positive size, dx<=0 ...)   */
+#define SDFB_ERR_NO_DEVICE     -2   /* no CUDA device / not an sm_100 part / driver failure        */
+#define SDFB_ERR_CUDA          -3   /* a CUDA call failed; message has the CUDA error string       */
+#define SDFB_ERR_OOM           -4   /* device or host allocation failed                            */
+#define SDFB_ERR_STATE         -5   /* call order violated (e.g. run before a mesh was set)        */
+#define SDFB_ERR_LIMIT         -6   /* more than SDFB_MAX_TRIANGLES triangles                      */
+
+/* closest-triangle ids share a 32-bit word with a 5-bit sweep stamp */
+#define SDFB_MAX_TRIANGLES     134217726u
+
+/* flags */
+#define SDFB_OUT_KFASTEST       0x1u  /* phi/tri/count outputs in C order [ni][nj][nk] (k fastest), the
+                                         layout sdfgen_ext.generate_sdf returns (sdfgen_py.cpp:80-86)
+                                         and the .sdf file stores (common/sdf_io.cpp:49-57)          */
+#define SDFB_SWEEP_LEVELS       0x2u  /* debug schedule: one launch per anti-diagonal level (slow,
+                                         trivially exact); default is the pipelined column schedule  */
+#define SDFB_NO_SIGN            0x4u  /* stop before the sign pass (phi stays unsigned)              */
+
+const char *sdfb_version(void);
+const char *sdfb_last_error(void);
+
+/* Number of usable sm_100 devices; 0 when none (never negative).  Replaces
+ * sdfgen::is_gpu_available (common/sdfgen_unified.cpp:19-28): available == (count > 0). */
+int sdfb_device_count(void);
+
+/* Kernel launches issued by this library in the calling process so far (all plans). */
+uint64_t sdfb_launch_count(void);
+
+/*
+ * One-shot, host buffers in and out, current device, blocking.  Drop-in for
+ * sdfgen::gpu::make_level_set3 (gpu_lib/makelevelset3_gpu.cu:595-777).
+ *   phi_out                 ni*nj*nk floats, required
+ *   closest_tri_out         ni*nj*nk int32 or NULL  (-1 where no triangle was ever assigned)
+ *   intersection_count_out  ni*nj*nk int32 or NULL
+ * The two nullable outputs exist because parity is graded on them and the reference keeps them as
+ * locals (cpu_lib/makelevelset3.cpp:198-199).
+ */
+int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
+                         const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
+                         int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
+                         int32_t *intersection_count_out, uint32_t flags);
+
+/* ---- plan API: device-resident state, explicit phases, k-slabs for multi-GPU ---------------- */
+
+typedef struct sdfb_plan sdfb_plan;
+
+/*
+ * A plan owns all device state for the k-slab [k_lo,k_hi) of a global ni x nj x nk grid on
+ * `device` (k_lo=0,k_hi=nk for a single GPU).  State: 8-byte cells {phi, stamp|closest_tri},
+ * int32 crossing counts, float output; plus one halo plane of cells below and above the slab.
+ */
+int sdfb_plan_create(sdfb_plan **plan, int device, int32_t ni, int32_t nj, int32_t nk,
+                     int32_t k_lo, int32_t k_hi, uint32_t flags);
+int sdfb_plan_destroy(sdfb_plan *plan);
+
+/* Mesh from host memory (copied, may be pageable) or already on the plan's device (borrowed until
+ * the next set/destroy).  Builds the per-triangle records. `stream` is a cudaStream_t (NULL = default). */
+int sdfb_plan_set_mesh_host(sdfb_plan *plan, const uint32_t *tri, uint64_t ntri,
+                            const float *xyz, uint64_t nvert, void *stream);
+int sdfb_plan_set_mesh_device(sdfb_plan *plan, const uint32_t *d_tri, uint64_t ntri,
+                              const float *d_xyz, uint64_t nvert, void *stream);
+
+/* Phase A: init + exact band + crossing counts (cpu_lib/makelevelset3.cpp:196-236). Asynchronous. */
+int sdfb_plan_band(sdfb_plan *plan, const float origin[3], float dx, int32_t exact_band, void *stream);
+/* Phase B: sweeps first..first+count-1 of the reference's 16 (index s uses direction s%8 of
+ * cpu_lib/makelevelset3.cpp:245-248).  Asynchronous.  Halo planes, if the slab has neighbours, must
+ * have been filled by the caller (sdfb_plan_halo_ptrs) before each call. */
+int sdfb_plan_sweep(sdfb_plan *plan, int32_t first, int32_t count, void *stream);
+/* Phase C: parity sign + unpack to the float output (cpu_lib/makelevelset3.cpp:295-303). Asynchronous. */
+int sdfb_plan_sign(sdfb_plan *plan, void *stream);
+/* All three phases with the reference's 16 sweeps. Asynchronous. */
+int sdfb_plan_run(sdfb_plan *plan, const float origin[3], float dx, int32_t exact_band, void *stream);
+
+/* Device pointers (valid until destroy): cells uint64[(k_hi-k_lo+2) planes], the first and last
+ * plane being the halos; counts int32[slab]; phi float[slab] (layout per plan flags). */
+int sdfb_plan_device_ptrs(sdfb_plan *plan, void **cells, void **counts, void **phi);
+/* Number of cells whose closest triangle changed during the sweeps since the last sdfb_plan_band or
+ * sdfb_plan_changed call (synchronises the stream; used by the multi-GPU fixed-point loop). */
+int sdfb_plan_changed(sdfb_plan *plan, void *stream, uint64_t *changed);
+
+/* Blocking copies of the slab results to host memory (any may be NULL).  phi is the output of
+ * sdfb_plan_sign (or the unsigned cell phi if the sign pass has not run). */
+int sdfb_plan_download(sdfb_plan *plan, float *phi_out, int32_t *closest_tri_out,
+                       int32_t *intersection_count_out, void *stream);
+
+/* Device time of the phases of the last completed run, in ms: out[0]=band (init+records+band+counts),
+ * out[1]=sweeps, out[2]=sign/unpack, out[3]=total.  Blocks until the work has finished. */
+int sdfb_plan_phase_ms(sdfb_plan *plan, float out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFB_H */

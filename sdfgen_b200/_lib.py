@@ -1,0 +1,168 @@
+"""ctypes binding of libsdfb.so (include/sdfb.h).  No fallback: a missing library is an ImportError
+that says how to build it, a missing GPU is a RuntimeError from the library itself."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdfb.so")
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
+OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN = 0x1, 0x2, 0x4
+
+_lib = None
+
+
+class SdfbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsdfb error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build the CUDA extension first: "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C sdfgen_b200/csrc`. "
+            "sdfgen_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32, u32, f32 = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.c_float
+    L.sdfb_version.restype = C.c_char_p
+    L.sdfb_last_error.restype = C.c_char_p
+    L.sdfb_device_count.restype = C.c_int
+    L.sdfb_launch_count.restype = u64
+    L.sdfb_make_level_set3.restype = C.c_int
+    L.sdfb_make_level_set3.argtypes = [vp, u64, vp, u64, vp, f32, i32, i32, i32, i32, vp, vp, vp, u32]
+    L.sdfb_plan_create.restype = C.c_int
+    L.sdfb_plan_create.argtypes = [C.POINTER(vp), C.c_int, i32, i32, i32, i32, i32, u32]
+    L.sdfb_plan_destroy.restype = C.c_int
+    L.sdfb_plan_destroy.argtypes = [vp]
+    for name in ("sdfb_plan_set_mesh_host", "sdfb_plan_set_mesh_device"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, u64, vp, u64, vp]
+    L.sdfb_plan_band.restype = C.c_int
+    L.sdfb_plan_band.argtypes = [vp, vp, f32, i32, vp]
+    L.sdfb_plan_sweep.restype = C.c_int
+    L.sdfb_plan_sweep.argtypes = [vp, i32, i32, vp]
+    L.sdfb_plan_sign.restype = C.c_int
+    L.sdfb_plan_sign.argtypes = [vp, vp]
+    L.sdfb_plan_run.restype = C.c_int
+    L.sdfb_plan_run.argtypes = [vp, vp, f32, i32, vp]
+    L.sdfb_plan_device_ptrs.restype = C.c_int
+    L.sdfb_plan_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.sdfb_plan_changed.restype = C.c_int
+    L.sdfb_plan_changed.argtypes = [vp, vp, C.POINTER(u64)]
+    L.sdfb_plan_download.restype = C.c_int
+    L.sdfb_plan_download.argtypes = [vp, vp, vp, vp, vp]
+    L.sdfb_plan_phase_ms.restype = C.c_int
+    L.sdfb_plan_phase_ms.argtypes = [vp, C.POINTER(f32 * 4)]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != OK:
+        msg = lib().sdfb_last_error().decode("utf-8", "replace")
+        if rc == ERR_INVALID:
+            raise ValueError(msg)          # the reference raises std::invalid_argument -> ValueError
+        if rc == ERR_OOM:
+            raise MemoryError(msg)
+        raise SdfbError(rc, msg)
+
+
+def _addr(a):
+    """Host address of a numpy array, or a raw integer address (device pointer / pinned buffer)."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data
+
+
+class Plan:
+    """Device-resident state for one k-slab of a grid (include/sdfb.h plan API)."""
+
+    def __init__(self, ni, nj, nk, k_lo=0, k_hi=None, device=0, flags=0):
+        self.ni, self.nj, self.nk = int(ni), int(nj), int(nk)
+        self.k_lo, self.k_hi = int(k_lo), int(nk if k_hi is None else k_hi)
+        self.device, self.flags = int(device), int(flags)
+        self._h = C.c_void_p()
+        check(lib().sdfb_plan_create(C.byref(self._h), self.device, self.ni, self.nj, self.nk,
+                                     self.k_lo, self.k_hi, self.flags))
+        self._keep = None
+
+    @property
+    def slab_voxels(self):
+        return self.ni * self.nj * (self.k_hi - self.k_lo)
+
+    def close(self):
+        if self._h:
+            lib().sdfb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mesh_host(self, vertices: np.ndarray, triangles: np.ndarray, stream=0):
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        check(lib().sdfb_plan_set_mesh_host(self._h, t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], stream or None))
+        self._keep = (v, t)
+
+    def set_mesh_host_ptr(self, tri_addr, ntri, xyz_addr, nvert, stream=0):
+        check(lib().sdfb_plan_set_mesh_host(self._h, tri_addr, ntri, xyz_addr, nvert, stream or None))
+
+    def set_mesh_device(self, d_tri_addr, ntri, d_xyz_addr, nvert, stream=0, keepalive=None):
+        check(lib().sdfb_plan_set_mesh_device(self._h, d_tri_addr, ntri, d_xyz_addr, nvert, stream or None))
+        self._keep = keepalive
+
+    def _origin(self, origin):
+        self._o = np.ascontiguousarray(origin, dtype=np.float32).reshape(3)
+        return self._o.ctypes.data
+
+    def band(self, origin, dx, exact_band=1, stream=0):
+        check(lib().sdfb_plan_band(self._h, self._origin(origin), float(dx), int(exact_band), stream or None))
+
+    def sweep(self, first=0, count=16, stream=0):
+        check(lib().sdfb_plan_sweep(self._h, int(first), int(count), stream or None))
+
+    def sign(self, stream=0):
+        check(lib().sdfb_plan_sign(self._h, stream or None))
+
+    def run(self, origin, dx, exact_band=1, stream=0):
+        check(lib().sdfb_plan_run(self._h, self._origin(origin), float(dx), int(exact_band), stream or None))
+
+    def device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().sdfb_plan_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def changed(self, stream=0) -> int:
+        n = C.c_uint64()
+        check(lib().sdfb_plan_changed(self._h, stream or None, C.byref(n)))
+        return int(n.value)
+
+    def download(self, phi=True, tri=False, counts=False, stream=0, phi_out=None):
+        """Blocking copy to host.  Returns (phi, tri, counts) flat arrays (None where not requested).
+        ``phi_out`` may be a preallocated float32 array or a raw (e.g. pinned) host address."""
+        V = self.slab_voxels
+        p = phi_out if phi_out is not None else (np.empty(V, np.float32) if phi else None)
+        t = np.empty(V, np.int32) if tri else None
+        c = np.empty(V, np.int32) if counts else None
+        check(lib().sdfb_plan_download(self._h, _addr(p), _addr(t), _addr(c), stream or None))
+        return p, t, c
+
+    def phase_ms(self):
+        out = (C.c_float * 4)()
+        check(lib().sdfb_plan_phase_ms(self._h, C.byref(out)))
+        return dict(band=out[0], sweeps=out[1], sign=out[2], total=out[3])

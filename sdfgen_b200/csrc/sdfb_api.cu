@@ -1,0 +1,377 @@
+// sdfb_api.cu -- host side of the C ABI declared in include/sdfb.h.
+//
+// Mirrors the host orchestration the reference does in gpu_lib/makelevelset3_gpu.cu:595-777
+// (allocate, H2D mesh, kernels, D2H phi, free) but: state lives in a reusable plan, everything is
+// enqueued asynchronously on one stream, errors come back as codes instead of exit(EXIT_FAILURE)
+// (gpu_lib/makelevelset3_gpu.cu:14-20), linear indices are 64-bit, and there is no debug D2H copy.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <atomic>
+#include <new>
+#include <cuda_runtime.h>
+#include "../../include/sdfb.h"
+#include "sdfb_kernels.cuh"
+
+using namespace sdfb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool device_is_sm100(int dev)
+{
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    return major == 10;    // the only code in libsdfb.so is sm_100a SASS
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct sdfb_plan {
+    int device = 0;
+    uint32_t flags = 0;
+    Grid g{};
+    float init_phi = 0.f;
+    // device state
+    uint64_t *cells = nullptr;       // (nkl+2) planes
+    int32_t *counts = nullptr;       // slab voxels
+    float *phi = nullptr;            // slab voxels, i fastest
+    float *phi_k = nullptr;          // slab voxels, k fastest (only with SDFB_OUT_KFASTEST)
+    int32_t *scratch = nullptr;      // slab voxels, lazily allocated for tri / count downloads
+    unsigned long long *changed = nullptr;
+    uint32_t *progress = nullptr;    // column-schedule flags
+    size_t progress_words = 0;
+    // mesh
+    uint64_t ntri = 0, nvert = 0;
+    uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
+    float *xyz_own = nullptr;
+    TriRec *rec = nullptr;
+    uint32_t *units = nullptr;
+    uint64_t *prefix = nullptr, *block_sums = nullptr;
+    uint64_t rec_cap = 0;
+    bool have_mesh = false, have_band = false, have_sign = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after band, after sweeps, after sign
+    bool timed = false;
+};
+
+namespace {
+
+void free_mesh(sdfb_plan *p)
+{
+    cudaFree(p->tri_own); cudaFree(p->xyz_own); cudaFree(p->rec); cudaFree(p->units);
+    cudaFree(p->prefix); cudaFree(p->block_sums);
+    p->tri_own = nullptr; p->xyz_own = nullptr; p->rec = nullptr; p->units = nullptr;
+    p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0; p->have_mesh = false;
+}
+
+int ensure_mesh_capacity(sdfb_plan *p, uint64_t ntri)
+{
+    if (ntri <= p->rec_cap && p->rec) return SDFB_OK;
+    cudaFree(p->rec); cudaFree(p->units); cudaFree(p->prefix); cudaFree(p->block_sums);
+    p->rec = nullptr; p->units = nullptr; p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0;
+    uint64_t cap = ntri ? ntri : 1;
+    CU(cudaMalloc(&p->rec, cap * sizeof(TriRec)));
+    CU(cudaMalloc(&p->units, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&p->prefix, (cap + 1) * sizeof(uint64_t)));
+    CU(cudaMalloc(&p->block_sums, (cap / 2048 + 2) * sizeof(uint64_t)));
+    p->rec_cap = cap;
+    return SDFB_OK;
+}
+
+int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint64_t ntri, uint64_t nvert, cudaStream_t st)
+{
+    if (ntri > SDFB_MAX_TRIANGLES) return fail(SDFB_ERR_LIMIT, "%llu triangles exceed the limit of %u", (unsigned long long)ntri, SDFB_MAX_TRIANGLES);
+    int rc = ensure_mesh_capacity(p, ntri);
+    if (rc) return rc;
+    g_launches += launch_tri_prep(d_tri, d_xyz, ntri, p->rec, st);
+    CU(cudaGetLastError());
+    p->ntri = ntri; p->nvert = nvert; p->have_mesh = true; p->have_band = false; p->have_sign = false;
+    return SDFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sdfb_version(void) { return "sdfgen-b200 0.1 (sm_100a)"; }
+const char *sdfb_last_error(void) { return g_err; }
+uint64_t sdfb_launch_count(void) { return g_launches.load(); }
+
+int sdfb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) if (device_is_sm100(d)) ++usable;
+    return usable;
+}
+
+int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_t nk,
+                     int32_t k_lo, int32_t k_hi, uint32_t flags)
+{
+    if (!out) return fail(SDFB_ERR_INVALID, "plan pointer is null");
+    *out = nullptr;
+    if (ni <= 0 || nj <= 0 || nk <= 0) return fail(SDFB_ERR_INVALID, "grid dimensions must be positive (got %d x %d x %d)", ni, nj, nk);
+    if (ni > 32767 || nj > 32767 || nk > 32767) return fail(SDFB_ERR_INVALID, "grid dimensions above 32767 are not supported");
+    if (k_lo < 0 || k_hi > nk || k_lo >= k_hi) return fail(SDFB_ERR_INVALID, "bad slab [%d,%d) of %d planes", k_lo, k_hi, nk);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SDFB_ERR_NO_DEVICE, "no CUDA device is visible; libsdfb has no CPU fallback"); }
+    if (device < 0 || device >= ndev) return fail(SDFB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    if (!device_is_sm100(device)) return fail(SDFB_ERR_NO_DEVICE, "device %d is not an sm_100 (B200) part; libsdfb ships sm_100a code only", device);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(SDFB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    sdfb_plan *p = new (std::nothrow) sdfb_plan();
+    if (!p) return fail(SDFB_ERR_OOM, "host allocation failed");
+    p->device = device; p->flags = flags;
+    p->g.ni = ni; p->g.nj = nj; p->g.nk = nk; p->g.k_lo = k_lo; p->g.k_hi = k_hi;
+    p->g.dx = 1.f; p->g.ox = p->g.oy = p->g.oz = 0.f; p->g.band = 1;
+    const size_t V = (size_t)p->g.slab_voxels();
+    cudaError_t e;
+    if ((e = cudaMalloc(&p->cells, (size_t)p->g.cell_count() * sizeof(uint64_t))) != cudaSuccess ||
+        (e = cudaMalloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
+        ((flags & SDFB_OUT_KFASTEST) && (e = cudaMalloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||
+        (e = cudaMalloc(&p->changed, sizeof(unsigned long long))) != cudaSuccess) {
+        sdfb_plan_destroy(p);
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
+    }
+    p->progress_words = sweep_columns_progress_words(p->g);
+    if (p->progress_words && (e = cudaMalloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
+        sdfb_plan_destroy(p);
+        cudaGetLastError();
+        return fail(SDFB_ERR_OOM, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    for (auto &ev : p->ev) {
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) { sdfb_plan_destroy(p); return fail(SDFB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+    }
+    cudaMemset(p->changed, 0, sizeof(unsigned long long));
+    *out = p;
+    return SDFB_OK;
+}
+
+int sdfb_plan_destroy(sdfb_plan *p)
+{
+    if (!p) return SDFB_OK;
+    DeviceGuard dg(p->device);
+    cudaDeviceSynchronize();
+    free_mesh(p);
+    cudaFree(p->cells); cudaFree(p->counts); cudaFree(p->phi); cudaFree(p->phi_k); cudaFree(p->scratch);
+    cudaFree(p->changed); cudaFree(p->progress);
+    for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
+    delete p;
+    cudaGetLastError();
+    return SDFB_OK;
+}
+
+int sdfb_plan_set_mesh_host(sdfb_plan *p, const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if ((ntri && !tri) || (nvert && !xyz)) return fail(SDFB_ERR_INVALID, "mesh pointer is null");
+    if (ntri > SDFB_MAX_TRIANGLES) return fail(SDFB_ERR_LIMIT, "%llu triangles exceed the limit of %u", (unsigned long long)ntri, SDFB_MAX_TRIANGLES);
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaFree(p->tri_own); cudaFree(p->xyz_own); p->tri_own = nullptr; p->xyz_own = nullptr;
+    CU(cudaMalloc(&p->tri_own, (ntri ? ntri : 1) * 3 * sizeof(uint32_t)));
+    CU(cudaMalloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
+    if (ntri) CU(cudaMemcpyAsync(p->tri_own, tri, ntri * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (nvert) CU(cudaMemcpyAsync(p->xyz_own, xyz, nvert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    return build_records(p, p->tri_own, p->xyz_own, ntri, nvert, st);
+}
+
+int sdfb_plan_set_mesh_device(sdfb_plan *p, const uint32_t *d_tri, uint64_t ntri, const float *d_xyz, uint64_t nvert, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if ((ntri && !d_tri) || (nvert && !d_xyz)) return fail(SDFB_ERR_INVALID, "mesh pointer is null");
+    DeviceGuard dg(p->device);
+    return build_records(p, d_tri, d_xyz, ntri, nvert, (cudaStream_t)stream);
+}
+
+int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_band, void *stream)
+{
+    if (!p || !origin) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->have_mesh) return fail(SDFB_ERR_STATE, "sdfb_plan_band called before a mesh was set");
+    if (!(dx > 0.f)) return fail(SDFB_ERR_INVALID, "cell spacing dx must be positive");
+    if (exact_band < 0 || exact_band > 1024) return fail(SDFB_ERR_INVALID, "exact_band %d out of range [0,1024]", exact_band);
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    p->g.dx = dx; p->g.ox = origin[0]; p->g.oy = origin[1]; p->g.oz = origin[2]; p->g.band = exact_band;
+    // (ni+nj+nk)*dx: int sum converted to float, one float multiply (cpu_lib/makelevelset3.cpp:197)
+    volatile float nsum = (float)(p->g.ni + p->g.nj + p->g.nk);
+    p->init_phi = nsum * dx;
+    CU(cudaEventRecord(p->ev[0], st));
+    g_launches += launch_init(p->cells, p->g.cell_count(), p->init_phi, st);
+    CU(cudaMemsetAsync(p->counts, 0, (size_t)p->g.slab_voxels() * sizeof(int32_t), st));
+    CU(cudaMemsetAsync(p->changed, 0, sizeof(unsigned long long), st));
+    g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev[1], st));
+    p->have_band = true; p->have_sign = false; p->timed = false;
+    return SDFB_OK;
+}
+
+int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "sdfb_plan_sweep called before sdfb_plan_band");
+    if (first < 0 || count < 0) return fail(SDFB_ERR_INVALID, "bad sweep range");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int s = first; s < first + count; ++s) {
+        if (p->flags & SDFB_SWEEP_LEVELS)
+            g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
+        else
+            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, st);
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev[2], st));
+    p->have_sign = false;
+    return SDFB_OK;
+}
+
+int sdfb_plan_sign(sdfb_plan *p, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "sdfb_plan_sign called before sdfb_plan_band");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    g_launches += launch_sign(p->cells, p->counts, p->g, !(p->flags & SDFB_NO_SIGN), false, p->phi, st);
+    if (p->flags & SDFB_OUT_KFASTEST)
+        g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev[3], st));
+    p->have_sign = true; p->timed = true;
+    return SDFB_OK;
+}
+
+int sdfb_plan_run(sdfb_plan *p, const float origin[3], float dx, int32_t exact_band, void *stream)
+{
+    int rc = sdfb_plan_band(p, origin, dx, exact_band, stream);
+    if (rc) return rc;
+    rc = sdfb_plan_sweep(p, 0, 16, stream);
+    if (rc) return rc;
+    return sdfb_plan_sign(p, stream);
+}
+
+int sdfb_plan_device_ptrs(sdfb_plan *p, void **cells, void **counts, void **phi)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (cells) *cells = p->cells;
+    if (counts) *counts = p->counts;
+    if (phi) *phi = (p->flags & SDFB_OUT_KFASTEST) ? p->phi_k : p->phi;
+    return SDFB_OK;
+}
+
+int sdfb_plan_changed(sdfb_plan *p, void *stream, uint64_t *changed)
+{
+    if (!p || !changed) return fail(SDFB_ERR_INVALID, "null argument");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long h = 0;
+    CU(cudaMemcpyAsync(&h, p->changed, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(p->changed, 0, sizeof(h), st));
+    CU(cudaStreamSynchronize(st));
+    *changed = h;
+    return SDFB_OK;
+}
+
+int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *count_out, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "nothing to download: run the plan first");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t V = (size_t)p->g.slab_voxels();
+    const bool kf = (p->flags & SDFB_OUT_KFASTEST) != 0;
+    if (phi_out) {
+        if (!p->have_sign) {   // unsigned phi straight from the cells
+            g_launches += launch_sign(p->cells, p->counts, p->g, false, false, p->phi, st);
+            if (kf) g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
+        }
+        CU(cudaMemcpyAsync(phi_out, kf ? p->phi_k : p->phi, V * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (tri_out || (count_out && kf)) {
+        if (!p->scratch) CU(cudaMalloc(&p->scratch, V * sizeof(int32_t) * (kf ? 2 : 1)));
+    }
+    if (tri_out) {
+        g_launches += launch_unpack_tri(p->cells, p->g, false, p->scratch, st);
+        if (kf) g_launches += launch_relayout_i32(p->scratch, p->g, p->scratch + V, st);
+        CU(cudaMemcpyAsync(tri_out, kf ? p->scratch + V : p->scratch, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (count_out) {
+        if (kf) {
+            g_launches += launch_relayout_i32(p->counts, p->g, p->scratch, st);
+            CU(cudaMemcpyAsync(count_out, p->scratch, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemcpyAsync(count_out, p->counts, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    return SDFB_OK;
+}
+
+int sdfb_plan_phase_ms(sdfb_plan *p, float out[4])
+{
+    if (!p || !out) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->timed) return fail(SDFB_ERR_STATE, "no completed run to time (band, sweep and sign must all have been enqueued)");
+    DeviceGuard dg(p->device);
+    CU(cudaEventSynchronize(p->ev[3]));
+    CU(cudaEventElapsedTime(&out[0], p->ev[0], p->ev[1]));
+    CU(cudaEventElapsedTime(&out[1], p->ev[1], p->ev[2]));
+    CU(cudaEventElapsedTime(&out[2], p->ev[2], p->ev[3]));
+    CU(cudaEventElapsedTime(&out[3], p->ev[0], p->ev[3]));
+    return SDFB_OK;
+}
+
+int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
+                         const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
+                         int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
+                         int32_t *intersection_count_out, uint32_t flags)
+{
+    if (!phi_out || !origin) return fail(SDFB_ERR_INVALID, "null argument");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(SDFB_ERR_NO_DEVICE, "no CUDA device is visible; libsdfb has no CPU fallback"); }
+    sdfb_plan *p = nullptr;
+    int rc = sdfb_plan_create(&p, dev, ni, nj, nk, 0, nk, flags);
+    if (rc) return rc;
+    rc = sdfb_plan_set_mesh_host(p, tri, ntri, xyz, nvert, nullptr);
+    if (!rc) rc = sdfb_plan_run(p, origin, dx, exact_band, nullptr);
+    if (!rc) rc = sdfb_plan_download(p, phi_out, closest_tri_out, intersection_count_out, nullptr);
+    sdfb_plan_destroy(p);
+    return rc;
+}
+
+}  // extern "C"

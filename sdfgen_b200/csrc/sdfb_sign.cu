@@ -1,0 +1,92 @@
+// sdfb_sign.cu -- phase C of make_level_set3 on sm_100a: inside/outside sign from the running parity
+// of x-ray crossing counts along i (reference: cpu_lib/makelevelset3.cpp:295-303), fused with the
+// unpacking of the 8-byte cells into the float output, plus the output layout helpers.
+//
+// Rows (j,k) are independent and contiguous in i, so one warp owns a row and walks it 32 voxels at a
+// time: the parity prefix inside a chunk is a ballot + popc, the carry between chunks is one bit.
+#include "sdfb_kernels.cuh"
+
+namespace sdfb {
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_sign_rows(const uint64_t *__restrict__ cells, const int32_t *__restrict__ counts,
+                                                   Grid g, int apply_sign, float *__restrict__ phi_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = (int64_t)g.nj * g.nkl();
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+        const int64_t vbase = row * g.ni;                    // slab-local dense index of (0,j,k)
+        const int64_t cbase = vbase + g.plane();             // cells have one halo plane in front
+        unsigned carry = 0;
+        for (int i0 = 0; i0 < g.ni; i0 += 32) {
+            int i = i0 + lane;
+            bool in = i < g.ni;
+            unsigned odd = 0;
+            float phi = 0.f;
+            if (in) {
+                phi = cell_phi(cells[cbase + i]);
+                if (apply_sign) odd = (unsigned)counts[vbase + i] & 1u;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, odd);
+            unsigned par = (__popc(bal & (0xffffffffu >> (31 - lane))) + carry) & 1u;   // inclusive prefix
+            if (in) phi_out[vbase + i] = par ? -phi : phi;
+            carry = (carry + __popc(bal)) & 1u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_unpack_tri(const uint64_t *__restrict__ cells, int64_t n, int64_t halo,
+                                                    int32_t *__restrict__ tri_out)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        tri_out[v] = lo_tri_signed(cell_lo(cells[halo + v]));
+}
+
+// i-fastest [k][j][i]  ->  k-fastest [i][j][k] for one slab; 32x32 (i,k) tiles per j through shared memory
+__global__ void __launch_bounds__(256) k_relayout(const uint32_t *__restrict__ src, int ni, int nj, int nk,
+                                                  uint32_t *__restrict__ dst)
+{
+    __shared__ uint32_t tile[32][33];
+    const int j = blockIdx.z;
+    const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int i = i0 + tx, k = k0 + r;
+        if (i < ni && k < nk) tile[r][tx] = src[(int64_t)i + (int64_t)ni * ((int64_t)j + (int64_t)nj * k)];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int i = i0 + r, k = k0 + tx;
+        if (i < ni && k < nk) dst[((int64_t)i * nj + j) * (int64_t)nk + k] = tile[tx][r];
+    }
+}
+
+}  // namespace
+
+int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
+                bool kfastest, float *phi_out, cudaStream_t st)
+{
+    (void)kfastest;   // layout change is a separate launch_relayout_i32 so this kernel stays streaming
+    k_sign_rows<<<148 * 8, 256, 0, st>>>(cells, counts, g, apply_sign ? 1 : 0, phi_out);
+    return 1;
+}
+
+int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st)
+{
+    (void)kfastest;
+    k_unpack_tri<<<148 * 8, 256, 0, st>>>(cells, g.slab_voxels(), g.plane(), tri_out);
+    return 1;
+}
+
+int launch_relayout_i32(const int32_t *src, const Grid &g, int32_t *dst_kfastest, cudaStream_t st)
+{
+    dim3 grid((g.ni + 31) / 32, (g.nkl() + 31) / 32, g.nj);
+    k_relayout<<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(src), g.ni, g.nj, g.nkl(),
+                                     reinterpret_cast<uint32_t *>(dst_kfastest));
+    return 1;
+}
+
+}  // namespace sdfb

@@ -1,0 +1,79 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/sdfb.h
+declares, argument validation mirrors the reference, and there is no CPU fallback."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sdfgen_b200
+from sdfgen_b200 import _lib, meshes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    return sdfgen_b200.is_gpu_available()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sdfb.h")).read()
+    names = sorted(set(re.findall(r"\b(sdfb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+    assert b"sm_100a" in _lib.lib().sdfb_version()
+
+
+def test_library_has_only_sm100a_code():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_validation_errors_match_reference_messages():
+    v, t = meshes.unit_cube()
+    o = (0.0, 0.0, 0.0)
+    with pytest.raises(ValueError, match="empty mesh"):
+        sdfgen_b200.generate_sdf(np.zeros((0, 3), np.float32), t, o, 0.1, 8, 8, 8)
+    with pytest.raises(ValueError, match="empty mesh"):
+        sdfgen_b200.generate_sdf(v, np.zeros((0, 3), np.uint32), o, 0.1, 8, 8, 8)
+    with pytest.raises(ValueError, match="must be positive"):
+        sdfgen_b200.generate_sdf(v, t, o, 0.1, 0, 8, 8)
+    with pytest.raises(ValueError, match="must be positive"):
+        sdfgen_b200.generate_sdf(v, t, o, 0.1, 8, -1, 8)
+    with pytest.raises(ValueError, match="dx must be positive"):
+        sdfgen_b200.generate_sdf(v, t, o, 0.0, 8, 8, 8)
+    with pytest.raises(ValueError, match="Invalid backend"):
+        sdfgen_b200.generate_sdf(v, t, o, 0.1, 8, 8, 8, backend="tpu")
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        sdfgen_b200.generate_sdf(v, t, o, 0.1, 8, 8, 8, backend="cpu")
+
+
+def test_no_cpu_fallback_without_device():
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    assert _lib.lib().sdfb_device_count() == 0
+    v, t = meshes.unit_cube()
+    with pytest.raises(_lib.SdfbError) as e:
+        sdfgen_b200.generate_sdf(v, t, (0, 0, 0), 0.1, 8, 8, 8)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(_lib.SdfbError):
+        _lib.Plan(8, 8, 8)
+
+
+def test_c_abi_argument_checks_without_device():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.sdfb_plan_create(ctypes.byref(h), 0, 0, 8, 8, 0, 8, 0) == _lib.ERR_INVALID
+    assert b"positive" in L.sdfb_last_error()
+    assert L.sdfb_plan_create(ctypes.byref(h), 0, 8, 8, 8, 4, 2, 0) == _lib.ERR_INVALID
+    assert L.sdfb_plan_create(None, 0, 8, 8, 8, 0, 8, 0) == _lib.ERR_INVALID
+    assert L.sdfb_plan_destroy(None) == 0
+    assert L.sdfb_plan_band(None, None, 1.0, 1, None) == _lib.ERR_INVALID
+    assert L.sdfb_make_level_set3(None, 0, None, 0, None, 1.0, 4, 4, 4, 1, None, None, None, 0) == _lib.ERR_INVALID

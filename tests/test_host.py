@@ -1,0 +1,90 @@
+"""CPU tests of the host-side pieces: mesh generators, file side-cars, grid sizing wrappers."""
+import os
+
+import numpy as np
+import pytest
+
+import sdfgen_b200
+from sdfgen_b200 import mesh_io, meshes
+
+
+def _closed(f):
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64)
+    key = e[:, 0] * (f.max() + 1) + e[:, 1]
+    rev = e[:, 1] * (f.max() + 1) + e[:, 0]
+    return np.array_equal(np.sort(key), np.sort(rev))       # every directed edge has its opposite
+
+
+def test_generators_counts_and_closedness():
+    v, f = meshes.icosphere(3, 0.4)
+    assert f.shape == (20 * 4 ** 3, 3) and v.shape[0] == 10 * 4 ** 3 + 2 and _closed(f)
+    assert np.allclose(np.linalg.norm(v, axis=1), 0.4, atol=1e-6)
+    v, f = meshes.uv_sphere(9, 11)
+    assert f.shape[0] == 2 * 11 * 8 and _closed(f)
+    v, f = meshes.blob(188, 188, 0.35)
+    assert f.shape[0] == 70312 and _closed(f)
+    v, f = meshes.torus(10, 7, 0.3, 0.1, jitter=0.2)
+    assert f.shape[0] == 140 and _closed(f)
+    v, f = meshes.unit_cube()
+    assert f.shape[0] == 12 and _closed(f)
+    # outward orientation: signed volume positive
+    for v, f in (meshes.icosphere(2), meshes.uv_sphere(8, 8), meshes.torus(12, 8, 1.0, 0.3), meshes.unit_cube()):
+        a, b, c = (v[f[:, i]].astype(np.float64) for i in range(3))
+        assert np.einsum("ij,ij->i", a, np.cross(b, c)).sum() > 0
+
+
+def test_workload_c2_triangle_count_is_stated_exactly():
+    assert 20 * 4 ** 8 == 1310720
+    w = meshes.workload("c1_blob_256")
+    assert (w["ni"], w["nj"], w["nk"]) == (256, 256, 256) and w["triangles"].shape[0] == 70312
+
+
+def test_sdf_file_roundtrip_and_layout(tmp_path):
+    a = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4) - 5
+    p = str(tmp_path / "x.sdf")
+    mesh_io.save_sdf(p, a, (1.0, 2.0, 3.0), 0.5)
+    raw = open(p, "rb").read()
+    assert len(raw) == 36 + 4 * 24
+    assert np.frombuffer(raw, np.int32, 3).tolist() == [2, 3, 4]
+    assert np.frombuffer(raw, np.float32, 3, 24).tolist() == [2.0, 3.5, 5.0]
+    assert np.frombuffer(raw, np.float32, 2, 36).tolist() == [-5.0, -4.0]      # k fastest
+    b, origin, dx, bounds = mesh_io.load_sdf(p)
+    assert np.array_equal(a, b) and origin == (1.0, 2.0, 3.0) and dx == 0.5
+    with pytest.raises(ValueError):
+        mesh_io.save_sdf(p, np.zeros((2, 2)), (0, 0, 0), 1.0)
+
+
+def test_mesh_loaders(tmp_path):
+    obj = tmp_path / "q.obj"
+    obj.write_text("# c\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf 1/1/1 2/2/1 3/3/1 4/4/1\nf 1 2 3\n")
+    v, t, b = mesh_io.load_mesh(str(obj))
+    assert v.shape == (4, 3) and t.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]] and b == ((0, 0, 0), (1, 1, 0))
+    stl = tmp_path / "a.stl"
+    stl.write_text("solid s\nfacet normal 0 0 1\nouter loop\nvertex 0 0 0\nvertex 1 0 0\nvertex 0 1 0\nendloop\nendfacet\nendsolid s\n")
+    v, t, b = mesh_io.load_mesh(str(stl))
+    assert v.shape == (3, 3) and t.tolist() == [[0, 1, 2]]
+    import struct
+    binp = tmp_path / "b.stl"
+    tri = np.array([[0, 0, 1], [0, 0, 0], [2, 0, 0], [0, 3, 0]], np.float32)
+    binp.write_bytes(b"\0" * 80 + struct.pack("<I", 1) + tri.tobytes() + b"\0\0")
+    v, t, b = mesh_io.load_mesh(str(binp))
+    assert v.tolist() == tri[1:].tolist() and b[1] == (2.0, 3.0, 0.0)
+    with pytest.raises(RuntimeError):
+        mesh_io.load_mesh(str(tmp_path / "missing.obj"))
+
+
+def test_generate_from_mesh_sizing(monkeypatch):
+    seen = {}
+
+    def fake(vertices, triangles, origin, dx, nx, ny, nz, exact_band=1, backend="auto", num_threads=0):
+        seen.update(origin=origin, dx=dx, dims=(nx, ny, nz), band=exact_band)
+        return np.zeros((nx, ny, nz), np.float32)
+
+    monkeypatch.setattr(sdfgen_b200, "generate_sdf", fake)
+    v, t = meshes.unit_cube(0.0, 2.0)
+    v[:, 1] *= 0.5
+    sdf, meta = sdfgen_b200.generate_from_mesh(v, t, nx=16, padding=2, exact_band=2)
+    assert seen["dims"] == (20, 12, 20) and seen["band"] == 2 and abs(seen["dx"] - 0.125) < 1e-7
+    assert np.allclose(seen["origin"], (-0.25, -0.25, -0.25)) and set(meta) == {"origin", "dx", "bounds", "backend"}
+    sdf, meta = sdfgen_b200.generate_from_mesh(v, t, nx=8, ny=8, nz=8, padding=1)
+    assert seen["dims"] == (10, 10, 10) and abs(seen["dx"] - 0.25) < 1e-7

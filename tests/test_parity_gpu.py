@@ -1,0 +1,154 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI of
+include/sdfb.h, against (a) golden outputs of the compiled reference, (b) the oracle run live on the
+same seeded inputs, (c) size-independent properties at full size.
+
+Bar (BASELINE.json north_star): crossing counts and signs bit-exact; exact-band phi within 1 ulp with
+bit-exact closest_tri (we assert 0 ulp); swept phi within 1e-5*dx with closest_tri divergences
+reported (we assert bit-exact phi and identical closest_tri: the schedules reproduce the serial
+Gauss-Seidel order)."""
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+import sdfgen_b200
+from cases import FIELDS, load_golden
+from sdfgen_b200 import _lib, meshes
+
+pytestmark = pytest.mark.gpu
+
+SCHEDULES = [("columns", 0), ("levels", _lib.SWEEP_LEVELS)]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _same(a, b):
+    return np.array_equal(_bits(a), _bits(b))
+
+
+def _staged_gpu(c, flags=0, band=None):
+    """Every staged output of the CUDA path for case c via the plan API."""
+    band = c.get("band", 1) if band is None else band
+    p = _lib.Plan(c["ni"], c["nj"], c["nk"], flags=flags)
+    try:
+        p.set_mesh_host(c["vertices"], c["triangles"])
+        p.band(c["origin"], c["dx"], band)
+        phi_band, tri_band, counts = p.download(phi=True, tri=True, counts=True)
+        phi_band = phi_band.copy()
+        p.sweep(0, 16)
+        phi_swept, tri_final, _ = p.download(phi=True, tri=True)
+        phi_swept = phi_swept.copy()
+        p.sign()
+        phi, _, _ = p.download(phi=True)
+        return dict(phi=phi, phi_band=phi_band, tri_band=tri_band, counts=counts, phi_swept=phi_swept, tri_final=tri_final)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("sched,flags", SCHEDULES)
+def test_golden_small_cases_bit_exact(golden_dir, sched, flags):
+    assert sdfgen_b200.is_gpu_available()
+    for c in load_golden(golden_dir):
+        g = _staged_gpu(c, flags)
+        for f in FIELDS:
+            assert _same(g[f], c["ref"][f]), (sched, c["name"], f, int((_bits(g[f]) != _bits(c["ref"][f])).sum()))
+
+
+def test_one_shot_abi_matches_golden(golden_dir):
+    for c in load_golden(golden_dir):
+        phi, tri, cnt = sdfgen_b200.generate_sdf_debug(c["vertices"], c["triangles"], c["origin"], c["dx"],
+                                                       c["ni"], c["nj"], c["nk"], c["band"])
+        assert _same(phi, c["ref"]["phi"]) and _same(tri, c["ref"]["tri_final"]) and _same(cnt, c["ref"]["counts"]), c["name"]
+        # public API: (nx,ny,nz) C-order == transpose of the i-fastest grid (python/sdfgen_py.cpp:80-86)
+        sdf = sdfgen_b200.generate_sdf(c["vertices"], c["triangles"], tuple(c["origin"]), c["dx"], c["ni"], c["nj"], c["nk"],
+                                       exact_band=c["band"])
+        assert sdf.shape == (c["ni"], c["nj"], c["nk"]) and sdf.dtype == np.float32 and sdf.flags.c_contiguous
+        assert _same(sdf, c["ref"]["phi"].reshape(c["nk"], c["nj"], c["ni"]).transpose(2, 1, 0))
+
+
+def test_reference_testmesh_known_answer_sha256(golden_dir):
+    """BASELINE configs[0]: the reference's own test mesh at 64x85x105; the .sdf the reference CLI writes
+    has sha256 d93ee4ce...."""
+    z = np.load(os.path.join(golden_dir, "c0_testmesh.npz"))
+    ni, nj, nk = (int(x) for x in z["dims"])
+    sdf = sdfgen_b200.generate_sdf(z["vertices"], z["triangles"], tuple(z["origin"]), float(z["dx"]), ni, nj, nk)
+    o = z["origin"].astype(np.float32)
+    hdr = struct.pack("<3i", ni, nj, nk) + o.tobytes()
+    hdr += (o + np.array([ni, nj, nk], np.float32) * np.float32(z["dx"])).astype(np.float32).tobytes()
+    assert hashlib.sha256(hdr + sdf.tobytes()).hexdigest() == "d93ee4cedca50cd0f280adea355210ef95c5954d9732a01d5286fd393261dc23"
+    assert int((sdf < 0).sum()) == 286481
+    phi, tri, cnt = sdfgen_b200.generate_sdf_debug(z["vertices"], z["triangles"], z["origin"], float(z["dx"]), ni, nj, nk)
+    assert _same(tri, z["tri_final"])
+    nzi = np.flatnonzero(cnt)
+    assert np.array_equal(nzi, z["counts_nonzero_idx"]) and np.array_equal(cnt[nzi], z["counts_nonzero_val"])
+
+
+@pytest.mark.parametrize("name,n,shuffle", [("c1_blob_256", 64, True), ("c2_icosphere_512", 48, True),
+                                             ("c1_blob_256", 96, False), ("c3_torus_1024", 56, False)])
+def test_live_oracle_downscaled_twins(name, n, shuffle):
+    """Same meshes as the BASELINE configs on down-scaled grids the CPU oracle finishes in seconds."""
+    w = meshes.workload(name, n=n, shuffle=shuffle)
+    c = dict(w, band=1)
+    chk = oracle.best()
+    r = chk.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+    for sched, flags in SCHEDULES:
+        g = _staged_gpu(c, flags)
+        for f in FIELDS:
+            nbad = int((_bits(g[f]) != _bits(getattr(r, f))).sum())
+            assert nbad == 0, (name, n, sched, f, nbad)
+
+
+def test_per_sweep_equality_with_oracle():
+    """Compare after EACH of the 16 sweeps, so a schedule bug cannot hide behind later sweeps."""
+    w = meshes.workload("c1_blob_256", n=40, shuffle=True)
+    args = (w["vertices"], w["triangles"], w["origin"], w["dx"], 40, 40, 40)
+    for sched, flags in SCHEDULES:
+        p = _lib.Plan(40, 40, 40, flags=flags)
+        p.set_mesh_host(w["vertices"], w["triangles"])
+        p.band(w["origin"], w["dx"], 1)
+        for s in range(16):
+            p.sweep(s, 1)
+            phi, tri, _ = p.download(phi=True, tri=True)
+            r = oracle.port.staged(*args, nsweeps=s + 1)
+            assert _same(phi, r.phi_swept) and _same(tri, r.tri_final), (sched, s)
+        p.close()
+
+
+def test_edge_shapes_and_reuse():
+    """Plan reuse across meshes/origins, exact_band 0, thin grids; each against the live oracle."""
+    v, t = meshes.icosphere(2, 0.3)
+    for dims, band in [((17, 9, 33), 1), ((33, 2, 5), 1), ((5, 40, 3), 2), ((8, 8, 8), 0)]:
+        ni, nj, nk = dims
+        o = np.array([-0.45, -0.4, -0.5], np.float32)
+        dx = 1.0 / max(dims)
+        r = oracle.port.staged(v, t, o, dx, ni, nj, nk, band)
+        for sched, flags in SCHEDULES:
+            p = _lib.Plan(ni, nj, nk, flags=flags)
+            for rep in range(2):            # second run on the same plan must give the same answer
+                p.set_mesh_host(v, t)
+                p.run(o, dx, band)
+                phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
+                assert _same(phi, r.phi) and _same(tri, r.tri_final) and _same(cnt, r.counts), (dims, band, sched, rep)
+            p.close()
+
+
+def test_slab_plans_band_and_sign_match_full_grid():
+    """Phases A and C are local in k: slab plans reproduce the matching window of the full grid."""
+    w = meshes.workload("c1_blob_256", n=48)
+    r = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], 48, 48, 48, nsweeps=0)
+    for k_lo, k_hi in [(0, 12), (12, 37), (37, 48)]:
+        p = _lib.Plan(48, 48, 48, k_lo=k_lo, k_hi=k_hi)
+        p.set_mesh_host(w["vertices"], w["triangles"])
+        p.band(w["origin"], w["dx"], 1)
+        phi_b, tri_b, cnt = p.download(phi=True, tri=True, counts=True)
+        sl = slice(k_lo * 48 * 48, k_hi * 48 * 48)
+        assert _same(phi_b, r.phi_band[sl]) and _same(tri_b, r.tri_band[sl]) and _same(cnt, r.counts[sl])
+        p.sign()
+        phi, _, _ = p.download(phi=True)
+        assert _same(phi, r.phi[sl])          # nsweeps=0 -> signed band-only phi
+        p.close()
