@@ -66,8 +66,8 @@ class _Port:
 
     def lib(self):
         if self._lib is None:
-            if not os.path.exists(_PORT_SO) or os.path.getmtime(_PORT_SO) < os.path.getmtime(
-                    os.path.join(_HERE, "sdf_oracle.c")):
+            srcs = [os.path.join(_HERE, f) for f in ("sdf_oracle.c", "columns_emu.c")]
+            if not os.path.exists(_PORT_SO) or os.path.getmtime(_PORT_SO) < max(os.path.getmtime(f) for f in srcs):
                 build()
             L = C.CDLL(_PORT_SO)
             L.sdfo_make_level_set3.restype = C.c_int
@@ -80,8 +80,35 @@ class _Port:
                                                 _f32p, np.ctypeslib.ndpointer(np.int32), np.ctypeslib.ndpointer(np.int32)]
             L.sdfo_point_triangle_distance.restype = C.c_float
             L.sdfo_point_triangle_distance.argtypes = [_f32p, _f32p, _f32p, _f32p]
+            L.sdfo_emu_sweep_columns.restype = C.c_long
+            L.sdfo_emu_sweep_columns.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
+            L.sdfo_emu_flag_violations.restype = C.c_long
             self._lib = L
         return self._lib
+
+    def emu_sweep_columns(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16,
+                          k_lo=0, k_hi=None):
+        """CPU emulation of the CUDA column schedule (oracle/columns_emu.c) starting from band results.
+        Returns (phi_swept, tri_final, evals_per_sweep, changed_per_sweep, flag_violations)."""
+        v, t, o = _prep(vertices, triangles, origin)
+        k_hi = nk if k_hi is None else k_hi
+        plane = ni * nj
+        nkl = k_hi - k_lo
+        init = np.float32(np.float32(ni + nj + nk) * np.float32(dx))
+        cphi = np.full(plane * (nkl + 2), init, np.float32)
+        clo = np.full(plane * (nkl + 2), 0xFFFFFFFF, np.uint32)
+        cphi[plane:plane * (nkl + 1)] = phi_band
+        tb = np.asarray(tri_band)
+        clo[plane:plane * (nkl + 1)] = np.where(tb < 0, np.uint32(0xFFFFFFFF), tb.astype(np.uint32))
+        evals, changed = [], []
+        for s in range(nsweeps):
+            ch = C.c_long()
+            e = self.lib().sdfo_emu_sweep_columns(t, v, cphi, clo, o, dx, ni, nj, nk, k_lo, k_hi, s, C.byref(ch))
+            evals.append(int(e)); changed.append(int(ch.value))
+        lo = clo[plane:plane * (nkl + 1)]
+        tri = np.where((lo & 0x07FFFFFF) == 0x07FFFFFF, -1, (lo & 0x07FFFFFF).astype(np.int64)).astype(np.int32)
+        return cphi[plane:plane * (nkl + 1)].copy(), tri, evals, changed, int(self.lib().sdfo_emu_flag_violations())
 
     def make_level_set3(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1):
         """Signed phi only (flat, i fastest)."""

@@ -72,6 +72,7 @@ struct sdfb_plan {
     unsigned long long *changed = nullptr;
     uint32_t *progress = nullptr;    // column-schedule flags
     size_t progress_words = 0;
+    uint32_t epoch = 0;              // column-schedule launch counter since the flags were last zeroed
     // mesh
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
@@ -235,6 +236,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     g_launches += launch_init(p->cells, p->g.cell_count(), p->init_phi, st);
     CU(cudaMemsetAsync(p->counts, 0, (size_t)p->g.slab_voxels() * sizeof(int32_t), st));
     CU(cudaMemsetAsync(p->changed, 0, sizeof(unsigned long long), st));
+    if (p->progress) { CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st)); p->epoch = 0; }
     g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
@@ -250,10 +252,15 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     for (int s = first; s < first + count; ++s) {
-        if (p->flags & SDFB_SWEEP_LEVELS)
+        if (p->flags & SDFB_SWEEP_LEVELS) {
             g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
-        else
-            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, st);
+        } else {
+            if (p->epoch >= 65000u) {   // progress words are epoch<<16 | steps: start over before it wraps
+                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
+                p->epoch = 0;
+            }
+            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
+        }
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[2], st));

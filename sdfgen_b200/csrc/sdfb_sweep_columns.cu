@@ -1,11 +1,329 @@
-// sdfb_sweep_columns.cu -- placeholder until the pipelined column schedule lands: routes to the
-// per-level schedule so the ABI is complete.
+// sdfb_sweep_columns.cu -- the production sweep schedule: pipelined columns.
+//
+// One launch per sweep direction.  In sweep-relative coordinates (ri,rj,rk >= 0, counted from the
+// corner the sweep starts at) the (rj,rk) plane is cut into columns of EJ x EK rows.  A CTA owns one
+// column at a time and marches along i: lane (a,b) of the column handles voxel ri = s - a - b - 2 at step
+// s, so lanes are skewed along the anti-diagonal and every one of the seven upstream neighbours
+// (cpu_lib/makelevelset3.cpp:143-149) was produced 1..3 steps earlier by lane (a-1|a, b-1|b):
+//
+//      m  neighbour (rel.)        produced by lane   at step
+//      0  (ri-1, rj,   rk  )      (a,   b  )         s-1   (register)
+//      1  (ri,   rj-1, rk  )      (a-1, b  )         s-1
+//      2  (ri-1, rj-1, rk  )      (a-1, b  )         s-2
+//      3  (ri,   rj,   rk-1)      (a,   b-1)         s-1
+//      4  (ri-1, rj,   rk-1)      (a,   b-1)         s-2
+//      5  (ri,   rj-1, rk-1)      (a-1, b-1)         s-2
+//      6  (ri-1, rj-1, rk-1)      (a-1, b-1)         s-3
+//
+// The lanes exchange the 32-bit {stamp|closest_tri} words through a 4-deep ring in shared memory,
+// one __syncthreads per step.  Lanes a=-1 / b=-1 are "halo lanes": two extra warps that, instead of
+// computing, load the word of their voxel from global memory -- it belongs to the column to the left
+// (J-1), below (K-1) or diagonal, or to the read-only ri/rj/rk = 0 faces (or a slab halo plane).
+// Columns are handed out by an atomic ticket in anti-diagonal order (J+K), so a column's producers
+// always hold lower tickets and are running or finished: the spin on their progress counters cannot
+// deadlock.  A column publishes its step count every PUBLISH steps (__syncthreads, __threadfence,
+// store); a consumer column may run step s once left >= s+EJ+2+... (see need_left/need_down).
+// Every dependency of the serial Gauss-Seidel order is respected, so the result is bit-identical to
+// the reference's single-threaded sweep.
+//
+// Work per voxel is data dependent (0..7 distance evaluations), so evaluation is decoupled from
+// ownership: each lane filters its candidates (drop "no triangle", the voxel's own triangle,
+// duplicates, and -- the stamp memo -- neighbours whose triangle has not changed since the last sweep
+// in which this voxel looked at the same offset: a candidate that lost once can never win later
+// because phi only decreases), pushes the survivors to a per-warp queue in shared memory, the 32
+// lanes evaluate the queue round-robin, and each owner then replays its own results in the
+// reference's order with the reference's strict "<".
 #include "sdfb_kernels.cuh"
+#include "sdfb_sweep_common.cuh"
+
 namespace sdfb {
-size_t sweep_columns_progress_words(const Grid &) { return 0; }
-int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                         unsigned long long *changed, uint32_t *, cudaStream_t st)
+
+namespace {
+
+constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
+constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
+constexpr int NTHREADS = NCOMPUTE + 64;      // + 2 halo warps
+constexpr int PUBLISH = 8;                   // steps between progress publications
+constexpr int RING = 4;
+constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
+constexpr int QCAP = 7 * 32;                 // queue entries per warp
+
+struct ColParams {
+    Grid g;
+    SweepDir sd;
+    int rk_first, rk_last;                   // relative k range updated by this launch (inclusive)
+    int NJ, NK;                              // columns in j and k
+    int steps;                               // steps per column = ni + EJ + EK
+    uint32_t stamp;                          // sweep_index + 1
+    uint32_t epoch;                          // progress values are epoch<<16 | steps_done
+    uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
-    return launch_sweep_levels(cells, rec, g, sweep_index, changed, st);
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
+
+// ring slot layout: [RING][EK+1][EJ+1], index (b+1)*(EJ+1) + (a+1); a fastest
+__device__ __forceinline__ int ring_idx(int slot, int a, int b) { return slot * ((EK + 1) * (EJ + 1)) + (b + 1) * (EJ + 1) + (a + 1); }
+
+__global__ void __launch_bounds__(NTHREADS, 3)
+k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
+                uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
+                unsigned long long *__restrict__ changed)
+{
+    __shared__ uint32_t ring[RING * (EK + 1) * (EJ + 1)];
+    __shared__ uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
+    __shared__ float q_d[NCOMPUTE / 32][QCAP];
+    __shared__ int col_s;
+
+    const Grid &g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_compute = tid < NCOMPUTE;
+    const int ncols = P.NJ * P.NK;
+    unsigned my_changed = 0;
+
+    // strides of the relative axes in the cell array
+    const int64_t si = (int64_t)P.sd.di, sj = (int64_t)P.sd.dj * g.ni, sk = (int64_t)P.sd.dk * g.plane();
+
+    for (;;) {
+        // ---- take the next column (anti-diagonal order) --------------------------------------
+        if (tid == 0) {
+            int t = (int)atomicAdd(ticket, 1u);
+            col_s = t;
+        }
+        __syncthreads();
+        const int tk = col_s;
+        if (tk >= ncols) break;
+        int J, K;
+        {
+            int d = 0, rem = tk;
+            for (;;) {
+                int lo = max(0, d - (P.NK - 1)), hi = min(d, P.NJ - 1);
+                int cnt = hi - lo + 1;
+                if (rem < cnt) { J = lo + rem; K = d - J; break; }
+                rem -= cnt; ++d;
+            }
+        }
+        const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
+        const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
+        const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
+        uint32_t *prog_mine = &progress[K * P.NJ + J];
+        const uint32_t ebase = P.epoch << 16;
+
+        // ---- lane identity ---------------------------------------------------------------------
+        int a, b;                      // lane coordinates in the column; halo lanes have a=-1 or b=-1
+        if (is_compute) { a = tid % EJ; b = tid / EJ; }
+        else {
+            int h = tid - NCOMPUTE;    // 0..63
+            if (h <= EK) { a = -1; b = h - 1; }            // (-1,-1), (-1,0) .. (-1,EK-1)
+            else if (h <= EK + EJ) { a = h - EK - 1; b = -1; }   // (0,-1) .. (EJ-1,-1)
+            else { a = -2; b = -2; }                        // idle
+        }
+        const int rj = rj0 + a, rk = rk0 + b;
+        const bool row_ok = (a > -2) && rj <= g.nj - 1 && rk <= P.rk_last;   // rj,rk >= 0 by construction
+        // cell index of (ri=0, rj, rk)
+        int64_t c_row = 0;
+        float gy = 0.f, gz = 0.f;
+        bool interior_row = false;
+        if (row_ok) {
+            int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
+            c_row = g.cidx(P.sd.abs_i(0, g), j, k);
+            gy = lattice(j, g.dx, g.oy); gz = lattice(k, g.dx, g.oz);
+            interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
+        }
+
+        // software pipeline registers
+        uint64_t own_next = 0;         // compute: own cell for step s (prefetched at s-1)
+        uint32_t halo_next = TRI_NONE; // halo: word for virtual step s (prefetched at s-1)
+        uint32_t prev_lo = TRI_NONE;   // compute: own result of step s-1
+        {
+            int ri0 = 0 - a - b - SHIFT;       // voxel of step 0
+            if (is_compute) { if (row_ok && ri0 >= 0 && ri0 <= g.ni - 1) own_next = cells[c_row + si * ri0]; }
+        }
+        // halo lanes start their pipeline inside the loop (after the first progress check)
+
+        for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
+            const int s1 = min(s0 + PUBLISH, P.steps);
+            // ---- wait until the producer columns are far enough for this chunk ----------------
+            // Halo lane (-1,b) loads at step s the word for virtual step s+1, produced by column
+            // (J-1,K) lane (EJ-1,b) at its step s+1+EJ  =>  needs steps_done >= s+EJ+2; same with EK
+            // (the SHIFT cancels: both columns use the same lane->voxel map).
+            if (tid == NCOMPUTE) {
+                if (prog_left) {
+                    uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 2);
+                    while (ld_acquire(prog_left) < need) __nanosleep(64);
+                }
+                if (prog_down) {
+                    uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 2);
+                    while (ld_acquire(prog_down) < need) __nanosleep(64);
+                }
+            }
+            __syncthreads();
+            if (!is_compute && s0 == 0 && row_ok) {
+                int ri0 = 0 - a - b - SHIFT;               // virtual step 0
+                halo_next = (ri0 >= 0 && ri0 <= g.ni - 1) ? cell_lo(__ldcg(&cells[c_row + si * ri0])) : TRI_NONE;
+            }
+
+            for (int s = s0; s < s1; ++s) {
+                const int ri = s - a - b - SHIFT;
+                const int slot = s & (RING - 1);
+                if (!is_compute) {
+                    // ---- halo lanes: publish the word loaded one step ago, prefetch the next ------
+                    if (row_ok) {
+                        ring[ring_idx(slot, a, b)] = halo_next;
+                        int rin = ri + 1;
+                        halo_next = (rin >= 0 && rin <= g.ni - 1 && s + 1 < P.steps) ? cell_lo(__ldcg(&cells[c_row + si * rin])) : TRI_NONE;
+                    }
+                } else {
+                    // ---- compute lanes -------------------------------------------------------------
+                    const bool in_row = row_ok && ri >= 0 && ri <= g.ni - 1;
+                    const uint64_t self = own_next;
+                    {   // prefetch own cell of the next step
+                        int rin = ri + 1;
+                        if (row_ok && rin >= 0 && rin <= g.ni - 1) own_next = cells[c_row + si * rin];
+                    }
+                    uint32_t cur = cell_lo(self);
+                    float phi = cell_phi(self);
+                    int ncand = 0;
+                    uint32_t cand[7];
+                    const bool update = in_row && ri >= 1;
+                    if (update) {
+                        const int s1r = (s + RING - 1) & (RING - 1), s2r = (s + RING - 2) & (RING - 1), s3r = (s + RING - 3) & (RING - 1);
+                        uint32_t nb[7];
+                        nb[0] = prev_lo;
+                        nb[1] = ring[ring_idx(s1r, a - 1, b)];
+                        nb[2] = ring[ring_idx(s2r, a - 1, b)];
+                        nb[3] = ring[ring_idx(s1r, a, b - 1)];
+                        nb[4] = ring[ring_idx(s2r, a, b - 1)];
+                        nb[5] = ring[ring_idx(s2r, a - 1, b - 1)];
+                        nb[6] = ring[ring_idx(s3r, a - 1, b - 1)];
+                        const int i = P.sd.abs_i(ri, g);
+                        const bool memo_ok = interior_row && i >= 1 && i <= g.ni - 2;
+                        const uint32_t cur_tri = lo_tri(cur);
+                        #pragma unroll
+                        for (int m = 0; m < 7; ++m) {
+                            const uint32_t t = lo_tri(nb[m]);
+                            bool keep = (t != TRI_NONE) && (t != cur_tri);
+                            if (keep && memo_ok && P.last[m] != 0 && lo_stamp(nb[m]) <= (uint32_t)P.last[m]) keep = false;
+                            #pragma unroll
+                            for (int u = 0; u < m; ++u) keep = keep && (lo_tri(nb[u]) != t || false);
+                            cand[m] = keep ? t : TRI_NONE;
+                            ncand += keep ? 1 : 0;
+                        }
+                    }
+                    // ---- warp queue: exclusive scan of candidate counts --------------------------
+                    int incl = ncand;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total > 0) {
+                        int off = incl - ncand;
+                        if (update) {
+                            int w = off;
+                            #pragma unroll
+                            for (int m = 0; m < 7; ++m) if (cand[m] != TRI_NONE) { q_ent[warp][w] = ((uint32_t)lane << 27) | cand[m]; ++w; }
+                        }
+                        __syncwarp();
+                        for (int q = lane; q < total; q += 32) {
+                            const uint32_t e = q_ent[warp][q];
+                            const int ol = (int)(e >> 27);                   // owner lane
+                            const int otid = warp * 32 + ol;
+                            const int oa = otid % EJ, ob = otid / EJ;
+                            const int ori = s - oa - ob - SHIFT;
+                            const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
+                            F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+                            const TriRec *tr = &rec[e & TRI_MASK];
+                            const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+                            q_d[warp][q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+                        }
+                        __syncwarp();
+                        if (ncand > 0) {
+                            uint32_t best = TRI_NONE;
+                            for (int q = off; q < off + ncand; ++q) {
+                                const float d = q_d[warp][q];
+                                if (d < phi) { phi = d; best = q_ent[warp][q] & TRI_MASK; }
+                            }
+                            if (best != TRI_NONE) {
+                                cur = (P.stamp << 27) | best;
+                                cells[c_row + si * ri] = pack_cell(phi, cur);
+                                ++my_changed;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (in_row) { ring[ring_idx(slot, a, b)] = cur; prev_lo = cur; }
+                }
+                __syncthreads();
+            }
+            // ---- publish progress ------------------------------------------------------------------
+            if (tid == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)s1;
+            }
+        }
+        (void)gy; (void)gz; (void)sj; (void)sk;
+    }
+
+    // ---- teardown: count changes; the last CTA out resets the ticket for the next launch ----------
+    unsigned wsum = my_changed;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+    if (lane == 0 && wsum) atomicAdd(changed, (unsigned long long)wsum);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned done = atomicAdd(ticket + 1, 1u);
+        if (done == gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; __threadfence(); }
+    }
+}
+
+}  // namespace
+
+// progress: [2] ticket words + [1] epoch counter slot (host side keeps the epoch) + NJ*NK flags
+size_t sweep_columns_progress_words(const Grid &g)
+{
+    size_t NJ = (size_t)(g.nj + EJ - 1) / EJ + 1, NK = (size_t)(g.nkl() + EK - 1) / EK + 1;
+    return 4 + NJ * NK;
+}
+
+int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
+                         unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st)
+{
+    ColParams P{};
+    P.g = g;
+    P.sd = SweepDir::of(sweep_index);
+    int rk_lo, rk_hi;
+    if (!P.sd.owned_rk_range(g, rk_lo, rk_hi)) return 0;
+    if (g.ni < 2 || g.nj < 2) return 0;
+    P.rk_first = rk_lo; P.rk_last = rk_hi;
+    P.NJ = (g.nj - 1 + EJ - 1) / EJ;
+    P.NK = (rk_hi - rk_lo + 1 + EK - 1) / EK;
+    P.steps = g.ni + EJ + EK - 2 + SHIFT;
+    P.stamp = (uint32_t)min(sweep_index + 1, 31);
+    // the epoch grows with every launch on a plan between resets of the progress array (host side)
+    P.epoch = epoch;
+    for (int m = 0; m < 7; ++m) {
+        P.last[m] = 0;
+        if (sweep_index + 1 > 31) continue;           // stamps saturate: no memo beyond 31 sweeps
+        const bool ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
+        for (int e = sweep_index - 1; e >= 0; --e) {
+            SweepDir d = SweepDir::of(e);
+            if ((!ci || d.di == P.sd.di) && (!cj || d.dj == P.sd.dj) && (!ck || d.dk == P.sd.dk)) { P.last[m] = (uint8_t)(e + 1); break; }
+        }
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_columns, NTHREADS, 0);
+    if (occ < 1) occ = 1;
+    int grid = sms * occ;
+    int ncols = P.NJ * P.NK;
+    if (grid > ncols) grid = ncols;
+    k_sweep_columns<<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
+    return 1;
+}
+
 }  // namespace sdfb
