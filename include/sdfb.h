@@ -112,6 +112,9 @@ int sdfb_plan_device_ptrs(sdfb_plan *plan, void **cells, void **counts, void **p
 /* Number of cells whose closest triangle changed during the sweeps since the last sdfb_plan_band or
  * sdfb_plan_changed call (synchronises the stream; used by the multi-GPU fixed-point loop). */
 int sdfb_plan_changed(sdfb_plan *plan, void *stream, uint64_t *changed);
+/* Same, plus out[1] = point_triangle_distance evaluations done by the sweeps (column schedule only);
+ * out[0] = changed cells.  Both counters are reset. */
+int sdfb_plan_counters(sdfb_plan *plan, void *stream, uint64_t out[2]);
 
 /* Blocking copies of the slab results to host memory (any may be NULL).  phi is the output of
  * sdfb_plan_sign (or the unsigned cell phi if the sign pass has not run). */

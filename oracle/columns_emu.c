@@ -21,8 +21,8 @@ float sdfo_point_triangle_distance(const float *x0, const float *x1, const float
 #define EK 16
 #define NCOMPUTE (EJ*EK)
 #define NLANES (NCOMPUTE + 64)
-#define PUBLISH 8
-#define RING 4
+#define PUBLISH 4
+#define RING 2
 #define SHIFT 2
 #define TRI_MASK 0x07ffffffu
 #define TRI_NONE 0x07ffffffu
@@ -91,7 +91,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
         int A[NLANES], B[NLANES], row_ok[NLANES], interior_row[NLANES];
         int64_t c_row[NLANES];
         uint64_t own_next_phi_lo[NLANES];   /* packed like the device: phi bits << 32 | lo */
-        uint32_t halo_next[NLANES], prev_lo[NLANES];
+        uint32_t halo_next[NLANES], prev_lo[NLANES], r1_old[NLANES], r3_old[NLANES], r5_old[NLANES], r5_old2[NLANES];
         for (int tid = 0; tid < NLANES; ++tid) {
             int a, b;
             if (tid < NCOMPUTE) { a = tid % EJ; b = tid / EJ; }
@@ -106,6 +106,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                 interior_row[tid] = (j >= 1 && j <= nj - 2 && k >= 1 && k <= nk - 2);
             }
             own_next_phi_lo[tid] = 0; halo_next[tid] = TRI_NONE; prev_lo[tid] = TRI_NONE;
+            r1_old[tid] = r3_old[tid] = r5_old[tid] = r5_old2[tid] = TRI_NONE;
             int ri0 = 0 - a - b - SHIFT;
             if (tid < NCOMPUTE && row_ok[tid] && ri0 >= 0 && ri0 <= ni - 1) {
                 int64_t c = c_row[tid] + si * ri0; uint32_t pb; memcpy(&pb, &cells_phi[c], 4);
@@ -121,7 +122,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                 halo_next[tid] = (ri0 >= 0 && ri0 <= ni - 1) ? cells_lo[c_row[tid] + si * ri0] : TRI_NONE;
             }
             for (int s = s0; s < s1; ++s) {
-                const int slot = s & (RING - 1);
+                const int slot = s & 1, pslot = slot ^ 1;
                 /* halo lanes */
                 for (int tid = NCOMPUTE; tid < NLANES; ++tid) if (row_ok[tid]) {
                     int a = A[tid], b = B[tid], ri = s - a - b - SHIFT;
@@ -155,29 +156,28 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                     uint64_t self = own_next_phi_lo[tid];
                     { int rin = ri + 1; if (row_ok[tid] && rin >= 0 && rin <= ni - 1) { int64_t c = c_row[tid] + si * rin; uint32_t pb; memcpy(&pb, &cells_phi[c], 4); own_next_phi_lo[tid] = ((uint64_t)pb << 32) | cells_lo[c]; } }
                     uint32_t cur = (uint32_t)self; uint32_t pb = (uint32_t)(self >> 32); float phi; memcpy(&phi, &pb, 4);
+                    uint32_t r1 = TRI_NONE, r3 = TRI_NONE, r5 = TRI_NONE;
+                    if (row_ok[tid] && ri >= -1 && ri <= ni - 1) {
+                        r1 = ring[ring_idx(pslot, a - 1, b)];
+                        r3 = ring[ring_idx(pslot, a, b - 1)];
+                        r5 = ring[ring_idx(pslot, a - 1, b - 1)];
+                    }
                     int n = 0; int update = in_row && ri >= 1;
                     if (update) {
-                        int s1r = (s + RING - 1) & (RING - 1), s2r = (s + RING - 2) & (RING - 1), s3r = (s + RING - 3) & (RING - 1);
-                        uint32_t nb[7];
-                        nb[0] = prev_lo[tid];
-                        nb[1] = ring[ring_idx(s1r, a - 1, b)];
-                        nb[2] = ring[ring_idx(s2r, a - 1, b)];
-                        nb[3] = ring[ring_idx(s1r, a, b - 1)];
-                        nb[4] = ring[ring_idx(s2r, a, b - 1)];
-                        nb[5] = ring[ring_idx(s2r, a - 1, b - 1)];
-                        nb[6] = ring[ring_idx(s3r, a - 1, b - 1)];
+                        uint32_t nb[7] = { prev_lo[tid], r1, r1_old[tid], r3, r3_old[tid], r5_old[tid], r5_old2[tid] };
                         int i = ABS_I(ri);
-                        int memo_ok = interior_row[tid] && i >= 1 && i <= ni - 2;
+                        int i_interior = (i >= 1 && i <= ni - 2);
                         uint32_t cur_tri = cur & TRI_MASK;
                         for (int m = 0; m < 7; ++m) {
                             uint32_t t = nb[m] & TRI_MASK;
-                            int keep = (t != TRI_NONE) && (t != cur_tri);
-                            if (keep && memo_ok && last[m] != 0 && (nb[m] >> 27) <= (uint32_t)last[m]) keep = 0;
+                            uint32_t fresh_min = (interior_row[tid] && last[m] != 0) ? (uint32_t)last[m] + 1u : 0u;
+                            int keep = (t != TRI_NONE) && (t != cur_tri) && (!i_interior || (nb[m] >> 27) >= fresh_min);
                             for (int u = 0; u < m; ++u) keep = keep && ((nb[u] & TRI_MASK) != t);
                             cand[tid][m] = keep ? t : TRI_NONE;
                             n += keep ? 1 : 0;
                         }
                     }
+                    r1_old[tid] = r1; r3_old[tid] = r3; r5_old2[tid] = r5_old[tid]; r5_old[tid] = r5;
                     ncand[tid] = n; upd[tid] = update; in_row_v[tid] = in_row; cur_v[tid] = cur; phi_v[tid] = phi;
                 }
                 /* phase 2..4 per warp */

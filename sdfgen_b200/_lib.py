@@ -59,6 +59,8 @@ def lib():
     L.sdfb_plan_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.sdfb_plan_changed.restype = C.c_int
     L.sdfb_plan_changed.argtypes = [vp, vp, C.POINTER(u64)]
+    L.sdfb_plan_counters.restype = C.c_int
+    L.sdfb_plan_counters.argtypes = [vp, vp, C.POINTER(u64 * 2)]
     L.sdfb_plan_download.restype = C.c_int
     L.sdfb_plan_download.argtypes = [vp, vp, vp, vp, vp]
     L.sdfb_plan_phase_ms.restype = C.c_int
@@ -151,6 +153,12 @@ class Plan:
         n = C.c_uint64()
         check(lib().sdfb_plan_changed(self._h, stream or None, C.byref(n)))
         return int(n.value)
+
+    def counters(self, stream=0):
+        """(changed cells, distance evaluations) of the sweeps since the last band/counters call."""
+        out = (C.c_uint64 * 2)()
+        check(lib().sdfb_plan_counters(self._h, stream or None, C.byref(out)))
+        return int(out[0]), int(out[1])
 
     def download(self, phi=True, tri=False, counts=False, stream=0, phi_out=None):
         """Blocking copy to host.  Returns (phi, tri, counts) flat arrays (None where not requested).

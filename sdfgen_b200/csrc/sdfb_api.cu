@@ -164,7 +164,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
         (e = cudaMalloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMalloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
         ((flags & SDFB_OUT_KFASTEST) && (e = cudaMalloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||
-        (e = cudaMalloc(&p->changed, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&p->changed, 2 * sizeof(unsigned long long))) != cudaSuccess) {
         sdfb_plan_destroy(p);
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
@@ -178,7 +178,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     for (auto &ev : p->ev) {
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { sdfb_plan_destroy(p); return fail(SDFB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
     }
-    cudaMemset(p->changed, 0, sizeof(unsigned long long));
+    cudaMemset(p->changed, 0, 2 * sizeof(unsigned long long));
     *out = p;
     return SDFB_OK;
 }
@@ -235,7 +235,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     CU(cudaEventRecord(p->ev[0], st));
     g_launches += launch_init(p->cells, p->g.cell_count(), p->init_phi, st);
     CU(cudaMemsetAsync(p->counts, 0, (size_t)p->g.slab_voxels() * sizeof(int32_t), st));
-    CU(cudaMemsetAsync(p->changed, 0, sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(p->changed, 0, 2 * sizeof(unsigned long long), st));
     if (p->progress) { CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st)); p->epoch = 0; }
     g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
     CU(cudaGetLastError());
@@ -301,17 +301,26 @@ int sdfb_plan_device_ptrs(sdfb_plan *p, void **cells, void **counts, void **phi)
     return SDFB_OK;
 }
 
-int sdfb_plan_changed(sdfb_plan *p, void *stream, uint64_t *changed)
+int sdfb_plan_counters(sdfb_plan *p, void *stream, uint64_t out[2])
 {
-    if (!p || !changed) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p || !out) return fail(SDFB_ERR_INVALID, "null argument");
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long h = 0;
-    CU(cudaMemcpyAsync(&h, p->changed, sizeof(h), cudaMemcpyDeviceToHost, st));
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, p->changed, sizeof(h), cudaMemcpyDeviceToHost, st));
     CU(cudaMemsetAsync(p->changed, 0, sizeof(h), st));
     CU(cudaStreamSynchronize(st));
-    *changed = h;
+    out[0] = h[0]; out[1] = h[1];
     return SDFB_OK;
+}
+
+int sdfb_plan_changed(sdfb_plan *p, void *stream, uint64_t *changed)
+{
+    if (!changed) return fail(SDFB_ERR_INVALID, "null argument");
+    uint64_t c[2];
+    int rc = sdfb_plan_counters(p, stream, c);
+    if (!rc) *changed = c[0];
+    return rc;
 }
 
 int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *count_out, void *stream)

@@ -15,8 +15,9 @@
 //      5  (ri,   rj-1, rk-1)      (a-1, b-1)         s-2
 //      6  (ri-1, rj-1, rk-1)      (a-1, b-1)         s-3
 //
-// The lanes exchange the 32-bit {stamp|closest_tri} words through a 4-deep ring in shared memory,
-// one __syncthreads per step.  Lanes a=-1 / b=-1 are "halo lanes": two extra warps that, instead of
+// The lanes exchange the 32-bit {stamp|closest_tri} words through a double-buffered array in shared
+// memory (three reads per step, all of step s-1; older words roll through registers), one
+// __syncthreads per step.  Lanes a=-1 / b=-1 are "halo lanes": two extra warps that, instead of
 // computing, load the word of their voxel from global memory -- it belongs to the column to the left
 // (J-1), below (K-1) or diagonal, or to the read-only ri/rj/rk = 0 faces (or a slab halo plane).
 // Columns are handed out by an atomic ticket in anti-diagonal order (J+K), so a column's producers
@@ -43,8 +44,8 @@ namespace {
 constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
 constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
 constexpr int NTHREADS = NCOMPUTE + 64;      // + 2 halo warps
-constexpr int PUBLISH = 8;                   // steps between progress publications
-constexpr int RING = 4;
+constexpr int PUBLISH = 4;                   // steps between progress publications
+constexpr int RING = 2;                      // the ring is double buffered: every read is from step s-1
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -83,10 +84,10 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_compute = tid < NCOMPUTE;
     const int ncols = P.NJ * P.NK;
-    unsigned my_changed = 0;
+    unsigned my_changed = 0, my_evals = 0;
 
     // strides of the relative axes in the cell array
-    const int64_t si = (int64_t)P.sd.di, sj = (int64_t)P.sd.dj * g.ni, sk = (int64_t)P.sd.dk * g.plane();
+    const int64_t si = (int64_t)P.sd.di;
 
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
@@ -126,23 +127,32 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
         const bool row_ok = (a > -2) && rj <= g.nj - 1 && rk <= P.rk_last;   // rj,rk >= 0 by construction
         // cell index of (ri=0, rj, rk)
         int64_t c_row = 0;
-        float gy = 0.f, gz = 0.f;
         bool interior_row = false;
         if (row_ok) {
             int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
             c_row = g.cidx(P.sd.abs_i(0, g), j, k);
-            gy = lattice(j, g.dx, g.oy); gz = lattice(k, g.dx, g.oz);
             interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
         }
 
         // software pipeline registers
         uint64_t own_next = 0;         // compute: own cell for step s (prefetched at s-1)
         uint32_t halo_next = TRI_NONE; // halo: word for virtual step s (prefetched at s-1)
-        uint32_t prev_lo = TRI_NONE;   // compute: own result of step s-1
+        uint32_t prev_lo = TRI_NONE;   // compute: own result of step s-1                 -> m=0
+        // ring words read in earlier steps, rolled through registers (see the table above):
+        //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )  m=1 now, m=2 one step later
+        //   R3(s) = lane(a,  b-1)@s-1 = (ri,   rj,   rk-1)  m=3 now, m=4 one step later
+        //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)  m=5 one step later, m=6 two steps later
+        uint32_t r1_old = TRI_NONE, r3_old = TRI_NONE, r5_old = TRI_NONE, r5_old2 = TRI_NONE;
+        const uint64_t *own_ptr = cells + c_row + si * (int64_t)(0 - a - b - SHIFT);   // cell of step 0 (may be out of range: guarded)
         {
             int ri0 = 0 - a - b - SHIFT;       // voxel of step 0
-            if (is_compute) { if (row_ok && ri0 >= 0 && ri0 <= g.ni - 1) own_next = cells[c_row + si * ri0]; }
+            if (is_compute) { if (row_ok && ri0 >= 0 && ri0 <= g.ni - 1) own_next = *own_ptr; }
         }
+        // memo thresholds: candidate m is fresh iff stamp(nb) >= fresh_min[m] (0 when never examined)
+        uint32_t fresh_min[7];
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) fresh_min[m] = (interior_row && P.last[m] != 0) ? (uint32_t)P.last[m] + 1u : 0u;
+        const uint32_t lt_mask = (1u << lane) - 1u;
         // halo lanes start their pipeline inside the loop (after the first progress check)
 
         for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
@@ -152,14 +162,17 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
             // (J-1,K) lane (EJ-1,b) at its step s+1+EJ  =>  needs steps_done >= s+EJ+2; same with EK
             // (the SHIFT cancels: both columns use the same lane->voxel map).
             if (tid == NCOMPUTE) {
+                // relaxed polls (an acquire load would invalidate this SM's L1 on every poll), one
+                // fence once the flags are seen
                 if (prog_left) {
                     uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 2);
-                    while (ld_acquire(prog_left) < need) __nanosleep(64);
+                    while (*reinterpret_cast<const volatile uint32_t *>(prog_left) < need) __nanosleep(32);
                 }
                 if (prog_down) {
                     uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 2);
-                    while (ld_acquire(prog_down) < need) __nanosleep(64);
+                    while (*reinterpret_cast<const volatile uint32_t *>(prog_down) < need) __nanosleep(32);
                 }
+                __threadfence();
             }
             __syncthreads();
             if (!is_compute && s0 == 0 && row_ok) {
@@ -169,7 +182,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
 
             for (int s = s0; s < s1; ++s) {
                 const int ri = s - a - b - SHIFT;
-                const int slot = s & (RING - 1);
+                const int slot = s & 1, pslot = slot ^ 1;
                 if (!is_compute) {
                     // ---- halo lanes: publish the word loaded one step ago, prefetch the next ------
                     if (row_ok) {
@@ -181,47 +194,43 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
                     // ---- compute lanes -------------------------------------------------------------
                     const bool in_row = row_ok && ri >= 0 && ri <= g.ni - 1;
                     const uint64_t self = own_next;
-                    {   // prefetch own cell of the next step
-                        int rin = ri + 1;
-                        if (row_ok && rin >= 0 && rin <= g.ni - 1) own_next = cells[c_row + si * rin];
-                    }
+                    own_ptr += si;
+                    if (row_ok && ri + 1 >= 0 && ri + 1 <= g.ni - 1) own_next = *own_ptr;   // prefetch the next step's cell
                     uint32_t cur = cell_lo(self);
                     float phi = cell_phi(self);
+                    // this step's ring reads (all from step s-1); meaningful from ri >= -1 on
+                    uint32_t r1 = TRI_NONE, r3 = TRI_NONE, r5 = TRI_NONE;
+                    if (row_ok && ri >= -1 && ri <= g.ni - 1) {
+                        r1 = ring[ring_idx(pslot, a - 1, b)];
+                        r3 = ring[ring_idx(pslot, a, b - 1)];
+                        r5 = ring[ring_idx(pslot, a - 1, b - 1)];
+                    }
                     int ncand = 0;
                     uint32_t cand[7];
                     const bool update = in_row && ri >= 1;
                     if (update) {
-                        const int s1r = (s + RING - 1) & (RING - 1), s2r = (s + RING - 2) & (RING - 1), s3r = (s + RING - 3) & (RING - 1);
-                        uint32_t nb[7];
-                        nb[0] = prev_lo;
-                        nb[1] = ring[ring_idx(s1r, a - 1, b)];
-                        nb[2] = ring[ring_idx(s2r, a - 1, b)];
-                        nb[3] = ring[ring_idx(s1r, a, b - 1)];
-                        nb[4] = ring[ring_idx(s2r, a, b - 1)];
-                        nb[5] = ring[ring_idx(s2r, a - 1, b - 1)];
-                        nb[6] = ring[ring_idx(s3r, a - 1, b - 1)];
+                        const uint32_t nb[7] = {prev_lo, r1, r1_old, r3, r3_old, r5_old, r5_old2};
                         const int i = P.sd.abs_i(ri, g);
-                        const bool memo_ok = interior_row && i >= 1 && i <= g.ni - 2;
+                        const bool i_interior = (i >= 1 && i <= g.ni - 2);      // memo only for voxels every sweep visits
                         const uint32_t cur_tri = lo_tri(cur);
                         #pragma unroll
                         for (int m = 0; m < 7; ++m) {
                             const uint32_t t = lo_tri(nb[m]);
-                            bool keep = (t != TRI_NONE) && (t != cur_tri);
-                            if (keep && memo_ok && P.last[m] != 0 && lo_stamp(nb[m]) <= (uint32_t)P.last[m]) keep = false;
+                            bool keep = (t != TRI_NONE) && (t != cur_tri) && (!i_interior || lo_stamp(nb[m]) >= fresh_min[m]);
                             #pragma unroll
-                            for (int u = 0; u < m; ++u) keep = keep && (lo_tri(nb[u]) != t || false);
+                            for (int u = 0; u < m; ++u) keep = keep && (lo_tri(nb[u]) != t);
                             cand[m] = keep ? t : TRI_NONE;
                             ncand += keep ? 1 : 0;
                         }
                     }
-                    // ---- warp queue: exclusive scan of candidate counts --------------------------
-                    int incl = ncand;
-                    #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    r1_old = r1; r3_old = r3; r5_old2 = r5_old; r5_old = r5;
+                    // ---- warp queue: exclusive scan of the candidate counts (3 ballots: ncand <= 7) ----
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
+                                   b2 = __ballot_sync(0xffffffffu, ncand & 4);
+                    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                     if (total > 0) {
-                        int off = incl - ncand;
-                        if (update) {
+                        const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+                        if (ncand > 0) {
                             int w = off;
                             #pragma unroll
                             for (int m = 0; m < 7; ++m) if (cand[m] != TRI_NONE) { q_ent[warp][w] = ((uint32_t)lane << 27) | cand[m]; ++w; }
@@ -238,6 +247,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
                             const TriRec *tr = &rec[e & TRI_MASK];
                             const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
                             q_d[warp][q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+                            ++my_evals;
                         }
                         __syncwarp();
                         if (ncand > 0) {
@@ -264,13 +274,13 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
                 *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)s1;
             }
         }
-        (void)gy; (void)gz; (void)sj; (void)sk;
     }
 
     // ---- teardown: count changes; the last CTA out resets the ticket for the next launch ----------
-    unsigned wsum = my_changed;
-    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_down_sync(0xffffffffu, wsum, o);
+    unsigned wsum = my_changed, esum = my_evals;
+    for (int o = 16; o > 0; o >>= 1) { wsum += __shfl_down_sync(0xffffffffu, wsum, o); esum += __shfl_down_sync(0xffffffffu, esum, o); }
     if (lane == 0 && wsum) atomicAdd(changed, (unsigned long long)wsum);
+    if (lane == 0 && esum) atomicAdd(changed + 1, (unsigned long long)esum);
     __syncthreads();
     if (tid == 0) {
         __threadfence();
