@@ -167,15 +167,23 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                         uint32_t nb[7] = { prev_lo[tid], r1, r1_old[tid], r3, r3_old[tid], r5_old[tid], r5_old2[tid] };
                         int i = ABS_I(ri);
                         int i_interior = (i >= 1 && i <= ni - 2);
-                        uint32_t cur_tri = cur & TRI_MASK;
+                        int edge = (ri == ni - 1);   /* same as !i_interior: ri=0 is never updated */
+                        (void)i_interior;
+                        uint32_t live = 0;
                         for (int m = 0; m < 7; ++m) {
-                            uint32_t t = nb[m] & TRI_MASK;
-                            uint32_t fresh_min = (interior_row[tid] && last[m] != 0) ? (uint32_t)last[m] + 1u : 0u;
-                            int keep = (t != TRI_NONE) && (t != cur_tri) && (!i_interior || (nb[m] >> 27) >= fresh_min);
-                            for (int u = 0; u < m; ++u) keep = keep && ((nb[u] & TRI_MASK) != t);
-                            cand[tid][m] = keep ? t : TRI_NONE;
-                            n += keep ? 1 : 0;
+                            uint32_t xw = nb[m];
+                            uint32_t thr = (interior_row[tid] && last[m] != 0) ? ((uint32_t)last[m] + 1u) << 27 : 0u;
+                            int keep = ((xw & TRI_MASK) != TRI_NONE) && (((xw ^ cur) & TRI_MASK) != 0) && (edge || xw >= thr);
+                            if (keep) live |= 1u << m;
                         }
+                        if (live & (live - 1)) {
+                            for (int m = 1; m < 7; ++m) {
+                                int dup = 0;
+                                for (int u = 0; u < m; ++u) dup = dup || (((live >> u) & 1u) && (((nb[u] ^ nb[m]) & TRI_MASK) == 0));
+                                if (dup) live &= ~(1u << m);
+                            }
+                        }
+                        for (int m = 0; m < 7; ++m) { int keep = (live >> m) & 1u; cand[tid][m] = keep ? (nb[m] & TRI_MASK) : TRI_NONE; n += keep; }
                     }
                     r1_old[tid] = r1; r3_old[tid] = r3; r5_old2[tid] = r5_old[tid]; r5_old[tid] = r5;
                     ncand[tid] = n; upd[tid] = update; in_row_v[tid] = in_row; cur_v[tid] = cur; phi_v[tid] = phi;

@@ -45,7 +45,6 @@ constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
 constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
 constexpr int NTHREADS = NCOMPUTE + 64;      // + 2 halo warps
 constexpr int PUBLISH = 4;                   // steps between progress publications
-constexpr int RING = 2;                      // the ring is double buffered: every read is from step s-1
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -60,43 +59,208 @@ struct ColParams {
     uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
 };
 
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
+// smem exchange array: [2 slots][EK+1][EJ+1] words, index (b+1)*(EJ+1) + (a+1); a fastest
+constexpr int RSTRIDE = (EK + 1) * (EJ + 1);
+__device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1) + (a + 1); }
+
+// named barriers: 0 = __syncthreads (column hand-over), 1 = per-step (all 320 lanes), 2 = halo warps only
+__device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
+__device__ __forceinline__ void bar_halo() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+
+struct ColShared {
+    uint32_t ring[2 * RSTRIDE];
+    uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
+    float q_d[NCOMPUTE / 32][QCAP];
+    int col;
+};
+
+// ---- halo warps: feed the words of the upstream columns / boundary faces into the exchange array ----
+__device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const ColParams &P, ColShared &sh,
+                                            int h, int rj0, int rk0, const uint32_t *prog_left,
+                                            const uint32_t *prog_down, uint32_t *prog_mine)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    const Grid &g = P.g;
+    int a, b;
+    if (h <= EK) { a = -1; b = h - 1; }                    // (-1,-1), (-1,0) .. (-1,EK-1)
+    else if (h <= EK + EJ) { a = h - EK - 1; b = -1; }     // (0,-1) .. (EJ-1,-1)
+    else { a = -2; b = -2; }                               // idle lanes (h = 63 publishes progress)
+    const int rj = rj0 + a, rk = rk0 + b;
+    const bool row_ok = (a > -2) && rj <= g.nj - 1 && rk <= P.rk_last;
+    const int64_t si = (int64_t)P.sd.di;
+    const uint64_t *ptr = cells;
+    if (row_ok) ptr = cells + g.cidx(P.sd.abs_i(0, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g)) + si * (int64_t)(0 - a - b - SHIFT);
+    const int widx = row_ok ? ring_idx(a, b) : 0;
+    const uint32_t ebase = P.epoch << 16;
+    int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
+    uint32_t next = TRI_NONE;                              // word of virtual step s, loaded during step s-1
+    for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
+        const int s1 = min(s0 + PUBLISH, P.steps);
+        // Lane (-1,b) loads at step s the word of virtual step s+1, produced by column (J-1,K) lane
+        // (EJ-1,b) at its step s+1+EJ  =>  needs steps_done >= s+EJ+2; same with EK for (a,-1); the
+        // diagonal column is covered transitively.  Relaxed polls (an acquire load would invalidate
+        // this SM's L1 on every poll), one fence once both flags are seen.
+        if (h == 0) {
+            if (prog_left) {
+                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 2);
+                while (*reinterpret_cast<const volatile uint32_t *>(prog_left) < need) __nanosleep(20);
+            }
+            if (prog_down) {
+                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 2);
+                while (*reinterpret_cast<const volatile uint32_t *>(prog_down) < need) __nanosleep(20);
+            }
+            __threadfence();
+        }
+        bar_halo();
+        if (s0 == 0 && row_ok && (unsigned)ri < (unsigned)g.ni) next = cell_lo(__ldcg(ptr));
+        for (int s = s0; s < s1; ++s) {
+            if (row_ok) {
+                sh.ring[(s & 1) * RSTRIDE + widx] = next;
+                ++ri; ptr += si;
+                next = ((unsigned)ri < (unsigned)g.ni && s + 1 < P.steps) ? cell_lo(__ldcg(ptr)) : TRI_NONE;
+            }
+            bar_step();
+        }
+        if (h == 63) {          // all stores of steps < s1 were issued before the last bar_step
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)s1;
+        }
+    }
 }
 
-// ring slot layout: [RING][EK+1][EJ+1], index (b+1)*(EJ+1) + (a+1); a fastest
-__device__ __forceinline__ int ring_idx(int slot, int a, int b) { return slot * ((EK + 1) * (EJ + 1)) + (b + 1) * (EJ + 1) + (a + 1); }
+// ---- compute warps ---------------------------------------------------------------------------------
+__device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
+                                               const ColParams &P, ColShared &sh, int tid, int rj0, int rk0,
+                                               unsigned &my_changed, unsigned &my_evals)
+{
+    const Grid &g = P.g;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int a = tid % EJ, b = tid / EJ;
+    const int rj = rj0 + a, rk = rk0 + b;
+    const bool row_ok = rj <= g.nj - 1 && rk <= P.rk_last;
+    const int64_t si = (int64_t)P.sd.di;
+    bool interior_row = false;
+    uint64_t *own_ptr = cells;
+    if (row_ok) {
+        const int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
+        own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)(0 - a - b - SHIFT);
+        interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
+    }
+    // memo thresholds: neighbour word nb (offset m) is fresh iff nb >= thr[m], i.e. stamp(nb) >= last[m]+1;
+    // 0 where the offset was never examined or the row is on the grid boundary (some sweeps skip it)
+    uint32_t thr[7];
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) thr[m] = (interior_row && P.last[m] != 0) ? ((uint32_t)P.last[m] + 1u) << 27 : 0u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int widx = ring_idx(a, b), idx1 = ring_idx(a - 1, b), idx3 = ring_idx(a, b - 1), idx5 = ring_idx(a - 1, b - 1);
+    uint32_t *const q_ent = sh.q_ent[warp];
+    float *const q_d = sh.q_d[warp];
+
+    int ri = 0 - a - b - SHIFT;          // voxel of step 0
+    uint64_t own_next = 0;               // own cell of step s, loaded during step s-1
+    if (row_ok && (unsigned)ri < (unsigned)g.ni) own_next = *own_ptr;
+    uint32_t prev_lo = TRI_NONE;         // own result of step s-1                                  -> m=0
+    // words read from the exchange array in earlier steps, rolled through registers:
+    //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )   m=1 now, m=2 one step later
+    //   R3(s) = lane(a,  b-1)@s-1 = (ri,   rj,   rk-1)   m=3 now, m=4 one step later
+    //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)   m=5 one step later, m=6 two steps later
+    uint32_t r1_old = TRI_NONE, r3_old = TRI_NONE, r5_old = TRI_NONE, r5_old2 = TRI_NONE;
+
+    for (int s = 0; s < P.steps; ++s, ++ri) {
+        const int pbase = ((s & 1) ^ 1) * RSTRIDE;
+        const uint64_t self = own_next;
+        uint64_t *const self_ptr = own_ptr;
+        own_ptr += si;
+        if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) own_next = *own_ptr;       // next step's cell
+        if (row_ok && (s & 3) == 0 && (unsigned)(ri + 40) < (unsigned)g.ni)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 39 * si));
+        uint32_t cur = cell_lo(self);
+        float phi = cell_phi(self);
+        const uint32_t r1 = sh.ring[pbase + idx1], r3 = sh.ring[pbase + idx3], r5 = sh.ring[pbase + idx5];
+        const bool in_row = row_ok && (unsigned)ri < (unsigned)g.ni;
+        const bool update = in_row && ri >= 1;
+        const uint32_t nb[7] = {prev_lo, r1, r1_old, r3, r3_old, r5_old, r5_old2};
+        uint32_t live = 0;               // bit m: neighbour m's triangle must be evaluated
+        if (update) {
+            // the last voxel of a row lies on a grid face (|i| = 0 or ni-1): some sweeps never visit it, so
+            // "already examined" cannot be inferred from stamps there
+            const bool edge = (ri == g.ni - 1);
+            #pragma unroll
+            for (int m = 0; m < 7; ++m) {
+                const uint32_t x = nb[m];
+                const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (edge || x >= thr[m]);
+                live |= keep ? (1u << m) : 0u;
+            }
+            if (live & (live - 1)) {     // two or more: drop repeats of an earlier live triangle
+                #pragma unroll
+                for (int m = 1; m < 7; ++m) {
+                    bool dup = false;
+                    #pragma unroll
+                    for (int u = 0; u < m; ++u) dup = dup || (((live >> u) & 1u) && (((nb[u] ^ nb[m]) & TRI_MASK) == 0));
+                    if (dup) live &= ~(1u << m);
+                }
+            }
+        }
+        r1_old = r1; r3_old = r3; r5_old2 = r5_old; r5_old = r5;
+        const int ncand = __popc(live);
+        // ---- warp queue: exclusive scan of the candidate counts (3 ballots: ncand <= 7) ----------------
+        const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
+                       b2 = __ballot_sync(0xffffffffu, ncand & 4);
+        if (b0 | b1 | b2) {
+            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+            if (live) {
+                int w = off;
+                #pragma unroll
+                for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) { q_ent[w] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++w; }
+            }
+            __syncwarp();
+            for (int q = lane; q < total; q += 32) {
+                const uint32_t e = q_ent[q];
+                const int otid = (warp << 5) + (int)(e >> 27);       // owner lane -> its voxel
+                const int oa = otid % EJ, ob = otid / EJ;
+                const int ori = s - oa - ob - SHIFT;
+                const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
+                const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+                const TriRec *tr = &rec[e & TRI_MASK];
+                const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+                q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+                ++my_evals;
+            }
+            __syncwarp();
+            if (live) {
+                uint32_t best = TRI_NONE;
+                for (int q = off; q < off + ncand; ++q) {            // the reference's order and strict "<"
+                    const float d = q_d[q];
+                    if (d < phi) { phi = d; best = q_ent[q] & TRI_MASK; }
+                }
+                if (best != TRI_NONE) {
+                    cur = (P.stamp << 27) | best;
+                    *self_ptr = pack_cell(phi, cur);
+                    ++my_changed;
+                }
+            }
+            __syncwarp();
+        }
+        if (in_row) { sh.ring[(s & 1) * RSTRIDE + widx] = cur; prev_lo = cur; }
+        bar_step();
+    }
+}
 
 __global__ void __launch_bounds__(NTHREADS, 3)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
                 unsigned long long *__restrict__ changed)
 {
-    __shared__ uint32_t ring[RING * (EK + 1) * (EJ + 1)];
-    __shared__ uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
-    __shared__ float q_d[NCOMPUTE / 32][QCAP];
-    __shared__ int col_s;
-
-    const Grid &g = P.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_compute = tid < NCOMPUTE;
+    __shared__ ColShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int ncols = P.NJ * P.NK;
     unsigned my_changed = 0, my_evals = 0;
 
-    // strides of the relative axes in the cell array
-    const int64_t si = (int64_t)P.sd.di;
-
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
-        if (tid == 0) {
-            int t = (int)atomicAdd(ticket, 1u);
-            col_s = t;
-        }
+        if (tid == 0) sh.col = (int)atomicAdd(ticket, 1u);
         __syncthreads();
-        const int tk = col_s;
+        const int tk = sh.col;
         if (tk >= ncols) break;
         int J, K;
         {
@@ -109,171 +273,14 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
             }
         }
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
-        const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
-        const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
-        uint32_t *prog_mine = &progress[K * P.NJ + J];
-        const uint32_t ebase = P.epoch << 16;
-
-        // ---- lane identity ---------------------------------------------------------------------
-        int a, b;                      // lane coordinates in the column; halo lanes have a=-1 or b=-1
-        if (is_compute) { a = tid % EJ; b = tid / EJ; }
-        else {
-            int h = tid - NCOMPUTE;    // 0..63
-            if (h <= EK) { a = -1; b = h - 1; }            // (-1,-1), (-1,0) .. (-1,EK-1)
-            else if (h <= EK + EJ) { a = h - EK - 1; b = -1; }   // (0,-1) .. (EJ-1,-1)
-            else { a = -2; b = -2; }                        // idle
+        if (tid < NCOMPUTE) {
+            compute_column(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+        } else {
+            const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
+            const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
+            halo_column(cells, P, sh, tid - NCOMPUTE, rj0, rk0, prog_left, prog_down, &progress[K * P.NJ + J]);
         }
-        const int rj = rj0 + a, rk = rk0 + b;
-        const bool row_ok = (a > -2) && rj <= g.nj - 1 && rk <= P.rk_last;   // rj,rk >= 0 by construction
-        // cell index of (ri=0, rj, rk)
-        int64_t c_row = 0;
-        bool interior_row = false;
-        if (row_ok) {
-            int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
-            c_row = g.cidx(P.sd.abs_i(0, g), j, k);
-            interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
-        }
-
-        // software pipeline registers
-        uint64_t own_next = 0;         // compute: own cell for step s (prefetched at s-1)
-        uint32_t halo_next = TRI_NONE; // halo: word for virtual step s (prefetched at s-1)
-        uint32_t prev_lo = TRI_NONE;   // compute: own result of step s-1                 -> m=0
-        // ring words read in earlier steps, rolled through registers (see the table above):
-        //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )  m=1 now, m=2 one step later
-        //   R3(s) = lane(a,  b-1)@s-1 = (ri,   rj,   rk-1)  m=3 now, m=4 one step later
-        //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)  m=5 one step later, m=6 two steps later
-        uint32_t r1_old = TRI_NONE, r3_old = TRI_NONE, r5_old = TRI_NONE, r5_old2 = TRI_NONE;
-        const uint64_t *own_ptr = cells + c_row + si * (int64_t)(0 - a - b - SHIFT);   // cell of step 0 (may be out of range: guarded)
-        {
-            int ri0 = 0 - a - b - SHIFT;       // voxel of step 0
-            if (is_compute) { if (row_ok && ri0 >= 0 && ri0 <= g.ni - 1) own_next = *own_ptr; }
-        }
-        // memo thresholds: candidate m is fresh iff stamp(nb) >= fresh_min[m] (0 when never examined)
-        uint32_t fresh_min[7];
-        #pragma unroll
-        for (int m = 0; m < 7; ++m) fresh_min[m] = (interior_row && P.last[m] != 0) ? (uint32_t)P.last[m] + 1u : 0u;
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        // halo lanes start their pipeline inside the loop (after the first progress check)
-
-        for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
-            const int s1 = min(s0 + PUBLISH, P.steps);
-            // ---- wait until the producer columns are far enough for this chunk ----------------
-            // Halo lane (-1,b) loads at step s the word for virtual step s+1, produced by column
-            // (J-1,K) lane (EJ-1,b) at its step s+1+EJ  =>  needs steps_done >= s+EJ+2; same with EK
-            // (the SHIFT cancels: both columns use the same lane->voxel map).
-            if (tid == NCOMPUTE) {
-                // relaxed polls (an acquire load would invalidate this SM's L1 on every poll), one
-                // fence once the flags are seen
-                if (prog_left) {
-                    uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 2);
-                    while (*reinterpret_cast<const volatile uint32_t *>(prog_left) < need) __nanosleep(32);
-                }
-                if (prog_down) {
-                    uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 2);
-                    while (*reinterpret_cast<const volatile uint32_t *>(prog_down) < need) __nanosleep(32);
-                }
-                __threadfence();
-            }
-            __syncthreads();
-            if (!is_compute && s0 == 0 && row_ok) {
-                int ri0 = 0 - a - b - SHIFT;               // virtual step 0
-                halo_next = (ri0 >= 0 && ri0 <= g.ni - 1) ? cell_lo(__ldcg(&cells[c_row + si * ri0])) : TRI_NONE;
-            }
-
-            for (int s = s0; s < s1; ++s) {
-                const int ri = s - a - b - SHIFT;
-                const int slot = s & 1, pslot = slot ^ 1;
-                if (!is_compute) {
-                    // ---- halo lanes: publish the word loaded one step ago, prefetch the next ------
-                    if (row_ok) {
-                        ring[ring_idx(slot, a, b)] = halo_next;
-                        int rin = ri + 1;
-                        halo_next = (rin >= 0 && rin <= g.ni - 1 && s + 1 < P.steps) ? cell_lo(__ldcg(&cells[c_row + si * rin])) : TRI_NONE;
-                    }
-                } else {
-                    // ---- compute lanes -------------------------------------------------------------
-                    const bool in_row = row_ok && ri >= 0 && ri <= g.ni - 1;
-                    const uint64_t self = own_next;
-                    own_ptr += si;
-                    if (row_ok && ri + 1 >= 0 && ri + 1 <= g.ni - 1) own_next = *own_ptr;   // prefetch the next step's cell
-                    uint32_t cur = cell_lo(self);
-                    float phi = cell_phi(self);
-                    // this step's ring reads (all from step s-1); meaningful from ri >= -1 on
-                    uint32_t r1 = TRI_NONE, r3 = TRI_NONE, r5 = TRI_NONE;
-                    if (row_ok && ri >= -1 && ri <= g.ni - 1) {
-                        r1 = ring[ring_idx(pslot, a - 1, b)];
-                        r3 = ring[ring_idx(pslot, a, b - 1)];
-                        r5 = ring[ring_idx(pslot, a - 1, b - 1)];
-                    }
-                    int ncand = 0;
-                    uint32_t cand[7];
-                    const bool update = in_row && ri >= 1;
-                    if (update) {
-                        const uint32_t nb[7] = {prev_lo, r1, r1_old, r3, r3_old, r5_old, r5_old2};
-                        const int i = P.sd.abs_i(ri, g);
-                        const bool i_interior = (i >= 1 && i <= g.ni - 2);      // memo only for voxels every sweep visits
-                        const uint32_t cur_tri = lo_tri(cur);
-                        #pragma unroll
-                        for (int m = 0; m < 7; ++m) {
-                            const uint32_t t = lo_tri(nb[m]);
-                            bool keep = (t != TRI_NONE) && (t != cur_tri) && (!i_interior || lo_stamp(nb[m]) >= fresh_min[m]);
-                            #pragma unroll
-                            for (int u = 0; u < m; ++u) keep = keep && (lo_tri(nb[u]) != t);
-                            cand[m] = keep ? t : TRI_NONE;
-                            ncand += keep ? 1 : 0;
-                        }
-                    }
-                    r1_old = r1; r3_old = r3; r5_old2 = r5_old; r5_old = r5;
-                    // ---- warp queue: exclusive scan of the candidate counts (3 ballots: ncand <= 7) ----
-                    const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
-                                   b2 = __ballot_sync(0xffffffffu, ncand & 4);
-                    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-                    if (total > 0) {
-                        const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-                        if (ncand > 0) {
-                            int w = off;
-                            #pragma unroll
-                            for (int m = 0; m < 7; ++m) if (cand[m] != TRI_NONE) { q_ent[warp][w] = ((uint32_t)lane << 27) | cand[m]; ++w; }
-                        }
-                        __syncwarp();
-                        for (int q = lane; q < total; q += 32) {
-                            const uint32_t e = q_ent[warp][q];
-                            const int ol = (int)(e >> 27);                   // owner lane
-                            const int otid = warp * 32 + ol;
-                            const int oa = otid % EJ, ob = otid / EJ;
-                            const int ori = s - oa - ob - SHIFT;
-                            const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
-                            F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
-                            const TriRec *tr = &rec[e & TRI_MASK];
-                            const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
-                            q_d[warp][q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
-                            ++my_evals;
-                        }
-                        __syncwarp();
-                        if (ncand > 0) {
-                            uint32_t best = TRI_NONE;
-                            for (int q = off; q < off + ncand; ++q) {
-                                const float d = q_d[warp][q];
-                                if (d < phi) { phi = d; best = q_ent[warp][q] & TRI_MASK; }
-                            }
-                            if (best != TRI_NONE) {
-                                cur = (P.stamp << 27) | best;
-                                cells[c_row + si * ri] = pack_cell(phi, cur);
-                                ++my_changed;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    if (in_row) { ring[ring_idx(slot, a, b)] = cur; prev_lo = cur; }
-                }
-                __syncthreads();
-            }
-            // ---- publish progress ------------------------------------------------------------------
-            if (tid == 0) {
-                __threadfence();
-                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)s1;
-            }
-        }
+        __syncthreads();        // sh.col is rewritten next; also orders the two roles' exits
     }
 
     // ---- teardown: count changes; the last CTA out resets the ticket for the next launch ----------
