@@ -92,31 +92,37 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     const int widx = row_ok ? ring_idx(a, b) : 0;
     const uint32_t ebase = P.epoch << 16;
     int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
-    uint32_t next = TRI_NONE;                              // word of virtual step s, loaded during step s-1
+    uint32_t w0 = TRI_NONE, w1 = TRI_NONE;                 // words of virtual steps s and s+1 (loaded at s-2, s-1)
     for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
         const int s1 = min(s0 + PUBLISH, P.steps);
-        // Lane (-1,b) loads at step s the word of virtual step s+1, produced by column (J-1,K) lane
-        // (EJ-1,b) at its step s+1+EJ  =>  needs steps_done >= s+EJ+2; same with EK for (a,-1); the
+        // Lane (-1,b) loads at step s the word of virtual step s+2, produced by column (J-1,K) lane
+        // (EJ-1,b) at its step s+2+EJ  =>  needs steps_done >= s+EJ+3; same with EK for (a,-1); the
         // diagonal column is covered transitively.  Relaxed polls (an acquire load would invalidate
         // this SM's L1 on every poll), one fence once both flags are seen.
         if (h == 0) {
             if (prog_left) {
-                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 2);
+                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3);
                 while (*reinterpret_cast<const volatile uint32_t *>(prog_left) < need) __nanosleep(20);
             }
             if (prog_down) {
-                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 2);
+                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3);
                 while (*reinterpret_cast<const volatile uint32_t *>(prog_down) < need) __nanosleep(20);
             }
             __threadfence();
         }
         bar_halo();
-        if (s0 == 0 && row_ok && (unsigned)ri < (unsigned)g.ni) next = cell_lo(__ldcg(ptr));
+        if (s0 == 0 && row_ok) {
+            if ((unsigned)ri < (unsigned)g.ni) w0 = cell_lo(__ldcg(ptr));
+            if ((unsigned)(ri + 1) < (unsigned)g.ni) w1 = cell_lo(__ldcg(ptr + si));
+        }
         for (int s = s0; s < s1; ++s) {
             if (row_ok) {
-                sh.ring[(s & 1) * RSTRIDE + widx] = next;
-                ++ri; ptr += si;
-                next = ((unsigned)ri < (unsigned)g.ni && s + 1 < P.steps) ? cell_lo(__ldcg(ptr)) : TRI_NONE;
+                sh.ring[(s & 1) * RSTRIDE + widx] = w0;
+                w0 = w1;
+                ++ri; ptr += si;                           // now the voxel of virtual step s+1
+                w1 = ((unsigned)(ri + 1) < (unsigned)g.ni && s + 2 < P.steps) ? cell_lo(__ldcg(ptr + si)) : TRI_NONE;
+                // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
+                if ((s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
             }
             bar_step();
         }
@@ -156,8 +162,9 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     float *const q_d = sh.q_d[warp];
 
     int ri = 0 - a - b - SHIFT;          // voxel of step 0
-    uint64_t own_next = 0;               // own cell of step s, loaded during step s-1
-    if (row_ok && (unsigned)ri < (unsigned)g.ni) own_next = *own_ptr;
+    uint64_t own0 = 0, own1 = 0;         // own cells of steps s and s+1 (loaded during s-2, s-1)
+    if (row_ok && (unsigned)ri < (unsigned)g.ni) own0 = *own_ptr;
+    if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) own1 = *(own_ptr + si);
     uint32_t prev_lo = TRI_NONE;         // own result of step s-1                                  -> m=0
     // words read from the exchange array in earlier steps, rolled through registers:
     //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )   m=1 now, m=2 one step later
@@ -167,12 +174,13 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 
     for (int s = 0; s < P.steps; ++s, ++ri) {
         const int pbase = ((s & 1) ^ 1) * RSTRIDE;
-        const uint64_t self = own_next;
+        const uint64_t self = own0;
         uint64_t *const self_ptr = own_ptr;
         own_ptr += si;
-        if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) own_next = *own_ptr;       // next step's cell
-        if (row_ok && (s & 3) == 0 && (unsigned)(ri + 40) < (unsigned)g.ni)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 39 * si));
+        own0 = own1;
+        if (row_ok && (unsigned)(ri + 2) < (unsigned)g.ni) own1 = *(own_ptr + si);    // the cell two steps ahead
+        if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 47 * si));
         uint32_t cur = cell_lo(self);
         float phi = cell_phi(self);
         const uint32_t r1 = sh.ring[pbase + idx1], r3 = sh.ring[pbase + idx3], r5 = sh.ring[pbase + idx5];
@@ -181,21 +189,30 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
         const uint32_t nb[7] = {prev_lo, r1, r1_old, r3, r3_old, r5_old, r5_old2};
         uint32_t live = 0;               // bit m: neighbour m's triangle must be evaluated
         if (update) {
-            // the last voxel of a row lies on a grid face (|i| = 0 or ni-1): some sweeps never visit it, so
-            // "already examined" cannot be inferred from stamps there
-            const bool edge = (ri == g.ni - 1);
-            #pragma unroll
-            for (int m = 0; m < 7; ++m) {
-                const uint32_t x = nb[m];
-                const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (edge || x >= thr[m]);
-                live |= keep ? (1u << m) : 0u;
-            }
-            if (live & (live - 1)) {     // two or more: drop repeats of an earlier live triangle
+            // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this
+            // voxel last looked at offset m.  The last voxel of a row lies on a grid face: some sweeps never
+            // visit it, so "already examined" cannot be inferred from stamps there -> no memo.
+            if (ri != g.ni - 1) {
                 #pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    const uint32_t x = nb[m];
+                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (x >= thr[m]);
+                    live |= keep ? (1u << m) : 0u;
+                }
+            } else {
+                #pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    const uint32_t x = nb[m];
+                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0);
+                    live |= keep ? (1u << m) : 0u;
+                }
+            }
+            if (live) {                  // drop repeats of ANY earlier neighbour's triangle: that triangle is
+                #pragma unroll           // either evaluated there, or the voxel's own, or a known loser (memo)
                 for (int m = 1; m < 7; ++m) {
                     bool dup = false;
                     #pragma unroll
-                    for (int u = 0; u < m; ++u) dup = dup || (((live >> u) & 1u) && (((nb[u] ^ nb[m]) & TRI_MASK) == 0));
+                    for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
                     if (dup) live &= ~(1u << m);
                 }
             }
@@ -211,7 +228,12 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
             if (live) {
                 int w = off;
                 #pragma unroll
-                for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) { q_ent[w] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++w; }
+                for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
+                    q_ent[w] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++w;
+                    const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);     // start the gather now
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
+                }
             }
             __syncwarp();
             for (int q = lane; q < total; q += 32) {
