@@ -21,7 +21,7 @@ float sdfo_point_triangle_distance(const float *x0, const float *x1, const float
 #define EK 16
 #define NCOMPUTE (EJ*EK)
 #define NLANES (NCOMPUTE + 64)
-#define PUBLISH 4
+#define PUBLISH 2
 #define RING 2
 #define SHIFT 2
 #define TRI_MASK 0x07ffffffu
@@ -60,7 +60,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
     if (rk_first < 1) rk_first = 1;
     if (rk_first > rk_last || ni < 2 || nj < 2) { if (changed_out) *changed_out = 0; return 0; }
     const int NJ = (nj - 1 + EJ - 1) / EJ, NK = (rk_last - rk_first + 1 + EK - 1) / EK;
-    const int steps = ni + EJ + EK - 2 + SHIFT;
+    const int steps = (ni + EJ + EK - 2 + SHIFT + 1) & ~1;
     const uint32_t stamp = (uint32_t)imin(sweep_index + 1, 31);
     uint8_t last[7];
     for (int m = 0; m < 7; ++m) {

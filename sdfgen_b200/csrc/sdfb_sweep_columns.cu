@@ -44,7 +44,10 @@ namespace {
 constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
 constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
 constexpr int NTHREADS = NCOMPUTE + 64;      // + 2 halo warps
-constexpr int PUBLISH = 4;                   // steps between progress publications
+#ifndef SDFB_PUBLISH
+#define SDFB_PUBLISH 2
+#endif
+constexpr int PUBLISH = SDFB_PUBLISH;                   // steps between progress publications
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -53,7 +56,7 @@ struct ColParams {
     SweepDir sd;
     int rk_first, rk_last;                   // relative k range updated by this launch (inclusive)
     int NJ, NK;                              // columns in j and k
-    int steps;                               // steps per column = ni + EJ + EK
+    int steps;                               // steps per column = ni + EJ + EK, rounded up to even
     uint32_t stamp;                          // sweep_index + 1
     uint32_t epoch;                          // progress values are epoch<<16 | steps_done
     uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
@@ -92,7 +95,10 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     const int widx = row_ok ? ring_idx(a, b) : 0;
     const uint32_t ebase = P.epoch << 16;
     int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
-    uint32_t w0 = TRI_NONE, w1 = TRI_NONE;                 // words of virtual steps s and s+1 (loaded at s-2, s-1)
+    // Raw cells of virtual steps s (even -> wA, odd -> wB), each loaded two steps before it is published.
+    // The step loop is unrolled by two so that a register is reloaded right after it was consumed and
+    // never copied: a copy (or a select) of a freshly loaded value would stall on the load at once.
+    uint64_t wA = ~0ull, wB = ~0ull;
     for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
         const int s1 = min(s0 + PUBLISH, P.steps);
         // Lane (-1,b) loads at step s the word of virtual step s+2, produced by column (J-1,K) lane
@@ -112,17 +118,23 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
         }
         bar_halo();
         if (s0 == 0 && row_ok) {
-            if ((unsigned)ri < (unsigned)g.ni) w0 = cell_lo(__ldcg(ptr));
-            if ((unsigned)(ri + 1) < (unsigned)g.ni) w1 = cell_lo(__ldcg(ptr + si));
+            if ((unsigned)ri < (unsigned)g.ni) wA = __ldcg(ptr);
+            if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
         }
-        for (int s = s0; s < s1; ++s) {
+        for (int s = s0; s < s1; s += 2) {                 // PUBLISH and P.steps are even
             if (row_ok) {
-                sh.ring[(s & 1) * RSTRIDE + widx] = w0;
-                w0 = w1;
-                ++ri; ptr += si;                           // now the voxel of virtual step s+1
-                w1 = ((unsigned)(ri + 1) < (unsigned)g.ni && s + 2 < P.steps) ? cell_lo(__ldcg(ptr + si)) : TRI_NONE;
+                sh.ring[widx] = cell_lo(wA);               // even step -> slot 0
+                wA = ~0ull;
+                if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
+            }
+            bar_step();
+            if (row_ok) {
+                sh.ring[RSTRIDE + widx] = cell_lo(wB);     // odd step -> slot 1
+                wB = ~0ull;
+                if ((unsigned)(ri + 3) < (unsigned)g.ni && s + 3 < P.steps) wB = __ldcg(ptr + 3 * si);
+                ri += 2; ptr += 2 * si;
                 // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
-                if ((s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
+                if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
             }
             bar_step();
         }
@@ -162,9 +174,11 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     float *const q_d = sh.q_d[warp];
 
     int ri = 0 - a - b - SHIFT;          // voxel of step 0
-    uint64_t own0 = 0, own1 = 0;         // own cells of steps s and s+1 (loaded during s-2, s-1)
-    if (row_ok && (unsigned)ri < (unsigned)g.ni) own0 = *own_ptr;
-    if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) own1 = *(own_ptr + si);
+    // own cells by step parity (even -> ownA, odd -> ownB), each loaded two steps before use and reloaded
+    // right after it was consumed (no copies of fresh loads, see halo_column)
+    uint64_t ownA = 0, ownB = 0;
+    if (row_ok && (unsigned)ri < (unsigned)g.ni) ownA = *own_ptr;
+    if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) ownB = *(own_ptr + si);
     uint32_t prev_lo = TRI_NONE;         // own result of step s-1                                  -> m=0
     // words read from the exchange array in earlier steps, rolled through registers:
     //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )   m=1 now, m=2 one step later
@@ -172,15 +186,14 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)   m=5 one step later, m=6 two steps later
     uint32_t r1_old = TRI_NONE, r3_old = TRI_NONE, r5_old = TRI_NONE, r5_old2 = TRI_NONE;
 
-    for (int s = 0; s < P.steps; ++s, ++ri) {
+    auto step = [&](const int s, uint64_t &own) {
         const int pbase = ((s & 1) ^ 1) * RSTRIDE;
-        const uint64_t self = own0;
+        const uint64_t self = own;
         uint64_t *const self_ptr = own_ptr;
-        own_ptr += si;
-        own0 = own1;
-        if (row_ok && (unsigned)(ri + 2) < (unsigned)g.ni) own1 = *(own_ptr + si);    // the cell two steps ahead
+        if (row_ok && (unsigned)(ri + 2) < (unsigned)g.ni) own = *(own_ptr + 2 * si);  // the cell two steps ahead
         if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 47 * si));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 48 * si));
+        own_ptr += si;
         uint32_t cur = cell_lo(self);
         float phi = cell_phi(self);
         const uint32_t r1 = sh.ring[pbase + idx1], r3 = sh.ring[pbase + idx3], r5 = sh.ring[pbase + idx5];
@@ -265,6 +278,11 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
         }
         if (in_row) { sh.ring[(s & 1) * RSTRIDE + widx] = cur; prev_lo = cur; }
         bar_step();
+        ++ri;
+    };
+    for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
+        step(s, ownA);
+        step(s + 1, ownB);
     }
 }
 
@@ -339,7 +357,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     P.rk_first = rk_lo; P.rk_last = rk_hi;
     P.NJ = (g.nj - 1 + EJ - 1) / EJ;
     P.NK = (rk_hi - rk_lo + 1 + EK - 1) / EK;
-    P.steps = g.ni + EJ + EK - 2 + SHIFT;
+    P.steps = (g.ni + EJ + EK - 2 + SHIFT + 1) & ~1;   // even: the step loops are unrolled by two
     P.stamp = (uint32_t)min(sweep_index + 1, 31);
     // the epoch grows with every launch on a plan between resets of the progress array (host side)
     P.epoch = epoch;
