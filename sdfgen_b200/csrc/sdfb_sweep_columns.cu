@@ -163,11 +163,10 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
         own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)(0 - a - b - SHIFT);
         interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
     }
-    // memo thresholds: neighbour word nb (offset m) is fresh iff nb >= thr[m], i.e. stamp(nb) >= last[m]+1;
-    // 0 where the offset was never examined or the row is on the grid boundary (some sweeps skip it)
-    uint32_t thr[7];
-    #pragma unroll
-    for (int m = 0; m < 7; ++m) thr[m] = (interior_row && P.last[m] != 0) ? ((uint32_t)P.last[m] + 1u) << 27 : 0u;
+    // memo thresholds (uniform, read from the kernel parameters): neighbour word nb at offset m is fresh
+    // iff nb >= thr(m) = (last[m]+1) << 27, i.e. stamp(nb) > last[m]; 0 where the offset was never examined.
+    // Rows on the grid boundary (some sweeps skip them) never use the memo.
+#define THR(m) (P.last[m] != 0 ? ((uint32_t)P.last[m] + 1u) << 27 : 0u)
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int widx = ring_idx(a, b), idx1 = ring_idx(a - 1, b), idx3 = ring_idx(a, b - 1), idx5 = ring_idx(a - 1, b - 1);
     uint32_t *const q_ent = sh.q_ent[warp];
@@ -205,11 +204,11 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
             // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this
             // voxel last looked at offset m.  The last voxel of a row lies on a grid face: some sweeps never
             // visit it, so "already examined" cannot be inferred from stamps there -> no memo.
-            if (ri != g.ni - 1) {
+            if (interior_row && ri != g.ni - 1) {
                 #pragma unroll
                 for (int m = 0; m < 7; ++m) {
                     const uint32_t x = nb[m];
-                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (x >= thr[m]);
+                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (x >= THR(m));
                     live |= keep ? (1u << m) : 0u;
                 }
             } else {
@@ -286,7 +285,10 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 3)
+#ifndef SDFB_MINB
+#define SDFB_MINB 3
+#endif
+__global__ void __launch_bounds__(NTHREADS, SDFB_MINB)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
                 unsigned long long *__restrict__ changed)
