@@ -146,6 +146,143 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
 }
 
 // ---- compute warps ---------------------------------------------------------------------------------
+// Per-lane state of a compute lane, kept in registers across the (unrolled) step loop.
+struct LaneState {
+    uint64_t *own_ptr;                    // cell of the current step's voxel
+    int ri;                               // its relative i
+    uint32_t prev_lo;                     // own result of step s-1                                  -> m=0
+    // words read from the exchange array in earlier steps, rolled through registers:
+    //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )   m=1 now, m=2 one step later
+    //   R3(s) = lane(a,  b-1)@s-1 = (ri,   rj,   rk-1)   m=3 now, m=4 one step later
+    //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)   m=5 one step later, m=6 two steps later
+    uint32_t r1_old, r3_old, r5_old, r5_old2;
+    unsigned changed, evals;
+};
+
+// The rare part of a step: at least one lane of the warp has a neighbour whose cell changed since the
+// lane last looked at that offset.  Filters the candidates, balances the distance evaluations over the
+// warp through a queue in shared memory and replays each lane's results in the reference's order.
+// Everything is passed and returned by value (registers): a reference to the caller's arrays would force
+// them into local memory on the hot path.  Returns {new cell word, (evaluations << 1) | changed}.
+__device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ rec, const ColParams &P, uint32_t *q_ent, float *q_d,
+                                                  int s, int lane, int warp, int rj0, int rk0, bool update, bool edge,
+                                                  uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
+                                                  uint32_t nb5, uint32_t nb6, uint32_t th0, uint32_t th1, uint32_t th2,
+                                                  uint32_t th3, uint32_t th4, uint32_t th5, uint32_t th6,
+                                                  uint32_t cur, uint64_t *self_ptr, float phi)
+{
+    const Grid &g = P.g;
+    const uint32_t nb[7] = {nb0, nb1, nb2, nb3, nb4, nb5, nb6}, thr[7] = {th0, th1, th2, th3, th4, th5, th6};
+    unsigned evals = 0, changed = 0;
+    uint32_t live = 0;                    // bit m: neighbour m's triangle must be evaluated
+    if (update) {
+        // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this voxel
+        // last looked at offset m
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            const uint32_t x = nb[m];
+            const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (edge || x >= thr[m]);
+            live |= keep ? (1u << m) : 0u;
+        }
+        if (live) {                       // drop repeats of ANY earlier neighbour's triangle: that triangle is
+            #pragma unroll                // either evaluated there, or the voxel's own, or a known loser (memo)
+            for (int m = 1; m < 7; ++m) {
+                bool dup = false;
+                #pragma unroll
+                for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
+                if (dup) live &= ~(1u << m);
+            }
+        }
+    }
+    const int ncand = __popc(live);
+    // exclusive scan of the candidate counts over the warp (3 ballots: ncand <= 7)
+    const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
+                   b2 = __ballot_sync(0xffffffffu, ncand & 4);
+    if ((b0 | b1 | b2) == 0) return make_uint2(cur, 0u);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+    if (live) {
+        int w = off;
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
+            q_ent[w] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++w;
+            const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);     // start the gather now
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
+        }
+    }
+    __syncwarp();
+    for (int q = lane; q < total; q += 32) {
+        const uint32_t e = q_ent[q];
+        const int otid = (warp << 5) + (int)(e >> 27);               // owner lane -> its voxel
+        const int oa = otid % EJ, ob = otid / EJ;
+        const int ori = s - oa - ob - SHIFT;
+        const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
+        const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+        const TriRec *tr = &rec[e & TRI_MASK];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+        ++evals;
+    }
+    __syncwarp();
+    if (live) {
+        uint32_t best = TRI_NONE;
+        for (int q = off; q < off + ncand; ++q) {                    // the reference's order and strict "<"
+            const float d = q_d[q];
+            if (d < phi) { phi = d; best = q_ent[q] & TRI_MASK; }
+        }
+        if (best != TRI_NONE) {
+            cur = (P.stamp << 27) | best;
+            *self_ptr = pack_cell(phi, cur);
+            changed = 1;
+        }
+    }
+    __syncwarp();
+    return make_uint2(cur, (evals << 1) | changed);
+}
+
+// One step of a compute lane.  PAR = step parity: reads exchange slot PAR^1, writes slot PAR.  `own` holds the
+// lane's cell for this step on entry and is reloaded with the cell two steps ahead (see halo_column).
+template <int PAR>
+__device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
+                                             const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
+                                             int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
+                                             uint64_t &own, LaneState &st)
+{
+    const int ni = P.g.ni;
+    const int64_t si = (int64_t)P.sd.di;
+    const int ri = st.ri;
+    const uint32_t *rr = ring_r + (PAR ^ 1) * RSTRIDE;
+    const uint32_t r5 = rr[0], r3 = rr[1], r1 = rr[EJ + 1];
+    const uint64_t self = own;
+    uint64_t *const self_ptr = st.own_ptr;
+    if (row_ok && (unsigned)(ri + 2) < (unsigned)ni) own = *(self_ptr + 2 * si);       // the cell two steps ahead
+    if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)ni)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(self_ptr + 48 * si));
+    uint32_t cur = cell_lo(self);
+    const bool update = row_ok && (unsigned)(ri - 1) < (unsigned)(ni - 1);            // 1 <= ri <= ni-1
+    // The last voxel of a row lies on a grid face: some sweeps never visit it, so "already examined" cannot
+    // be inferred from stamps there -> it always takes the full path (as do boundary rows: thr = 0).
+    const bool edge = (ri == ni - 1);
+    const uint32_t nb[7] = {st.prev_lo, r1, st.r1_old, r3, st.r3_old, st.r5_old, st.r5_old2};
+    bool fresh = edge;
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) fresh = fresh || (nb[m] >= thr[m]);
+    if (__any_sync(0xffffffffu, update && fresh)) {
+        const uint2 r = evaluate_candidates(rec, P, sh.q_ent[warp], sh.q_d[warp], s, lane, warp, rj0, rk0, update, edge,
+                                            nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
+                                            thr[0], thr[1], thr[2], thr[3], thr[4], thr[5], thr[6],
+                                            cur, self_ptr, cell_phi(self));
+        cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
+    }
+    st.r1_old = r1; st.r3_old = r3; st.r5_old2 = st.r5_old; st.r5_old = r5;
+    if (row_ok && (unsigned)ri < (unsigned)ni) { ring_w[PAR * RSTRIDE] = cur; st.prev_lo = cur; }
+    st.own_ptr = self_ptr + si;
+    st.ri = ri + 1;
+    bar_step();
+}
+
 __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
                                                const ColParams &P, ColShared &sh, int tid, int rj0, int rk0,
                                                unsigned &my_changed, unsigned &my_evals)
@@ -157,136 +294,38 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     const bool row_ok = rj <= g.nj - 1 && rk <= P.rk_last;
     const int64_t si = (int64_t)P.sd.di;
     bool interior_row = false;
-    uint64_t *own_ptr = cells;
+    LaneState st;
+    st.own_ptr = cells;
+    st.ri = 0 - a - b - SHIFT;            // voxel of step 0
     if (row_ok) {
         const int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
-        own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)(0 - a - b - SHIFT);
+        st.own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)st.ri;
         interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
     }
-    // memo thresholds (uniform, read from the kernel parameters): neighbour word nb at offset m is fresh
-    // iff nb >= thr(m) = (last[m]+1) << 27, i.e. stamp(nb) > last[m]; 0 where the offset was never examined.
-    // Rows on the grid boundary (some sweeps skip them) never use the memo.
-#define THR(m) (P.last[m] != 0 ? ((uint32_t)P.last[m] + 1u) << 27 : 0u)
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int widx = ring_idx(a, b), idx1 = ring_idx(a - 1, b), idx3 = ring_idx(a, b - 1), idx5 = ring_idx(a - 1, b - 1);
-    uint32_t *const q_ent = sh.q_ent[warp];
-    float *const q_d = sh.q_d[warp];
-
-    int ri = 0 - a - b - SHIFT;          // voxel of step 0
+    // memo thresholds: the neighbour word nb at offset m is fresh iff nb >= thr[m] = (last[m]+1) << 27, i.e.
+    // stamp(nb) > last[m]; 0 (always fresh) where the offset was never examined or the row is on the grid
+    // boundary (some sweeps skip it, so stamps prove nothing there)
+    uint32_t thr[7];
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) thr[m] = (interior_row && P.last[m] != 0) ? ((uint32_t)P.last[m] + 1u) << 27 : 0u;
+    const uint32_t *ring_r = sh.ring + ring_idx(a - 1, b - 1);     // R5 at +0, R3 at +1, R1 at +(EJ+1)
+    uint32_t *ring_w = sh.ring + ring_idx(a, b);
+    st.prev_lo = TRI_NONE; st.r1_old = TRI_NONE; st.r3_old = TRI_NONE; st.r5_old = TRI_NONE; st.r5_old2 = TRI_NONE;
+    st.changed = 0; st.evals = 0;
     // own cells by step parity (even -> ownA, odd -> ownB), each loaded two steps before use and reloaded
     // right after it was consumed (no copies of fresh loads, see halo_column)
     uint64_t ownA = 0, ownB = 0;
-    if (row_ok && (unsigned)ri < (unsigned)g.ni) ownA = *own_ptr;
-    if (row_ok && (unsigned)(ri + 1) < (unsigned)g.ni) ownB = *(own_ptr + si);
-    uint32_t prev_lo = TRI_NONE;         // own result of step s-1                                  -> m=0
-    // words read from the exchange array in earlier steps, rolled through registers:
-    //   R1(s) = lane(a-1,b  )@s-1 = (ri,   rj-1, rk  )   m=1 now, m=2 one step later
-    //   R3(s) = lane(a,  b-1)@s-1 = (ri,   rj,   rk-1)   m=3 now, m=4 one step later
-    //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)   m=5 one step later, m=6 two steps later
-    uint32_t r1_old = TRI_NONE, r3_old = TRI_NONE, r5_old = TRI_NONE, r5_old2 = TRI_NONE;
-
-    auto step = [&](const int s, uint64_t &own) {
-        const int pbase = ((s & 1) ^ 1) * RSTRIDE;
-        const uint64_t self = own;
-        uint64_t *const self_ptr = own_ptr;
-        if (row_ok && (unsigned)(ri + 2) < (unsigned)g.ni) own = *(own_ptr + 2 * si);  // the cell two steps ahead
-        if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(own_ptr + 48 * si));
-        own_ptr += si;
-        uint32_t cur = cell_lo(self);
-        float phi = cell_phi(self);
-        const uint32_t r1 = sh.ring[pbase + idx1], r3 = sh.ring[pbase + idx3], r5 = sh.ring[pbase + idx5];
-        const bool in_row = row_ok && (unsigned)ri < (unsigned)g.ni;
-        const bool update = in_row && ri >= 1;
-        const uint32_t nb[7] = {prev_lo, r1, r1_old, r3, r3_old, r5_old, r5_old2};
-        uint32_t live = 0;               // bit m: neighbour m's triangle must be evaluated
-        if (update) {
-            // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this
-            // voxel last looked at offset m.  The last voxel of a row lies on a grid face: some sweeps never
-            // visit it, so "already examined" cannot be inferred from stamps there -> no memo.
-            if (interior_row && ri != g.ni - 1) {
-                #pragma unroll
-                for (int m = 0; m < 7; ++m) {
-                    const uint32_t x = nb[m];
-                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (x >= THR(m));
-                    live |= keep ? (1u << m) : 0u;
-                }
-            } else {
-                #pragma unroll
-                for (int m = 0; m < 7; ++m) {
-                    const uint32_t x = nb[m];
-                    const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0);
-                    live |= keep ? (1u << m) : 0u;
-                }
-            }
-            if (live) {                  // drop repeats of ANY earlier neighbour's triangle: that triangle is
-                #pragma unroll           // either evaluated there, or the voxel's own, or a known loser (memo)
-                for (int m = 1; m < 7; ++m) {
-                    bool dup = false;
-                    #pragma unroll
-                    for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
-                    if (dup) live &= ~(1u << m);
-                }
-            }
-        }
-        r1_old = r1; r3_old = r3; r5_old2 = r5_old; r5_old = r5;
-        const int ncand = __popc(live);
-        // ---- warp queue: exclusive scan of the candidate counts (3 ballots: ncand <= 7) ----------------
-        const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
-                       b2 = __ballot_sync(0xffffffffu, ncand & 4);
-        if (b0 | b1 | b2) {
-            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-            if (live) {
-                int w = off;
-                #pragma unroll
-                for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
-                    q_ent[w] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++w;
-                    const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);     // start the gather now
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
-                }
-            }
-            __syncwarp();
-            for (int q = lane; q < total; q += 32) {
-                const uint32_t e = q_ent[q];
-                const int otid = (warp << 5) + (int)(e >> 27);       // owner lane -> its voxel
-                const int oa = otid % EJ, ob = otid / EJ;
-                const int ori = s - oa - ob - SHIFT;
-                const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
-                const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
-                const TriRec *tr = &rec[e & TRI_MASK];
-                const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
-                q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
-                ++my_evals;
-            }
-            __syncwarp();
-            if (live) {
-                uint32_t best = TRI_NONE;
-                for (int q = off; q < off + ncand; ++q) {            // the reference's order and strict "<"
-                    const float d = q_d[q];
-                    if (d < phi) { phi = d; best = q_ent[q] & TRI_MASK; }
-                }
-                if (best != TRI_NONE) {
-                    cur = (P.stamp << 27) | best;
-                    *self_ptr = pack_cell(phi, cur);
-                    ++my_changed;
-                }
-            }
-            __syncwarp();
-        }
-        if (in_row) { sh.ring[(s & 1) * RSTRIDE + widx] = cur; prev_lo = cur; }
-        bar_step();
-        ++ri;
-    };
+    if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
+    if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        step(s, ownA);
-        step(s + 1, ownB);
+        compute_step<0>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, ownA, st);
+        compute_step<1>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, ownB, st);
     }
+    my_changed += st.changed; my_evals += st.evals;
 }
 
 #ifndef SDFB_MINB
-#define SDFB_MINB 3
+#define SDFB_MINB 2
 #endif
 __global__ void __launch_bounds__(NTHREADS, SDFB_MINB)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
