@@ -34,6 +34,8 @@
 // because phi only decreases), pushes the survivors to a per-warp queue in shared memory, the 32
 // lanes evaluate the queue round-robin, and each owner then replays its own results in the
 // reference's order with the reference's strict "<".
+#include <cstdio>
+#include <cstdlib>
 #include "sdfb_kernels.cuh"
 #include "sdfb_sweep_common.cuh"
 
@@ -59,6 +61,7 @@ struct ColParams {
     int steps;                               // steps per column = ni + EJ + EK, rounded up to even
     uint32_t stamp;                          // sweep_index + 1
     uint32_t epoch;                          // progress values are epoch<<16 | steps_done
+    unsigned long long *trace;               // debug builds (-DSDFB_TRACE) only: per-warp step timestamps
     uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
 };
 
@@ -69,6 +72,12 @@ __device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1
 // named barriers: 0 = __syncthreads (column hand-over), 1 = per-step (all 320 lanes), 2 = halo warps only
 __device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 __device__ __forceinline__ void bar_halo() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+
+#ifdef SDFB_TRACE
+#define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && blockIdx.x == 0) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(P, warp, s, slot) do { } while (0)
+#endif
 
 struct ColShared {
     uint32_t ring[2 * RSTRIDE];
@@ -122,12 +131,15 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
             if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
         }
         for (int s = s0; s < s1; s += 2) {                 // PUBLISH and P.steps are even
+            TRACE(P, 8 + (h >> 5), s, 0);
             if (row_ok) {
                 sh.ring[widx] = cell_lo(wA);               // even step -> slot 0
                 wA = ~0ull;
                 if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
             }
+            TRACE(P, 8 + (h >> 5), s, 1);
             bar_step();
+            TRACE(P, 8 + (h >> 5), s + 1, 0);
             if (row_ok) {
                 sh.ring[RSTRIDE + widx] = cell_lo(wB);     // odd step -> slot 1
                 wB = ~0ull;
@@ -136,6 +148,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
                 if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
             }
+            TRACE(P, 8 + (h >> 5), s + 1, 1);
             bar_step();
         }
         if (h == 63) {          // all stores of steps < s1 were issued before the last bar_step
@@ -253,6 +266,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     const int ni = P.g.ni;
     const int64_t si = (int64_t)P.sd.di;
     const int ri = st.ri;
+    TRACE(P, warp, s, 0);
     const uint32_t *rr = ring_r + (PAR ^ 1) * RSTRIDE;
     const uint32_t r5 = rr[0], r3 = rr[1], r1 = rr[EJ + 1];
     const uint64_t self = own;
@@ -280,6 +294,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     if (row_ok && (unsigned)ri < (unsigned)ni) { ring_w[PAR * RSTRIDE] = cur; st.prev_lo = cur; }
     st.own_ptr = self_ptr + si;
     st.ri = ri + 1;
+    TRACE(P, warp, s, 1);
     bar_step();
 }
 
@@ -411,6 +426,15 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
             if ((!ci || d.di == P.sd.di) && (!cj || d.dj == P.sd.dj) && (!ck || d.dk == P.sd.dk)) { P.last[m] = (uint8_t)(e + 1); break; }
         }
     }
+#ifdef SDFB_TRACE
+    static unsigned long long *trace_buf = nullptr;
+    const size_t trace_n = (size_t)10 * 8192 * 2;
+    if (getenv("SDFB_TRACE") && P.steps <= 8192) {
+        if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long));
+        cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), st);
+        P.trace = trace_buf;
+    }
+#endif
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -421,6 +445,18 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     int ncols = P.NJ * P.NK;
     if (grid > ncols) grid = ncols;
     k_sweep_columns<<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
+#ifdef SDFB_TRACE
+    if (P.trace) {
+        cudaStreamSynchronize(st);
+        unsigned long long *h = (unsigned long long *)malloc(trace_n * sizeof(unsigned long long));
+        cudaMemcpy(h, trace_buf, trace_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        char name[256];
+        snprintf(name, sizeof(name), "%s.%d.bin", getenv("SDFB_TRACE"), sweep_index);
+        FILE *f = fopen(name, "wb");
+        if (f) { fwrite(h, sizeof(unsigned long long), trace_n, f); fclose(f); }
+        free(h);
+    }
+#endif
     return 1;
 }
 
