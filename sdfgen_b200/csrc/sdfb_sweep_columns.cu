@@ -61,6 +61,7 @@ struct ColParams {
     int steps;                               // steps per column = ni + EJ + EK, rounded up to even
     uint32_t stamp;                          // sweep_index + 1
     uint32_t epoch;                          // progress values are epoch<<16 | steps_done
+    int trace_col;                           // ticket of the column to trace
     unsigned long long *trace;               // debug builds (-DSDFB_TRACE) only: per-warp step timestamps
     uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
 };
@@ -74,7 +75,7 @@ __device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n
 __device__ __forceinline__ void bar_halo() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 
 #ifdef SDFB_TRACE
-#define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && blockIdx.x == 0) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
+#define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
 #else
 #define TRACE(P, warp, s, slot) do { } while (0)
 #endif
@@ -433,6 +434,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
         if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), st);
         P.trace = trace_buf;
+        P.trace_col = getenv("SDFB_TRACE_COL") ? atoi(getenv("SDFB_TRACE_COL")) : (P.NJ * P.NK) / 2;
     }
 #endif
     int dev = 0, sms = 148;
