@@ -45,7 +45,9 @@ namespace {
 
 constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
 constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
-constexpr int NTHREADS = NCOMPUTE + 64;      // + 2 halo warps
+constexpr int NHALO = 64;                    // 2 halo warps
+constexpr int NSTEPPERS = NCOMPUTE + NHALO;  // lanes that take part in the per-step barrier
+constexpr int NTHREADS = NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
 #ifndef SDFB_PUBLISH
 #define SDFB_PUBLISH 2
 #endif
@@ -70,9 +72,8 @@ struct ColParams {
 constexpr int RSTRIDE = (EK + 1) * (EJ + 1);
 __device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1) + (a + 1); }
 
-// named barriers: 0 = __syncthreads (column hand-over), 1 = per-step (all 320 lanes), 2 = halo warps only
-__device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
-__device__ __forceinline__ void bar_halo() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+// named barriers: 0 = __syncthreads (column hand-over, all 352 threads), 1 = per-step (compute + halo lanes)
+__device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NSTEPPERS) : "memory"); }
 
 #ifdef SDFB_TRACE
 #define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
@@ -85,53 +86,74 @@ struct ColShared {
     uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
     float q_d[NCOMPUTE / 32][QCAP];
     int col;
+    volatile int go;        // chunks cleared to run (their upstream words are published); written by the sync warp
+    volatile int done;      // chunks whose steps are complete; written by compute lane 0
 };
+
+// ---- sync warp: keeps flag polling and progress publication off the step loop's critical path ----------
+// Lane 0 only.  Chunk c = steps [c*PUBLISH, (c+1)*PUBLISH).  A halo lane loads at step s the word of virtual
+// step s+2, produced by column (J-1,K) lane (EJ-1,b) at its step s+2+EJ, so chunk c may run once the left
+// column has completed s1-1+EJ+3 steps (EK for the column below; the diagonal column is covered transitively,
+// because the left column itself waited for it).  Chunks are cleared a little ahead of need through sh.go;
+// finished chunks (sh.done, set after the chunk's last step barrier) are fenced and published at once.
+__device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, const uint32_t *prog_left,
+                                            const uint32_t *prog_down, uint32_t *prog_mine)
+{
+    const uint32_t ebase = P.epoch << 16;
+    const int nchunks = P.steps / PUBLISH;
+    int cleared = 0, published = 0;                        // counts of chunks
+    while (published < nchunks) {
+        if (cleared < nchunks && cleared < published + 3) {
+            const int s1 = (cleared + 1) * PUBLISH;
+            const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
+            const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
+            if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) {
+                __threadfence();                           // acquire side: order the halo loads after the flag reads
+                sh.go = ++cleared;
+                continue;                                  // try to clear further ahead before sleeping
+            }
+        }
+        const int d = sh.done;
+        if (d > published) {
+            __threadfence();                               // release: the chunk's stores happen-before the flag
+            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+            published = d;
+        } else {
+            __nanosleep(20);
+        }
+    }
+}
 
 // ---- halo warps: feed the words of the upstream columns / boundary faces into the exchange array ----
 __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const ColParams &P, ColShared &sh,
-                                            int h, int rj0, int rk0, const uint32_t *prog_left,
-                                            const uint32_t *prog_down, uint32_t *prog_mine)
+                                            int h, int rj0, int rk0)
 {
     const Grid &g = P.g;
     int a, b;
     if (h <= EK) { a = -1; b = h - 1; }                    // (-1,-1), (-1,0) .. (-1,EK-1)
     else if (h <= EK + EJ) { a = h - EK - 1; b = -1; }     // (0,-1) .. (EJ-1,-1)
-    else { a = -2; b = -2; }                               // idle lanes (h = 63 publishes progress)
+    else { a = -2; b = -2; }                               // idle lanes
     const int rj = rj0 + a, rk = rk0 + b;
     const bool row_ok = (a > -2) && rj <= g.nj - 1 && rk <= P.rk_last;
     const int64_t si = (int64_t)P.sd.di;
     const uint64_t *ptr = cells;
     if (row_ok) ptr = cells + g.cidx(P.sd.abs_i(0, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g)) + si * (int64_t)(0 - a - b - SHIFT);
     const int widx = row_ok ? ring_idx(a, b) : 0;
-    const uint32_t ebase = P.epoch << 16;
     int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
     // Raw cells of virtual steps s (even -> wA, odd -> wB), each loaded two steps before it is published.
     // The step loop is unrolled by two so that a register is reloaded right after it was consumed and
     // never copied: a copy (or a select) of a freshly loaded value would stall on the load at once.
     uint64_t wA = ~0ull, wB = ~0ull;
-    for (int s0 = 0; s0 < P.steps; s0 += PUBLISH) {
-        const int s1 = min(s0 + PUBLISH, P.steps);
-        // Lane (-1,b) loads at step s the word of virtual step s+2, produced by column (J-1,K) lane
-        // (EJ-1,b) at its step s+2+EJ  =>  needs steps_done >= s+EJ+3; same with EK for (a,-1); the
-        // diagonal column is covered transitively.  Relaxed polls (an acquire load would invalidate
-        // this SM's L1 on every poll), one fence once both flags are seen.
-        if (h == 0) {
-            if (prog_left) {
-                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3);
-                while (*reinterpret_cast<const volatile uint32_t *>(prog_left) < need) __nanosleep(20);
-            }
-            if (prog_down) {
-                const uint32_t need = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3);
-                while (*reinterpret_cast<const volatile uint32_t *>(prog_down) < need) __nanosleep(20);
-            }
-            __threadfence();
-        }
-        bar_halo();
+    for (int s0 = 0, c = 0; s0 < P.steps; s0 += PUBLISH, ++c) {
+        const int s1 = s0 + PUBLISH;                       // P.steps is a multiple of PUBLISH
+        if ((h & 31) == 0) { while (sh.go <= c) { } }      // wait until chunk c is cleared (shared-memory spin)
+        __syncwarp();
+        __threadfence_block();
         if (s0 == 0 && row_ok) {
             if ((unsigned)ri < (unsigned)g.ni) wA = __ldcg(ptr);
             if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
         }
-        for (int s = s0; s < s1; s += 2) {                 // PUBLISH and P.steps are even
+        for (int s = s0; s < s1; s += 2) {                 // PUBLISH is even
             TRACE(P, 8 + (h >> 5), s, 0);
             if (row_ok) {
                 sh.ring[widx] = cell_lo(wA);               // even step -> slot 0
@@ -151,10 +173,6 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
             }
             TRACE(P, 8 + (h >> 5), s + 1, 1);
             bar_step();
-        }
-        if (h == 63) {          // all stores of steps < s1 were issued before the last bar_step
-            __threadfence();
-            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)s1;
         }
     }
 }
@@ -336,6 +354,10 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
         compute_step<0>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, ownA, st);
         compute_step<1>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, ownB, st);
+        if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
+            __threadfence_block();
+            sh.done = (s + 2) / PUBLISH;
+        }
     }
     my_changed += st.changed; my_evals += st.evals;
 }
@@ -355,7 +377,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
 
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
-        if (tid == 0) sh.col = (int)atomicAdd(ticket, 1u);
+        if (tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.go = 0; sh.done = 0; }
         __syncthreads();
         const int tk = sh.col;
         if (tk >= ncols) break;
@@ -372,10 +394,12 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
         if (tid < NCOMPUTE) {
             compute_column(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
-        } else {
+        } else if (tid < NSTEPPERS) {
+            halo_column(cells, P, sh, tid - NCOMPUTE, rj0, rk0);
+        } else if (tid == NSTEPPERS) {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
-            halo_column(cells, P, sh, tid - NCOMPUTE, rj0, rk0, prog_left, prog_down, &progress[K * P.NJ + J]);
+            sync_column(P, sh, prog_left, prog_down, &progress[K * P.NJ + J]);
         }
         __syncthreads();        // sh.col is rewritten next; also orders the two roles' exits
     }
@@ -414,7 +438,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     P.rk_first = rk_lo; P.rk_last = rk_hi;
     P.NJ = (g.nj - 1 + EJ - 1) / EJ;
     P.NK = (rk_hi - rk_lo + 1 + EK - 1) / EK;
-    P.steps = (g.ni + EJ + EK - 2 + SHIFT + 1) & ~1;   // even: the step loops are unrolled by two
+    P.steps = (g.ni + EJ + EK - 2 + SHIFT + PUBLISH - 1) / PUBLISH * PUBLISH;   // whole chunks (PUBLISH is even: the step loops are unrolled by two)
     P.stamp = (uint32_t)min(sweep_index + 1, 31);
     // the epoch grows with every launch on a plan between resets of the progress array (host side)
     P.epoch = epoch;
@@ -429,7 +453,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     }
 #ifdef SDFB_TRACE
     static unsigned long long *trace_buf = nullptr;
-    const size_t trace_n = (size_t)10 * 8192 * 2;
+    const size_t trace_n = (size_t)11 * 8192 * 2;
     if (getenv("SDFB_TRACE") && P.steps <= 8192) {
         if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), st);
