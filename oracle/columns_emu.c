@@ -62,14 +62,15 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
     const int NJ = (nj - 1 + EJ - 1) / EJ, NK = (rk_last - rk_first + 1 + EK - 1) / EK;
     const int steps = (ni + EJ + EK - 2 + SHIFT + 1) & ~1;
     const uint32_t stamp = (uint32_t)imin(sweep_index + 1, 31);
-    uint8_t last[7];
-    for (int m = 0; m < 7; ++m) {
-        last[m] = 0;
+    uint8_t last[8][7];
+    for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
+        last[c][m] = 0;
         if (sweep_index + 1 > 31) continue;
         int ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
         for (int e = sweep_index - 1; e >= 0; --e) {
             const int *d = DIRS[e % 8];
-            if ((!ci || d[0] == di) && (!cj || d[1] == dj) && (!ck || d[2] == dk)) { last[m] = (uint8_t)(e + 1); break; }
+            int same_i = d[0] == di, same_j = d[1] == dj, same_k = d[2] == dk;
+            if ((!(ci || (c & 1)) || same_i) && (!(cj || (c & 2)) || same_j) && (!(ck || (c & 4)) || same_k)) { last[c][m] = (uint8_t)(e + 1); break; }
         }
     }
     const int64_t ncell = (int64_t)ni * nj * (k_hi - k_lo + 2);
@@ -88,7 +89,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
         int J, K;
         { int d = 0, rem = tk; for (;;) { int lo = imax(0, d - (NK - 1)), hi = imin(d, NJ - 1), cnt = hi - lo + 1; if (rem < cnt) { J = lo + rem; K = d - J; break; } rem -= cnt; ++d; } }
         const int rj0 = 1 + J * EJ, rk0 = rk_first + K * EK;
-        int A[NLANES], B[NLANES], row_ok[NLANES], interior_row[NLANES];
+        int A[NLANES], B[NLANES], row_ok[NLANES];
         int64_t c_row[NLANES];
         uint64_t own_next_phi_lo[NLANES];   /* packed like the device: phi bits << 32 | lo */
         uint32_t halo_w1[NLANES], halo_next[NLANES], prev_lo[NLANES], r1_old[NLANES], r3_old[NLANES], r5_old[NLANES], r5_old2[NLANES];
@@ -99,11 +100,10 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
             A[tid] = a; B[tid] = b;
             int rj = rj0 + a, rk = rk0 + b;
             row_ok[tid] = (a > -2) && rj <= nj - 1 && rk <= rk_last;
-            c_row[tid] = 0; interior_row[tid] = 0;
+            c_row[tid] = 0;
             if (row_ok[tid]) {
                 int j = ABS_J(rj), k = ABS_K(rk);
                 c_row[tid] = cidx(g, ABS_I(0), j, k);
-                interior_row[tid] = (j >= 1 && j <= nj - 2 && k >= 1 && k <= nk - 2);
             }
             own_next_phi_lo[tid] = 0; halo_next[tid] = TRI_NONE; prev_lo[tid] = TRI_NONE;
             r1_old[tid] = r3_old[tid] = r5_old[tid] = r5_old2[tid] = TRI_NONE;
@@ -169,13 +169,13 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                         uint32_t nb[7] = { prev_lo[tid], r1, r1_old[tid], r3, r3_old[tid], r5_old[tid], r5_old2[tid] };
                         int i = ABS_I(ri);
                         int i_interior = (i >= 1 && i <= ni - 2);
-                        int edge = (ri == ni - 1);   /* same as !i_interior: ri=0 is never updated */
                         (void)i_interior;
+                        int cls = (ri == ni - 1 ? 1 : 0) | (rj0 + a == nj - 1 ? 2 : 0) | (rk0 + b == nk - 1 ? 4 : 0);
                         uint32_t live = 0;
                         for (int m = 0; m < 7; ++m) {
                             uint32_t xw = nb[m];
-                            uint32_t thr = (interior_row[tid] && last[m] != 0) ? ((uint32_t)last[m] + 1u) << 27 : 0u;
-                            int keep = ((xw & TRI_MASK) != TRI_NONE) && (((xw ^ cur) & TRI_MASK) != 0) && (edge || xw >= thr);
+                            uint32_t thr = last[cls][m] ? ((uint32_t)last[cls][m] + 1u) << 27 : 0u;
+                            int keep = ((xw & TRI_MASK) != TRI_NONE) && (((xw ^ cur) & TRI_MASK) != 0) && (xw >= thr);
                             if (keep) live |= 1u << m;
                         }
                         if (live) {

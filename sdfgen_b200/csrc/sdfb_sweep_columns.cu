@@ -65,7 +65,11 @@ struct ColParams {
     uint32_t epoch;                          // progress values are epoch<<16 | steps_done
     int trace_col;                           // ticket of the column to trace
     unsigned long long *trace;               // debug builds (-DSDFB_TRACE) only: per-warp step timestamps
-    uint8_t last[8];                         // last[m]: stamp of the latest earlier sweep that examined offset m (0: none)
+    // last[c][m]: stamp (sweep index + 1) of the latest earlier sweep in which a voxel of class c examined
+    // neighbour offset m, 0 if none.  Class bits: 1 = last voxel of its row (ri = ni-1), 2 = last row
+    // (rj = nj-1), 4 = last plane (rk = nk-1): such voxels lie on a grid face and are only visited by sweeps
+    // whose direction along that axis equals the current one.
+    uint8_t last[8][8];
 };
 
 // smem exchange array: [2 slots][EK+1][EJ+1] words, index (b+1)*(EJ+1) + (a+1); a fastest
@@ -103,12 +107,13 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, c
     const int nchunks = P.steps / PUBLISH;
     int cleared = 0, published = 0;                        // counts of chunks
     while (published < nchunks) {
-        if (cleared < nchunks && cleared < published + 3) {
+        if (cleared < nchunks && cleared < sh.done + 4) {
             const int s1 = (cleared + 1) * PUBLISH;
             const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
             const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
             if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) {
-                __threadfence();                           // acquire side: order the halo loads after the flag reads
+                // no fence here: the halo lanes' loads are issued only after they have read sh.go (control
+                // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
                 sh.go = ++cleared;
                 continue;                                  // try to clear further ahead before sleeping
             }
@@ -280,7 +285,7 @@ template <int PAR>
 __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                              const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
                                              int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
-                                             uint64_t &own, LaneState &st)
+                                             const uint32_t (&thr_edge)[7], uint64_t &own, LaneState &st)
 {
     const int ni = P.g.ni;
     const int64_t si = (int64_t)P.sd.di;
@@ -295,17 +300,17 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
         asm volatile("prefetch.global.L2 [%0];" ::"l"(self_ptr + 48 * si));
     uint32_t cur = cell_lo(self);
     const bool update = row_ok && (unsigned)(ri - 1) < (unsigned)(ni - 1);            // 1 <= ri <= ni-1
-    // The last voxel of a row lies on a grid face: some sweeps never visit it, so "already examined" cannot
-    // be inferred from stamps there -> it always takes the full path (as do boundary rows: thr = 0).
+    // The last voxel of a row lies on the far i face: only sweeps with the same di visit it (thr_edge).
     const bool edge = (ri == ni - 1);
     const uint32_t nb[7] = {st.prev_lo, r1, st.r1_old, r3, st.r3_old, st.r5_old, st.r5_old2};
-    bool fresh = edge;
+    uint32_t t[7];
+    bool fresh = false;
     #pragma unroll
-    for (int m = 0; m < 7; ++m) fresh = fresh || (nb[m] >= thr[m]);
+    for (int m = 0; m < 7; ++m) { t[m] = edge ? thr_edge[m] : thr[m]; fresh = fresh || (nb[m] >= t[m]); }
     if (__any_sync(0xffffffffu, update && fresh)) {
-        const uint2 r = evaluate_candidates(rec, P, sh.q_ent[warp], sh.q_d[warp], s, lane, warp, rj0, rk0, update, edge,
+        const uint2 r = evaluate_candidates(rec, P, sh.q_ent[warp], sh.q_d[warp], s, lane, warp, rj0, rk0, update, false,
                                             nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
-                                            thr[0], thr[1], thr[2], thr[3], thr[4], thr[5], thr[6],
+                                            t[0], t[1], t[2], t[3], t[4], t[5], t[6],
                                             cur, self_ptr, cell_phi(self));
         cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
     }
@@ -327,21 +332,24 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     const int rj = rj0 + a, rk = rk0 + b;
     const bool row_ok = rj <= g.nj - 1 && rk <= P.rk_last;
     const int64_t si = (int64_t)P.sd.di;
-    bool interior_row = false;
     LaneState st;
     st.own_ptr = cells;
     st.ri = 0 - a - b - SHIFT;            // voxel of step 0
     if (row_ok) {
         const int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
         st.own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)st.ri;
-        interior_row = (j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2);
     }
     // memo thresholds: the neighbour word nb at offset m is fresh iff nb >= thr[m] = (last[m]+1) << 27, i.e.
-    // stamp(nb) > last[m]; 0 (always fresh) where the offset was never examined or the row is on the grid
-    // boundary (some sweeps skip it, so stamps prove nothing there)
-    uint32_t thr[7];
+    // stamp(nb) > last[m] (0 = always fresh where the offset was never examined).  Rows on the far j / k
+    // face use the table of their class; the last voxel of a row (far i face) has its own thresholds.
+    const int row_class = (rj == g.nj - 1 ? 2 : 0) | (rk == g.nk - 1 ? 4 : 0);
+    uint32_t thr[7], thr_edge[7];
     #pragma unroll
-    for (int m = 0; m < 7; ++m) thr[m] = (interior_row && P.last[m] != 0) ? ((uint32_t)P.last[m] + 1u) << 27 : 0u;
+    for (int m = 0; m < 7; ++m) {
+        const uint32_t l0 = P.last[row_class][m], l1 = P.last[row_class | 1][m];
+        thr[m] = l0 ? (l0 + 1u) << 27 : 0u;
+        thr_edge[m] = l1 ? (l1 + 1u) << 27 : 0u;
+    }
     const uint32_t *ring_r = sh.ring + ring_idx(a - 1, b - 1);     // R5 at +0, R3 at +1, R1 at +(EJ+1)
     uint32_t *ring_w = sh.ring + ring_idx(a, b);
     st.prev_lo = TRI_NONE; st.r1_old = TRI_NONE; st.r3_old = TRI_NONE; st.r5_old = TRI_NONE; st.r5_old2 = TRI_NONE;
@@ -352,8 +360,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        compute_step<0>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, ownA, st);
-        compute_step<1>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, ownB, st);
+        compute_step<0>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, st);
+        compute_step<1>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, st);
         if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
             __threadfence_block();
             sh.done = (s + 2) / PUBLISH;
@@ -442,13 +450,16 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     P.stamp = (uint32_t)min(sweep_index + 1, 31);
     // the epoch grows with every launch on a plan between resets of the progress array (host side)
     P.epoch = epoch;
-    for (int m = 0; m < 7; ++m) {
-        P.last[m] = 0;
+    for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
+        P.last[c][m] = 0;
         if (sweep_index + 1 > 31) continue;           // stamps saturate: no memo beyond 31 sweeps
         const bool ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
         for (int e = sweep_index - 1; e >= 0; --e) {
             SweepDir d = SweepDir::of(e);
-            if ((!ci || d.di == P.sd.di) && (!cj || d.dj == P.sd.dj) && (!ck || d.dk == P.sd.dk)) { P.last[m] = (uint8_t)(e + 1); break; }
+            // sweep e examined offset m (same direction along the offset's axes) and visited a voxel of class c
+            // (same direction along every axis on whose far face the voxel lies)
+            const bool same_i = d.di == P.sd.di, same_j = d.dj == P.sd.dj, same_k = d.dk == P.sd.dk;
+            if ((!(ci || (c & 1)) || same_i) && (!(cj || (c & 2)) || same_j) && (!(ck || (c & 4)) || same_k)) { P.last[c][m] = (uint8_t)(e + 1); break; }
         }
     }
 #ifdef SDFB_TRACE
