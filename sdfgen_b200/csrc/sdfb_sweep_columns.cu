@@ -257,9 +257,17 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
         const int ori = s - oa - ob - SHIFT;
         const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
         const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+#if defined(SDFB_WHATIF) && SDFB_WHATIF == 1        /* timing experiment only: no gather */
+        const TriRec *tr = &rec[(e & TRI_MASK) & 1023];
+#else
         const TriRec *tr = &rec[e & TRI_MASK];
+#endif
         const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+#if defined(SDFB_WHATIF) && SDFB_WHATIF == 2        /* timing experiment only: no distance arithmetic */
+        q_d[q] = fadd(fadd(fmul(gx.x, p.x), fmul(gx.y, qq.y)), fmul(gx.z, r.z));
+#else
         q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+#endif
         ++evals;
     }
     __syncwarp();
