@@ -99,7 +99,7 @@ int sdfb_plan_set_mesh_device(sdfb_plan *plan, const uint32_t *d_tri, uint64_t n
 int sdfb_plan_band(sdfb_plan *plan, const float origin[3], float dx, int32_t exact_band, void *stream);
 /* Phase B: sweeps first..first+count-1 of the reference's 16 (index s uses direction s%8 of
  * cpu_lib/makelevelset3.cpp:245-248).  Asynchronous.  Halo planes, if the slab has neighbours, must
- * have been filled by the caller (sdfb_plan_halo_ptrs) before each call. */
+ * have been filled by the caller (sdfb_plan_device_ptrs + sdfb_plan_halo_refresh) before each call. */
 int sdfb_plan_sweep(sdfb_plan *plan, int32_t first, int32_t count, void *stream);
 /* Phase C: parity sign + unpack to the float output (cpu_lib/makelevelset3.cpp:295-303). Asynchronous. */
 int sdfb_plan_sign(sdfb_plan *plan, void *stream);
@@ -109,6 +109,10 @@ int sdfb_plan_run(sdfb_plan *plan, const float origin[3], float dx, int32_t exac
 /* Device pointers (valid until destroy): cells uint64[(k_hi-k_lo+2) planes], the first and last
  * plane being the halos; counts int32[slab]; phi float[slab] (layout per plan flags). */
 int sdfb_plan_device_ptrs(sdfb_plan *plan, void **cells, void **counts, void **phi);
+/* Multi-GPU: call after new contents were written into the two halo planes (plane 0 and plane
+ * k_hi-k_lo+1 of `cells`) and before the next sdfb_plan_sweep.  Marks the received cells as freshly
+ * changed so the sweep re-examines them (their previous copy may have been stale). Asynchronous. */
+int sdfb_plan_halo_refresh(sdfb_plan *plan, void *stream);
 /* Number of cells whose closest triangle changed during the sweeps since the last sdfb_plan_band or
  * sdfb_plan_changed call (synchronises the stream; used by the multi-GPU fixed-point loop). */
 int sdfb_plan_changed(sdfb_plan *plan, void *stream, uint64_t *changed);

@@ -59,6 +59,8 @@ def lib():
     L.sdfb_plan_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.sdfb_plan_changed.restype = C.c_int
     L.sdfb_plan_changed.argtypes = [vp, vp, C.POINTER(u64)]
+    L.sdfb_plan_halo_refresh.restype = C.c_int
+    L.sdfb_plan_halo_refresh.argtypes = [vp, vp]
     L.sdfb_plan_counters.restype = C.c_int
     L.sdfb_plan_counters.argtypes = [vp, vp, C.POINTER(u64 * 2)]
     L.sdfb_plan_download.restype = C.c_int
@@ -153,6 +155,9 @@ class Plan:
         n = C.c_uint64()
         check(lib().sdfb_plan_changed(self._h, stream or None, C.byref(n)))
         return int(n.value)
+
+    def halo_refresh(self, stream=0):
+        check(lib().sdfb_plan_halo_refresh(self._h, stream or None))
 
     def counters(self, stream=0):
         """(changed cells, distance evaluations) of the sweeps since the last band/counters call."""

@@ -77,6 +77,7 @@ struct sdfb_plan {
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
     float *xyz_own = nullptr;
+    uint64_t tri_own_cap = 0, xyz_own_cap = 0;
     TriRec *rec = nullptr;
     uint32_t *units = nullptr;
     uint64_t *prefix = nullptr, *block_sums = nullptr;
@@ -93,6 +94,7 @@ void free_mesh(sdfb_plan *p)
     cudaFree(p->tri_own); cudaFree(p->xyz_own); cudaFree(p->rec); cudaFree(p->units);
     cudaFree(p->prefix); cudaFree(p->block_sums);
     p->tri_own = nullptr; p->xyz_own = nullptr; p->rec = nullptr; p->units = nullptr;
+    p->tri_own_cap = 0; p->xyz_own_cap = 0;
     p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0; p->have_mesh = false;
 }
 
@@ -204,9 +206,16 @@ int sdfb_plan_set_mesh_host(sdfb_plan *p, const uint32_t *tri, uint64_t ntri, co
     if (ntri > SDFB_MAX_TRIANGLES) return fail(SDFB_ERR_LIMIT, "%llu triangles exceed the limit of %u", (unsigned long long)ntri, SDFB_MAX_TRIANGLES);
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaFree(p->tri_own); cudaFree(p->xyz_own); p->tri_own = nullptr; p->xyz_own = nullptr;
-    CU(cudaMalloc(&p->tri_own, (ntri ? ntri : 1) * 3 * sizeof(uint32_t)));
-    CU(cudaMalloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
+    if (ntri > p->tri_own_cap || !p->tri_own) {      // grow-only staging buffers: repeated calls do not reallocate
+        cudaFree(p->tri_own); p->tri_own = nullptr; p->tri_own_cap = 0;
+        CU(cudaMalloc(&p->tri_own, (ntri ? ntri : 1) * 3 * sizeof(uint32_t)));
+        p->tri_own_cap = ntri ? ntri : 1;
+    }
+    if (nvert > p->xyz_own_cap || !p->xyz_own) {
+        cudaFree(p->xyz_own); p->xyz_own = nullptr; p->xyz_own_cap = 0;
+        CU(cudaMalloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
+        p->xyz_own_cap = nvert ? nvert : 1;
+    }
     if (ntri) CU(cudaMemcpyAsync(p->tri_own, tri, ntri * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     if (nvert) CU(cudaMemcpyAsync(p->xyz_own, xyz, nvert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     return build_records(p, p->tri_own, p->xyz_own, ntri, nvert, st);
@@ -298,6 +307,15 @@ int sdfb_plan_device_ptrs(sdfb_plan *p, void **cells, void **counts, void **phi)
     if (cells) *cells = p->cells;
     if (counts) *counts = p->counts;
     if (phi) *phi = (p->flags & SDFB_OUT_KFASTEST) ? p->phi_k : p->phi;
+    return SDFB_OK;
+}
+
+int sdfb_plan_halo_refresh(sdfb_plan *p, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    DeviceGuard dg(p->device);
+    g_launches += launch_halo_refresh(p->cells, p->g, (cudaStream_t)stream);
+    CU(cudaGetLastError());
     return SDFB_OK;
 }
 

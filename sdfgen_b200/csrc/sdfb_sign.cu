@@ -64,7 +64,25 @@ __global__ void __launch_bounds__(256) k_relayout(const uint32_t *__restrict__ s
     }
 }
 
+// Halo planes received from a neighbouring slab: raise the stamp to the maximum so that the sweep's
+// "unchanged since I last looked" memo never skips them (the copy this slab looked at may have been stale).
+__global__ void __launch_bounds__(256) k_halo_refresh(uint64_t *__restrict__ cells, int64_t plane, int64_t far_off)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < 2 * plane; v += stride) {
+        uint64_t *c = cells + (v < plane ? v : far_off + (v - plane));
+        uint64_t x = *c;
+        if ((cell_lo(x) & TRI_MASK) != TRI_NONE) *c = x | ((uint64_t)31u << 27);
+    }
+}
+
 }  // namespace
+
+int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st)
+{
+    k_halo_refresh<<<148 * 2, 256, 0, st>>>(cells, g.plane(), g.plane() * (int64_t)(g.nkl() + 1));
+    return 1;
+}
 
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st)

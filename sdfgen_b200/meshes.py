@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["icosphere", "uv_sphere", "blob", "torus", "unit_cube", "shuffle_triangles",
+__all__ = ["icosphere", "uv_sphere", "blob", "torus", "unit_cube", "shuffle_triangles", "stacked_workload",
            "workload", "WORKLOADS"]
 
 
@@ -166,3 +166,20 @@ def workload(name: str, n: int | None = None, shuffle: bool = False):
     origin, dx = _placed(n, L)
     return dict(name=name, vertices=np.ascontiguousarray(v), triangles=np.ascontiguousarray(f),
                 origin=origin, dx=float(dx), ni=n, nj=n, nk=n)
+
+
+def stacked_workload(copies: int, n: int = 512, level: int = 8):
+    """Weak-scaling workload for `copies` GPUs: `copies` icospheres (level 8, radius 0.4 L, the C2 mesh)
+    stacked along z, one per n^3 block of an n x n x (copies*n) grid.  With z-slab sharding every rank gets
+    one block and one sphere's worth of surface, so per-GPU work equals the single-GPU C2 configuration."""
+    L = 1.0
+    v0, f0 = icosphere(level, 0.4 * L)
+    vs, fs = [], []
+    for g in range(copies):
+        vs.append(v0 + np.array([0.0, 0.0, g * L], dtype=np.float32))
+        fs.append(f0 + np.uint32(g * v0.shape[0]))
+    v = np.ascontiguousarray(np.concatenate(vs, axis=0), dtype=np.float32)
+    f = np.ascontiguousarray(np.concatenate(fs, axis=0), dtype=np.uint32)
+    origin, dx = _placed(n, L)
+    return dict(name=f"c2_icosphere_{n}_stack{copies}", vertices=v, triangles=f, origin=origin, dx=float(dx),
+                ni=n, nj=n, nk=n * copies)
