@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.5)
 
     def stop(self):
         self._stop_evt.set()
