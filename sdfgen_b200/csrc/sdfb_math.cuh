@@ -36,7 +36,10 @@ __device__ __forceinline__ double max_std(double a, double b) { return (a < b) ?
 // innocuous and equals the correctly rounded float quotient (checked exhaustively-at-random on the
 // CPU, tests/test_oracle.py::test_float_div_equals_narrowed_double_div), so one fp32 IEEE divide is
 // used here instead of an fp64 one.
-__device__ __forceinline__ float seg_distance(F3 x0, F3 x1, F3 x2)
+// Returns the SQUARED distance; the callers take one square root of the smaller of two candidates, which
+// is bit-identical to the reference's min(sqrt(a), sqrt(b)): sqrt is monotone and correctly rounded, and the
+// std::min tie/NaN ordering is the same on the squares (a NaN operand wins or loses identically).
+__device__ __forceinline__ float seg_distance2(F3 x0, F3 x1, F3 x2)
 {
     F3 e = sub3(x2, x1);
     float m2 = mag2_3(e);
@@ -46,8 +49,9 @@ __device__ __forceinline__ float seg_distance(F3 x0, F3 x1, F3 x2)
     F3 p = F3{ fadd(fmul(s12, x1.x), fmul(om, x2.x)),
                fadd(fmul(s12, x1.y), fmul(om, x2.y)),
                fadd(fmul(s12, x1.z), fmul(om, x2.z)) };
-    return dist3(x0, p);
+    return mag2_3(sub3(x0, p));
 }
+__device__ __forceinline__ float seg_distance(F3 x0, F3 x1, F3 x2) { return __fsqrt_rn(seg_distance2(x0, x1, x2)); }
 
 // cpu_lib/makelevelset3.cpp:49-70
 __device__ __forceinline__ float point_triangle_distance(F3 x0, F3 x1, F3 x2, F3 x3)
@@ -59,18 +63,20 @@ __device__ __forceinline__ float point_triangle_distance(F3 x0, F3 x1, F3 x2, F3
     float w23 = fmul(invdet, fsub(fmul(m23, a), fmul(d, b)));
     float w31 = fmul(invdet, fsub(fmul(m13, b), fmul(d, a)));
     float w12 = fsub(fsub(1.f, w23), w31);
+    float d2;
     if (w23 >= 0.f && w31 >= 0.f && w12 >= 0.f) {
         F3 p = F3{ fadd(fadd(fmul(w23, x1.x), fmul(w31, x2.x)), fmul(w12, x3.x)),
                    fadd(fadd(fmul(w23, x1.y), fmul(w31, x2.y)), fmul(w12, x3.y)),
                    fadd(fadd(fmul(w23, x1.z), fmul(w31, x2.z)), fmul(w12, x3.z)) };
-        return dist3(x0, p);
+        d2 = mag2_3(sub3(x0, p));
     } else if (w23 > 0.f) {
-        return min_std(seg_distance(x0, x1, x2), seg_distance(x0, x1, x3));
+        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x1, x3));
     } else if (w31 > 0.f) {
-        return min_std(seg_distance(x0, x1, x2), seg_distance(x0, x2, x3));
+        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x2, x3));
     } else {
-        return min_std(seg_distance(x0, x1, x3), seg_distance(x0, x2, x3));
+        d2 = min_std(seg_distance2(x0, x1, x3), seg_distance2(x0, x2, x3));
     }
+    return __fsqrt_rn(d2);
 }
 
 // World position of lattice point c along one axis: float(c)*dx + origin  (cpu_lib/makelevelset3.cpp:214)
