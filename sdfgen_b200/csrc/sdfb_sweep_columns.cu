@@ -250,25 +250,17 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
         }
     }
     __syncwarp();
-    // two queue entries per lane and iteration: the two distance evaluations are independent dependency
-    // chains, which the scheduler interleaves (the warp count per SM is too low to hide them otherwise)
-    for (int q = lane; q < total; q += 64) {
-        const bool two = q + 32 < total;
-        const uint32_t e0 = q_ent[q], e1 = two ? q_ent[q + 32] : e0;
-        const int t0 = (warp << 5) + (int)(e0 >> 27), t1 = (warp << 5) + (int)(e1 >> 27);   // owner lanes -> their voxels
-        const int a0 = t0 % EJ, b0_ = t0 / EJ, a1 = t1 % EJ, b1_ = t1 / EJ;
-        const F3 g0{lattice(P.sd.abs_i(s - a0 - b0_ - SHIFT, g), g.dx, g.ox), lattice(P.sd.abs_j(rj0 + a0, g), g.dx, g.oy),
-                    lattice(P.sd.abs_k(rk0 + b0_, g), g.dx, g.oz)};
-        const F3 g1{lattice(P.sd.abs_i(s - a1 - b1_ - SHIFT, g), g.dx, g.ox), lattice(P.sd.abs_j(rj0 + a1, g), g.dx, g.oy),
-                    lattice(P.sd.abs_k(rk0 + b1_, g), g.dx, g.oz)};
-        const TriRec *r0 = &rec[e0 & TRI_MASK], *r1 = &rec[e1 & TRI_MASK];
-        const float4 p0 = __ldg(&r0->p), q0 = __ldg(&r0->q), s0 = __ldg(&r0->r);
-        const float4 p1 = __ldg(&r1->p), q1 = __ldg(&r1->q), s1 = __ldg(&r1->r);
-        const float d0 = point_triangle_distance(g0, F3{p0.x, p0.y, p0.z}, F3{q0.x, q0.y, q0.z}, F3{s0.x, s0.y, s0.z});
-        const float d1 = point_triangle_distance(g1, F3{p1.x, p1.y, p1.z}, F3{q1.x, q1.y, q1.z}, F3{s1.x, s1.y, s1.z});
-        q_d[q] = d0;
-        if (two) q_d[q + 32] = d1;
-        evals += two ? 2u : 1u;
+    for (int q = lane; q < total; q += 32) {
+        const uint32_t e = q_ent[q];
+        const int otid = (warp << 5) + (int)(e >> 27);               // owner lane -> its voxel
+        const int oa = otid % EJ, ob = otid / EJ;
+        const int ori = s - oa - ob - SHIFT;
+        const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
+        const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+        const TriRec *tr = &rec[e & TRI_MASK];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+        ++evals;
     }
     __syncwarp();
     if (live) {
