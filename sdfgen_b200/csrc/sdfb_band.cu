@@ -36,11 +36,9 @@ __global__ void k_tri_prep(const uint32_t *__restrict__ tri, const float *__rest
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntri) return;
     uint32_t p = tri[3 * t], q = tri[3 * t + 1], r = tri[3 * t + 2];
-    TriRec o;
-    o.p = make_float4(xyz[3 * (size_t)p], xyz[3 * (size_t)p + 1], xyz[3 * (size_t)p + 2], 0.f);
-    o.q = make_float4(xyz[3 * (size_t)q], xyz[3 * (size_t)q + 1], xyz[3 * (size_t)q + 2], 0.f);
-    o.r = make_float4(xyz[3 * (size_t)r], xyz[3 * (size_t)r + 1], xyz[3 * (size_t)r + 2], 0.f);
-    rec[t] = o;
+    rec[t] = make_tri_rec(F3{xyz[3 * (size_t)p], xyz[3 * (size_t)p + 1], xyz[3 * (size_t)p + 2]},
+                          F3{xyz[3 * (size_t)q], xyz[3 * (size_t)q + 1], xyz[3 * (size_t)q + 2]},
+                          F3{xyz[3 * (size_t)r], xyz[3 * (size_t)r + 1], xyz[3 * (size_t)r + 2]});
 }
 
 // Integer extents of one triangle on the grid: the exact-band box (cpu_lib/makelevelset3.cpp:206-212)
@@ -207,7 +205,6 @@ __global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, ui
             const uint32_t wi = b.i1 - b.i0 + 1, wj = b.j1 - b.j0 + 1;
             const uint64_t v0 = (uint64_t)local * UNIT;
             const uint64_t v1 = min(nvox, v0 + UNIT);
-            const F3 x1{tr.p.x, tr.p.y, tr.p.z}, x2{tr.q.x, tr.q.y, tr.q.z}, x3{tr.r.x, tr.r.y, tr.r.z};
             const bool small = nvox <= 0xffffffffull;   // 32-bit div/mod for all but absurd boxes
             for (uint64_t v = v0 + lane; v < v1; v += 32) {
                 uint32_t i, j, k;
@@ -219,7 +216,7 @@ __global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, ui
                     i = b.i0 + (uint32_t)(v - r * wi); k = (uint32_t)(r / wj); j = b.j0 + (uint32_t)(r - (uint64_t)k * wj); k += b.k0;
                 }
                 F3 gx{lattice(i, g.dx, g.ox), lattice(j, g.dx, g.oy), lattice(k, g.dx, g.oz)};
-                float d = point_triangle_distance(gx, x1, x2, x3);
+                float d = ptd_rec(gx, tr);
                 if (d < init_phi) {                       // also rejects NaN (degenerate triangles)
                     uint64_t cand = pack_cell(d, (uint32_t)t);
                     uint64_t *c = &cells[g.cidx(i, j, k)];

@@ -142,10 +142,49 @@ __device__ __forceinline__ int32_t  lo_tri_signed(uint32_t lo) { uint32_t t = lo
 
 // Per-triangle record: the three vertices pre-gathered as 3 x float4 (48 B, 16-byte aligned) so a
 // candidate evaluation is three LDG.128 instead of an index load plus three scattered 12-byte loads.
+// The three spare lanes carry per-triangle invariants of point_triangle_distance, computed once with the
+// same operations in the same order (so the bits are those of the reference): p.w = m13 = |x1-x3|^2,
+// q.w = m23 = |x2-x3|^2, r.w = invdet = 1/max(m13*m23 - d*d, 1e-30f)  (cpu_lib/makelevelset3.cpp:52-54).
 struct __align__(16) TriRec { float4 p, q, r; };
-__device__ __forceinline__ float ptd_rec(F3 gx, const TriRec &t)
+
+__device__ __forceinline__ TriRec make_tri_rec(F3 x1, F3 x2, F3 x3)
 {
-    return point_triangle_distance(gx, F3{t.p.x, t.p.y, t.p.z}, F3{t.q.x, t.q.y, t.q.z}, F3{t.r.x, t.r.y, t.r.z});
+    F3 x13 = sub3(x1, x3), x23 = sub3(x2, x3);
+    float m13 = mag2_3(x13), m23 = mag2_3(x23), d = dot3(x13, x23);
+    float invdet = __fdiv_rn(1.f, max_std(fsub(fmul(m13, m23), fmul(d, d)), 1e-30f));
+    TriRec t;
+    t.p = make_float4(x1.x, x1.y, x1.z, m13);
+    t.q = make_float4(x2.x, x2.y, x2.z, m23);
+    t.r = make_float4(x3.x, x3.y, x3.z, invdet);
+    return t;
 }
+
+// point_triangle_distance with the record's invariants (bit-identical to the full function)
+__device__ __forceinline__ float ptd_rec(F3 x0, float4 P, float4 Q, float4 R)
+{
+    const F3 x1{P.x, P.y, P.z}, x2{Q.x, Q.y, Q.z}, x3{R.x, R.y, R.z};
+    const float m13 = P.w, m23 = Q.w, invdet = R.w;
+    F3 x13 = sub3(x1, x3), x23 = sub3(x2, x3), x03 = sub3(x0, x3);
+    float d = dot3(x13, x23);
+    float a = dot3(x13, x03), b = dot3(x23, x03);
+    float w23 = fmul(invdet, fsub(fmul(m23, a), fmul(d, b)));
+    float w31 = fmul(invdet, fsub(fmul(m13, b), fmul(d, a)));
+    float w12 = fsub(fsub(1.f, w23), w31);
+    float d2;
+    if (w23 >= 0.f && w31 >= 0.f && w12 >= 0.f) {
+        F3 p = F3{ fadd(fadd(fmul(w23, x1.x), fmul(w31, x2.x)), fmul(w12, x3.x)),
+                   fadd(fadd(fmul(w23, x1.y), fmul(w31, x2.y)), fmul(w12, x3.y)),
+                   fadd(fadd(fmul(w23, x1.z), fmul(w31, x2.z)), fmul(w12, x3.z)) };
+        d2 = mag2_3(sub3(x0, p));
+    } else if (w23 > 0.f) {
+        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x1, x3));
+    } else if (w31 > 0.f) {
+        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x2, x3));
+    } else {
+        d2 = min_std(seg_distance2(x0, x1, x3), seg_distance2(x0, x2, x3));
+    }
+    return __fsqrt_rn(d2);
+}
+__device__ __forceinline__ float ptd_rec(F3 gx, const TriRec &t) { return ptd_rec(gx, t.p, t.q, t.r); }
 
 }  // namespace sdfb

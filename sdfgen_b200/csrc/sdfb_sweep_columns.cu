@@ -89,6 +89,7 @@ struct ColShared {
     uint32_t ring[2 * RSTRIDE];
     uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
     float q_d[NCOMPUTE / 32][QCAP];
+    float gx[NCOMPUTE], gy[NCOMPUTE], gz[NCOMPUTE];   // world position of each compute lane's current voxel
     int col;
     volatile int go;        // chunks cleared to run (their upstream words are published); written by the sync warp
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
@@ -201,14 +202,16 @@ struct LaneState {
 // warp through a queue in shared memory and replays each lane's results in the reference's order.
 // Everything is passed and returned by value (registers): a reference to the caller's arrays would force
 // them into local memory on the hot path.  Returns {new cell word, (evaluations << 1) | changed}.
-__device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ rec, const ColParams &P, uint32_t *q_ent, float *q_d,
-                                                  int s, int lane, int warp, int rj0, int rk0, bool update, bool edge,
+__device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
+                                                  int ri, int lane, int warp, bool update, bool edge,
                                                   uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
                                                   uint32_t nb5, uint32_t nb6, uint32_t th0, uint32_t th1, uint32_t th2,
                                                   uint32_t th3, uint32_t th4, uint32_t th5, uint32_t th6,
                                                   uint32_t cur, uint64_t *self_ptr, float phi)
 {
     const Grid &g = P.g;
+    uint32_t *const q_ent = sh.q_ent[warp];
+    float *const q_d = sh.q_d[warp];
     const uint32_t nb[7] = {nb0, nb1, nb2, nb3, nb4, nb5, nb6}, thr[7] = {th0, th1, th2, th3, th4, th5, th6};
     unsigned evals = 0, changed = 0;
     uint32_t live = 0;                    // bit m: neighbour m's triangle must be evaluated
@@ -240,6 +243,7 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
     const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
     if (live) {
+        sh.gx[(warp << 5) + lane] = lattice(P.sd.abs_i(ri, g), g.dx, g.ox);      // gy, gz were stored once per column
         int w = off;
         #pragma unroll
         for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
@@ -252,14 +256,11 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
     __syncwarp();
     for (int q = lane; q < total; q += 32) {
         const uint32_t e = q_ent[q];
-        const int otid = (warp << 5) + (int)(e >> 27);               // owner lane -> its voxel
-        const int oa = otid % EJ, ob = otid / EJ;
-        const int ori = s - oa - ob - SHIFT;
-        const int oi = P.sd.abs_i(ori, g), oj = P.sd.abs_j(rj0 + oa, g), ok = P.sd.abs_k(rk0 + ob, g);
-        const F3 gx{lattice(oi, g.dx, g.ox), lattice(oj, g.dx, g.oy), lattice(ok, g.dx, g.oz)};
+        const int ot = (warp << 5) + (int)(e >> 27);                 // owner lane -> its voxel's position
+        const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
         const TriRec *tr = &rec[e & TRI_MASK];
         const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
-        q_d[q] = point_triangle_distance(gx, F3{p.x, p.y, p.z}, F3{qq.x, qq.y, qq.z}, F3{r.x, r.y, r.z});
+        q_d[q] = ptd_rec(gx, p, qq, r);
         ++evals;
     }
     __syncwarp();
@@ -308,7 +309,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     #pragma unroll
     for (int m = 0; m < 7; ++m) { t[m] = edge ? thr_edge[m] : thr[m]; fresh = fresh || (nb[m] >= t[m]); }
     if (__any_sync(0xffffffffu, update && fresh)) {
-        const uint2 r = evaluate_candidates(rec, P, sh.q_ent[warp], sh.q_d[warp], s, lane, warp, rj0, rk0, update, false,
+        const uint2 r = evaluate_candidates(rec, P, sh, ri, lane, warp, update, false,
                                             nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
                                             t[0], t[1], t[2], t[3], t[4], t[5], t[6],
                                             cur, self_ptr, cell_phi(self));
@@ -338,6 +339,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     if (row_ok) {
         const int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
         st.own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)st.ri;
+        sh.gy[tid] = lattice(j, g.dx, g.oy);
+        sh.gz[tid] = lattice(k, g.dx, g.oz);
     }
     // memo thresholds: the neighbour word nb at offset m is fresh iff nb >= thr[m] = (last[m]+1) << 27, i.e.
     // stamp(nb) > last[m] (0 = always fresh where the offset was never examined).  Rows on the far j / k
