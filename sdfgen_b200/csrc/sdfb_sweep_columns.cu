@@ -78,6 +78,8 @@ __device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1
 
 // named barriers: 0 = __syncthreads (column hand-over, all 352 threads), 1 = per-step (compute + halo lanes)
 __device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NSTEPPERS) : "memory"); }
+// 2 = compute warps only (column-wide evaluation queue)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" ::"n"(NCOMPUTE) : "memory"); }
 
 #ifdef SDFB_TRACE
 #define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
@@ -90,6 +92,7 @@ struct ColShared {
     uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
     float q_d[NCOMPUTE / 32][QCAP];
     float gx[NCOMPUTE], gy[NCOMPUTE], gz[NCOMPUTE];   // world position of each compute lane's current voxel
+    int wtot[NCOMPUTE / 32];                          // candidates per warp in this step (column-wide queue mode)
     int col;
     volatile int go;        // chunks cleared to run (their upstream words are published); written by the sync warp
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
@@ -280,9 +283,83 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
     return make_uint2(cur, (evals << 1) | changed);
 }
 
+// Column-wide variant used in the evaluation-heavy sweeps: the candidates of all 8 compute warps go to one
+// queue and all 256 lanes evaluate it, so every warp does ceil(total/256) rounds instead of waiting at the
+// step barrier for the warp with the longest private queue.  Costs one compute-only barrier per step (three
+// when there is work).  Must be called by every compute lane in every step.
+__device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
+                                                      int ri, int tid, bool update, uint32_t live_in,
+                                                      uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
+                                                      uint32_t nb5, uint32_t nb6, uint32_t cur, uint64_t *self_ptr, float phi)
+{
+    const Grid &g = P.g;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t *const q_ent = &sh.q_ent[0][0];       // flat: NCOMPUTE * 7 entries
+    float *const q_d = &sh.q_d[0][0];
+    const uint32_t nb[7] = {nb0, nb1, nb2, nb3, nb4, nb5, nb6};
+    unsigned evals = 0, changed = 0;
+    uint32_t live = update ? live_in : 0u;
+    if (live) {                           // drop repeats of ANY earlier neighbour's triangle (see evaluate_candidates)
+        #pragma unroll
+        for (int m = 1; m < 7; ++m) {
+            bool dup = false;
+            #pragma unroll
+            for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
+            if (dup) live &= ~(1u << m);
+        }
+    }
+    const int ncand = __popc(live);
+    const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
+                   b2 = __ballot_sync(0xffffffffu, ncand & 4);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    bar_compute();
+    int base = 0, total = 0;
+    #pragma unroll
+    for (int w = 0; w < NCOMPUTE / 32; ++w) { const int t = sh.wtot[w]; base += (w < warp) ? t : 0; total += t; }
+    if (total == 0) return make_uint2(cur, 0u);                       // uniform over the column
+    const int off = base + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+    if (live) {
+        sh.gx[tid] = lattice(P.sd.abs_i(ri, g), g.dx, g.ox);           // gy, gz were stored once per column
+        int w = off;
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
+            q_ent[w] = nb[m] & TRI_MASK;
+            q_d[w] = __int_as_float(tid);                              // owner, replaced by the distance below
+            ++w;
+            const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);     // start the gather now
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
+        }
+    }
+    bar_compute();
+    for (int q = tid; q < total; q += NCOMPUTE) {
+        const int ot = __float_as_int(q_d[q]);
+        const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
+        const TriRec *tr = &rec[q_ent[q]];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        q_d[q] = ptd_rec(gx, p, qq, r);
+        ++evals;
+    }
+    bar_compute();
+    if (live) {
+        uint32_t best = TRI_NONE;
+        for (int q = off; q < off + ncand; ++q) {                    // the reference's order and strict "<"
+            const float d = q_d[q];
+            if (d < phi) { phi = d; best = q_ent[q]; }
+        }
+        if (best != TRI_NONE) {
+            cur = (P.stamp << 27) | best;
+            *self_ptr = pack_cell(phi, cur);
+            changed = 1;
+        }
+    }
+    return make_uint2(cur, (evals << 1) | changed);
+}
+
 // One step of a compute lane.  PAR = step parity: reads exchange slot PAR^1, writes slot PAR.  `own` holds the
 // lane's cell for this step on entry and is reloaded with the cell two steps ahead (see halo_column).
-template <int PAR>
+template <int PAR, bool CTA_QUEUE>
 __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                              const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
                                              int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
@@ -308,7 +385,21 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     bool fresh = false;
     #pragma unroll
     for (int m = 0; m < 7; ++m) { t[m] = edge ? thr_edge[m] : thr[m]; fresh = fresh || (nb[m] >= t[m]); }
-    if (__any_sync(0xffffffffu, update && fresh)) {
+    if (CTA_QUEUE) {
+        // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this voxel last looked
+        uint32_t live = 0;
+        if (update && fresh) {
+            #pragma unroll
+            for (int m = 0; m < 7; ++m) {
+                const uint32_t x = nb[m];
+                const bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ cur) & TRI_MASK) != 0) && (x >= t[m]);
+                live |= keep ? (1u << m) : 0u;
+            }
+        }
+        const uint2 r = evaluate_candidates_cta(rec, P, sh, ri, (warp << 5) + lane, update, live,
+                                                nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6], cur, self_ptr, cell_phi(self));
+        cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
+    } else if (__any_sync(0xffffffffu, update && fresh)) {
         const uint2 r = evaluate_candidates(rec, P, sh, ri, lane, warp, update, false,
                                             nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
                                             t[0], t[1], t[2], t[3], t[4], t[5], t[6],
@@ -323,6 +414,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     bar_step();
 }
 
+template <bool CTA_QUEUE>
 __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
                                                const ColParams &P, ColShared &sh, int tid, int rj0, int rk0,
                                                unsigned &my_changed, unsigned &my_evals)
@@ -363,8 +455,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        compute_step<0>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, st);
-        compute_step<1>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, st);
+        compute_step<0, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, st);
+        compute_step<1, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, st);
         if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
             __threadfence_block();
             sh.done = (s + 2) / PUBLISH;
@@ -376,6 +468,7 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 #ifndef SDFB_MINB
 #define SDFB_MINB 2
 #endif
+template <bool CTA_QUEUE>
 __global__ void __launch_bounds__(NTHREADS, SDFB_MINB)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
@@ -404,7 +497,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
         }
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
         if (tid < NCOMPUTE) {
-            compute_column(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+            compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
             halo_column(cells, P, sh, tid - NCOMPUTE, rj0, rk0);
         } else if (tid == NSTEPPERS) {
@@ -478,13 +571,16 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // evaluation-heavy sweeps (the first pass) balance the distance evaluations over the whole column
+    const bool cta_queue = getenv("SDFB_CTA_QUEUE") ? atoi(getenv("SDFB_CTA_QUEUE")) != 0 : (sweep_index < 8);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_columns, NTHREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cta_queue ? k_sweep_columns<true> : k_sweep_columns<false>, NTHREADS, 0);
     if (occ < 1) occ = 1;
     int grid = sms * occ;
     int ncols = P.NJ * P.NK;
     if (grid > ncols) grid = ncols;
-    k_sweep_columns<<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
+    if (cta_queue) k_sweep_columns<true><<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
+    else k_sweep_columns<false><<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
 #ifdef SDFB_TRACE
     if (P.trace) {
         cudaStreamSynchronize(st);
