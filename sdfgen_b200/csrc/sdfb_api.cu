@@ -119,6 +119,25 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
     if (rc) return rc;
     g_launches += launch_tri_prep(d_tri, d_xyz, ntri, p->rec, st);
     CU(cudaGetLastError());
+    // Keep the triangle records resident in L2 while the grid streams through it: the sweeps gather them at
+    // random (48 B per evaluation).  Best effort: ignored where persisting L2 is unavailable.
+    {
+        int dev = p->device, max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t bytes = (size_t)ntri * sizeof(TriRec);
+        if (max_persist > 0 && max_window > 0 && bytes > 0 && !getenv("SDFB_NO_L2_PERSIST")) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = p->rec;
+            attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+            attr.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError();
+        }
+    }
     p->ntri = ntri; p->nvert = nvert; p->have_mesh = true; p->have_band = false; p->have_sign = false;
     return SDFB_OK;
 }

@@ -363,8 +363,19 @@ template <int PAR, bool CTA_QUEUE>
 __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                              const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
                                              int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
-                                             const uint32_t (&thr_edge)[7], uint64_t &own, LaneState &st)
+                                             const uint32_t (&thr_edge)[7], uint64_t &own, const uint64_t &own_other,
+                                             LaneState &st)
 {
+    if (CTA_QUEUE) {
+        // evaluation-heavy sweeps: the triangle of the lane's NEXT voxel (cell loaded one step ago) will be a
+        // candidate of its neighbours one or two steps from now -- start the record gather a step early
+        const uint32_t tn = lo_tri(cell_lo(own_other));
+        if (row_ok && tn != TRI_NONE) {
+            const char *ra = reinterpret_cast<const char *>(&rec[tn]);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ra));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ra + 32));
+        }
+    }
     const int ni = P.g.ni;
     const int64_t si = (int64_t)P.sd.di;
     const int ri = st.ri;
@@ -455,8 +466,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        compute_step<0, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, st);
-        compute_step<1, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, st);
+        compute_step<0, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, ownB, st);
+        compute_step<1, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, ownA, st);
         if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
             __threadfence_block();
             sh.done = (s + 2) / PUBLISH;
