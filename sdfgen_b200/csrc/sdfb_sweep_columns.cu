@@ -82,7 +82,7 @@ __device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" ::"n"(NCOMPUTE) : "memory"); }
 
 #ifdef SDFB_TRACE
-#define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 2 + (slot)] = clock64(); } while (0)
+#define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 8 + (slot)] = clock64(); } while (0)
 #else
 #define TRACE(P, warp, s, slot) do { } while (0)
 #endif
@@ -169,7 +169,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 wA = ~0ull;
                 if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
             }
-            TRACE(P, 8 + (h >> 5), s, 1);
+            TRACE(P, 8 + (h >> 5), s, 7);
             bar_step();
             TRACE(P, 8 + (h >> 5), s + 1, 0);
             if (row_ok) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
                 if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
             }
-            TRACE(P, 8 + (h >> 5), s + 1, 1);
+            TRACE(P, 8 + (h >> 5), s + 1, 7);
             bar_step();
         }
     }
@@ -288,7 +288,7 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
 // step barrier for the warp with the longest private queue.  Costs one compute-only barrier per step (three
 // when there is work).  Must be called by every compute lane in every step.
 __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
-                                                      int ri, int tid, bool update, uint32_t live_in,
+                                                      int ri, int tid, int s, bool update, uint32_t live_in,
                                                       uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
                                                       uint32_t nb5, uint32_t nb6, uint32_t cur, uint64_t *self_ptr, float phi)
 {
@@ -313,7 +313,9 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
                    b2 = __ballot_sync(0xffffffffu, ncand & 4);
     const uint32_t lt_mask = (1u << lane) - 1u;
     if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    TRACE(P, warp, s, 1);
     bar_compute();
+    TRACE(P, warp, s, 2);
     int base = 0, total = 0;
     #pragma unroll
     for (int w = 0; w < NCOMPUTE / 32; ++w) { const int t = sh.wtot[w]; base += (w < warp) ? t : 0; total += t; }
@@ -332,7 +334,9 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
             asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
         }
     }
+    TRACE(P, warp, s, 3);
     bar_compute();
+    TRACE(P, warp, s, 4);
     for (int q = tid; q < total; q += NCOMPUTE) {
         const int ot = __float_as_int(q_d[q]);
         const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
@@ -341,7 +345,9 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
         q_d[q] = ptd_rec(gx, p, qq, r);
         ++evals;
     }
+    TRACE(P, warp, s, 5);
     bar_compute();
+    TRACE(P, warp, s, 6);
     if (live) {
         uint32_t best = TRI_NONE;
         for (int q = off; q < off + ncand; ++q) {                    // the reference's order and strict "<"
@@ -407,7 +413,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
                 live |= keep ? (1u << m) : 0u;
             }
         }
-        const uint2 r = evaluate_candidates_cta(rec, P, sh, ri, (warp << 5) + lane, update, live,
+        const uint2 r = evaluate_candidates_cta(rec, P, sh, ri, (warp << 5) + lane, s, update, live,
                                                 nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6], cur, self_ptr, cell_phi(self));
         cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
     } else if (__any_sync(0xffffffffu, update && fresh)) {
@@ -421,7 +427,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     if (row_ok && (unsigned)ri < (unsigned)ni) { ring_w[PAR * RSTRIDE] = cur; st.prev_lo = cur; }
     st.own_ptr = self_ptr + si;
     st.ri = ri + 1;
-    TRACE(P, warp, s, 1);
+    TRACE(P, warp, s, 7);
     bar_step();
 }
 
@@ -571,7 +577,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     }
 #ifdef SDFB_TRACE
     static unsigned long long *trace_buf = nullptr;
-    const size_t trace_n = (size_t)11 * 8192 * 2;
+    const size_t trace_n = (size_t)11 * 8192 * 8;
     if (getenv("SDFB_TRACE") && P.steps <= 8192) {
         if (!trace_buf) cudaMalloc(&trace_buf, trace_n * sizeof(unsigned long long));
         cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), st);
