@@ -159,7 +159,12 @@ __device__ __forceinline__ TriRec make_tri_rec(F3 x1, F3 x2, F3 x3)
     return t;
 }
 
-// point_triangle_distance with the record's invariants (bit-identical to the full function)
+// point_triangle_distance with the record's invariants (bit-identical to the full function).
+// The three "clamp to two edges" cases of the reference (:63-68) always measure two of the segments
+// (x1,x2), (x1,x3), (x2,x3) in that orientation and take min(first, second); instead of branching three ways
+// (lanes of a warp disagree on the case all the time) the endpoints are SELECTED and the two segment
+// distances are computed once, uniformly.  Same operations on the same values per lane => same bits.
+__device__ __forceinline__ F3 sel3(bool c, F3 a, F3 b) { return F3{c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z}; }
 __device__ __forceinline__ float ptd_rec(F3 x0, float4 P, float4 Q, float4 R)
 {
     const F3 x1{P.x, P.y, P.z}, x2{Q.x, Q.y, Q.z}, x3{R.x, R.y, R.z};
@@ -176,12 +181,12 @@ __device__ __forceinline__ float ptd_rec(F3 x0, float4 P, float4 Q, float4 R)
                    fadd(fadd(fmul(w23, x1.y), fmul(w31, x2.y)), fmul(w12, x3.y)),
                    fadd(fadd(fmul(w23, x1.z), fmul(w31, x2.z)), fmul(w12, x3.z)) };
         d2 = mag2_3(sub3(x0, p));
-    } else if (w23 > 0.f) {
-        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x1, x3));
-    } else if (w31 > 0.f) {
-        d2 = min_std(seg_distance2(x0, x1, x2), seg_distance2(x0, x2, x3));
     } else {
-        d2 = min_std(seg_distance2(x0, x1, x3), seg_distance2(x0, x2, x3));
+        const bool c1 = w23 > 0.f, c12 = c1 || (w31 > 0.f);
+        // first segment: (x1,x2) in cases 1 and 2, (x1,x3) in case 3; second: (x1,x3) in case 1, else (x2,x3)
+        const F3 fb = sel3(c12, x2, x3);
+        const F3 sa = sel3(c1, x1, x2);
+        d2 = min_std(seg_distance2(x0, x1, fb), seg_distance2(x0, sa, x3));
     }
     return __fsqrt_rn(d2);
 }

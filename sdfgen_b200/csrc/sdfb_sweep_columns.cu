@@ -329,9 +329,6 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
             q_ent[w] = nb[m] & TRI_MASK;
             q_d[w] = __int_as_float(tid);                              // owner, replaced by the distance below
             ++w;
-            const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);     // start the gather now
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
         }
     }
     TRACE(P, warp, s, 3);
