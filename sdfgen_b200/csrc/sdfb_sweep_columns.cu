@@ -334,32 +334,13 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
     TRACE(P, warp, s, 3);
     bar_compute();
     TRACE(P, warp, s, 4);
-    // software pipelined: the record and position of the NEXT entry are fetched while this one is evaluated
-    // (the gather is a random 48-byte read from L2/HBM; the distance is a ~200-instruction dependent chain)
-    {
-        int q = tid;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), qq = p, r = p;
-        F3 gx{0.f, 0.f, 0.f};
-        if (q < total) {
-            const int ot = __float_as_int(q_d[q]);
-            gx = F3{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
-            const TriRec *tr = &rec[q_ent[q]];
-            p = __ldg(&tr->p); qq = __ldg(&tr->q); r = __ldg(&tr->r);
-        }
-        while (q < total) {
-            const int qn = q + NCOMPUTE;
-            float4 pn = p, qqn = qq, rn = r;
-            F3 gxn = gx;
-            if (qn < total) {
-                const int ot = __float_as_int(q_d[qn]);
-                gxn = F3{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
-                const TriRec *tr = &rec[q_ent[qn]];
-                pn = __ldg(&tr->p); qqn = __ldg(&tr->q); rn = __ldg(&tr->r);
-            }
-            q_d[q] = ptd_rec(gx, p, qq, r);
-            ++evals;
-            p = pn; qq = qqn; r = rn; gx = gxn; q = qn;
-        }
+    for (int q = tid; q < total; q += NCOMPUTE) {
+        const int ot = __float_as_int(q_d[q]);
+        const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
+        const TriRec *tr = &rec[q_ent[q]];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        q_d[q] = ptd_rec(gx, p, qq, r);
+        ++evals;
     }
     TRACE(P, warp, s, 5);
     bar_compute();
@@ -501,9 +482,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 #ifndef SDFB_MINB
 #define SDFB_MINB 2
 #endif
-// 352 threads x 88 registers x 2 CTAs = 61952 <= 65536: two columns per SM without spills
 template <bool CTA_QUEUE>
-__global__ void __maxnreg__(88)
+__global__ void __launch_bounds__(NTHREADS, SDFB_MINB)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
                 unsigned long long *__restrict__ changed)
