@@ -78,8 +78,9 @@ __device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1
 
 // named barriers: 0 = __syncthreads (column hand-over, all 352 threads), 1 = per-step (compute + halo lanes)
 __device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NSTEPPERS) : "memory"); }
-// 2 = compute warps only (column-wide evaluation queue)
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" ::"n"(NCOMPUTE) : "memory"); }
+// 2 = evaluation barrier of the column-wide queue: compute AND halo lanes (the halo warps are nearly idle, so
+// they take a share of the distance evaluations)
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" ::"n"(NSTEPPERS) : "memory"); }
 
 #ifdef SDFB_TRACE
 #define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 8 + (slot)] = clock64(); } while (0)
@@ -97,6 +98,38 @@ struct ColShared {
     volatile int go;        // chunks cleared to run (their upstream words are published); written by the sync warp
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
 };
+
+// Evaluation share of one lane in the column-wide queue: entries first, first+NSTEPPERS, ...
+__device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restrict__ rec, ColShared &sh, int first, int total)
+{
+    uint32_t *const q_ent = &sh.q_ent[0][0];
+    float *const q_d = &sh.q_d[0][0];
+    unsigned evals = 0;
+    for (int q = first; q < total; q += NSTEPPERS) {
+        const int ot = __float_as_int(q_d[q]);                         // owner lane, replaced by the distance
+        const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
+        const TriRec *tr = &rec[q_ent[q]];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        q_d[q] = ptd_rec(gx, p, qq, r);
+        ++evals;
+    }
+    return evals;
+}
+
+// What a halo lane does per step in the column-wide queue mode: the same three barriers as the compute
+// lanes (one when the queue is empty) and its share of the evaluations.
+__device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict__ rec, ColShared &sh, int h)
+{
+    bar_compute();
+    int total = 0;
+    #pragma unroll
+    for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
+    if (total == 0) return 0u;
+    bar_compute();
+    const unsigned e = evaluate_queue_share(rec, sh, NCOMPUTE + h, total);
+    bar_compute();
+    return e;
+}
 
 // ---- sync warp: keeps flag polling and progress publication off the step loop's critical path ----------
 // Lane 0 only.  Chunk c = steps [c*PUBLISH, (c+1)*PUBLISH).  A halo lane loads at step s the word of virtual
@@ -134,8 +167,9 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, c
 }
 
 // ---- halo warps: feed the words of the upstream columns / boundary faces into the exchange array ----
-__device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const ColParams &P, ColShared &sh,
-                                            int h, int rj0, int rk0)
+template <bool CTA_QUEUE>
+__device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
+                                            const ColParams &P, ColShared &sh, int h, int rj0, int rk0, unsigned &my_evals)
 {
     const Grid &g = P.g;
     int a, b;
@@ -169,6 +203,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 wA = ~0ull;
                 if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
             }
+            if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
             TRACE(P, 8 + (h >> 5), s, 7);
             bar_step();
             TRACE(P, 8 + (h >> 5), s + 1, 0);
@@ -180,6 +215,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
                 if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
             }
+            if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
             TRACE(P, 8 + (h >> 5), s + 1, 7);
             bar_step();
         }
@@ -334,25 +370,20 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
     TRACE(P, warp, s, 3);
     bar_compute();
     TRACE(P, warp, s, 4);
-    for (int q = tid; q < total; q += NCOMPUTE) {
-        const int ot = __float_as_int(q_d[q]);
-        const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
-        const TriRec *tr = &rec[q_ent[q]];
-        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
-        q_d[q] = ptd_rec(gx, p, qq, r);
-        ++evals;
-    }
+    evals = evaluate_queue_share(rec, sh, tid, total);
     TRACE(P, warp, s, 5);
     bar_compute();
     TRACE(P, warp, s, 6);
     if (live) {
-        uint32_t best = TRI_NONE;
-        for (int q = off; q < off + ncand; ++q) {                    // the reference's order and strict "<"
-            const float d = q_d[q];
-            if (d < phi) { phi = d; best = q_ent[q]; }
-        }
-        if (best != TRI_NONE) {
-            cur = (P.stamp << 27) | best;
+        // the reference's order and strict "<": all distances are fetched first (independent loads)
+        float dv[7];
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) dv[m] = (m < ncand) ? q_d[off + m] : __int_as_float(0x7f800000);
+        int best = -1;
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) if (dv[m] < phi) { phi = dv[m]; best = m; }
+        if (best >= 0) {
+            cur = (P.stamp << 27) | q_ent[off + best];
             *self_ptr = pack_cell(phi, cur);
             changed = 1;
         }
@@ -513,7 +544,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
         if (tid < NCOMPUTE) {
             compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
-            halo_column(cells, P, sh, tid - NCOMPUTE, rj0, rk0);
+            halo_column<CTA_QUEUE>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
         } else if (tid == NSTEPPERS) {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
