@@ -95,7 +95,6 @@ struct ColShared {
     float gx[NCOMPUTE], gy[NCOMPUTE], gz[NCOMPUTE];   // world position of each compute lane's current voxel
     int wtot[NCOMPUTE / 32];                          // candidates per warp in this step (column-wide queue mode)
     int col;
-    volatile int go;        // chunks cleared to run (their upstream words are published); written by the sync warp
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
 };
 
@@ -137,28 +136,43 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
 // column has completed s1-1+EJ+3 steps (EK for the column below; the diagonal column is covered transitively,
 // because the left column itself waited for it).  Chunks are cleared a little ahead of need through sh.go;
 // finished chunks (sh.done, set after the chunk's last step barrier) are fenced and published at once.
-__device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, const uint32_t *prog_left,
+__device__ __forceinline__ void bar_go_arrive(int chunk) { asm volatile("bar.arrive %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
+__device__ __forceinline__ void bar_go_wait(int chunk) { asm volatile("bar.sync %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
+
+// Runs on the whole sync warp (lane 0 reads and writes; the named barriers need the full warp).  "Chunk c may
+// run" is signalled to the halo warps with bar.arrive on barrier 4 + (c & 3): they block in hardware instead
+// of spinning.  The sync warp clears at most 3 chunks beyond the finished ones, so when it re-arms a barrier
+// (chunk c+4) its previous phase (chunk c) was consumed long ago.
+__device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, int lane, const uint32_t *prog_left,
                                             const uint32_t *prog_down, uint32_t *prog_mine)
 {
     const uint32_t ebase = P.epoch << 16;
     const int nchunks = P.steps / PUBLISH;
     int cleared = 0, published = 0;                        // counts of chunks
     while (published < nchunks) {
-        if (cleared < nchunks && cleared < sh.done + 4) {
-            const int s1 = (cleared + 1) * PUBLISH;
-            const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
-            const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
-            if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) {
-                // no fence here: the halo lanes' loads are issued only after they have read sh.go (control
+        int act = 0, d = 0;                                // 1: clear the next chunk, 2: publish finished chunks
+        if (lane == 0) {
+            d = sh.done;
+            if (cleared < nchunks && cleared < d + 3) {
+                const int s1 = (cleared + 1) * PUBLISH;
+                const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
+                const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
+                // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
                 // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-                sh.go = ++cleared;
-                continue;                                  // try to clear further ahead before sleeping
+                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) act = 1;
             }
+            if (!act && d > published) act = 2;
         }
-        const int d = sh.done;
-        if (d > published) {
-            __threadfence();                               // release: the chunk's stores happen-before the flag
-            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+        act = __shfl_sync(0xffffffffu, act, 0);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (act == 1) {
+            bar_go_arrive(cleared);
+            ++cleared;
+        } else if (act == 2) {
+            if (lane == 0) {
+                __threadfence();                           // release: the chunk's stores happen-before the flag
+                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+            }
             published = d;
         } else {
             __nanosleep(20);
@@ -189,9 +203,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     uint64_t wA = ~0ull, wB = ~0ull;
     for (int s0 = 0, c = 0; s0 < P.steps; s0 += PUBLISH, ++c) {
         const int s1 = s0 + PUBLISH;                       // P.steps is a multiple of PUBLISH
-        if ((h & 31) == 0) { while (sh.go <= c) { } }      // wait until chunk c is cleared (shared-memory spin)
-        __syncwarp();
-        __threadfence_block();
+        bar_go_wait(c);                                    // until the sync warp has cleared chunk c
         if (s0 == 0 && row_ok) {
             if ((unsigned)ri < (unsigned)g.ni) wA = __ldcg(ptr);
             if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
@@ -526,7 +538,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
 
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
-        if (tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.go = 0; sh.done = 0; }
+        if (tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; }
         __syncthreads();
         const int tk = sh.col;
         if (tk >= ncols) break;
@@ -545,10 +557,10 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
             compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
             halo_column<CTA_QUEUE>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
-        } else if (tid == NSTEPPERS) {
+        } else {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
-            sync_column(P, sh, prog_left, prog_down, &progress[K * P.NJ + J]);
+            sync_column(P, sh, lane, prog_left, prog_down, &progress[K * P.NJ + J]);
         }
         __syncthreads();        // sh.col is rewritten next; also orders the two roles' exits
     }

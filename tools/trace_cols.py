@@ -14,7 +14,7 @@ for col in [0, 1, 2, 5, 20, 100, 300, 512, 700, 1000, 1023]:
     p.sweep(0, 16)
     torch.cuda.synchronize()
     for s in (15,):
-        tr = np.fromfile(f"gpurun_out/ctrace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 2)[:10].astype(np.int64)
+        tr = np.fromfile(f"gpurun_out/ctrace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 8)[:10][:, :, [0, 7]].astype(np.int64)
         a = tr[:, 40:500, :]
         d = np.diff(a[0, :, 0])
         busy = (a[:, :, 1] - a[:, :, 0]).mean(axis=1)

@@ -13,7 +13,7 @@ p.band(np.array([-0.5, -0.13, -0.13], np.float32), 1.0 / 64, 1)
 p.sweep(0, 16)
 torch.cuda.synchronize()
 for s in (12, 13):
-    tr = np.fromfile(f"gpurun_out/trace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 2)[:10].astype(np.int64)
+    tr = np.fromfile(f"gpurun_out/trace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 8)[:10][:, :, [0, 7]].astype(np.int64)
     steps = 2000
     a = tr[:, 1000:1000 + steps, :]
     t0 = a[0, 0, 0]

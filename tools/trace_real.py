@@ -12,7 +12,7 @@ p.band(w["origin"], w["dx"], 1)
 p.sweep(0, 16)
 torch.cuda.synchronize()
 for s in (0, 4, 8, 12, 15):
-    tr = np.fromfile(f"gpurun_out/rtrace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 2)[:10].astype(np.int64)
+    tr = np.fromfile(f"gpurun_out/rtrace.{s}.bin", dtype=np.uint64).reshape(11, 8192, 8)[:10][:, :, [0, 7]].astype(np.int64)
     a = tr[:, 40:500, :]
     print("sweep", s, "cycles/step", (a[0, -1, 0] - a[0, 0, 0]) / (a.shape[1] - 1), "column span cycles", tr[0, 543, 1] - tr[0, 0, 0])
     busy = (a[:, :, 1] - a[:, :, 0]).mean(axis=1)
