@@ -149,34 +149,40 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
     const uint32_t ebase = P.epoch << 16;
     const int nchunks = P.steps / PUBLISH;
     int cleared = 0, published = 0;                        // counts of chunks
+    // chunks a producer that has completed `p` steps allows: chunk c needs min(steps, (c+1)*PUBLISH-1+E+3) steps
+    auto allowed = [&](uint32_t flag, int E) -> int {
+        if (flag < ebase) return 0;                        // the producer has not started this sweep yet
+        const int p = (int)(flag - ebase);
+        if (p >= P.steps) return nchunks;
+        const int c = (p - (E + 2)) / PUBLISH;             // largest c+1 with (c+1)*PUBLISH + E + 2 <= p
+        return c < 0 ? 0 : c;
+    };
     while (published < nchunks) {
-        int act = 0, d = 0;                                // 1: clear the next chunk, 2: publish finished chunks
+        // one round trip to L2 per iteration: publish what is finished, then clear as many chunks as the
+        // producers' flags allow (at most 3 beyond the finished ones, see above)
+        int d = 0, target = 0;
         if (lane == 0) {
             d = sh.done;
-            if (cleared < nchunks && cleared < d + 3) {
-                const int s1 = (cleared + 1) * PUBLISH;
-                const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
-                const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
-                // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
-                // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) act = 1;
-            }
-            if (!act && d > published) act = 2;
-        }
-        act = __shfl_sync(0xffffffffu, act, 0);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        if (act == 1) {
-            bar_go_arrive(cleared);
-            ++cleared;
-        } else if (act == 2) {
-            if (lane == 0) {
-                __threadfence();                           // release: the chunk's stores happen-before the flag
+            if (d > published) {
+                __threadfence();                           // release: the chunks' stores happen-before the flag
                 *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
             }
-            published = d;
-        } else {
-            __nanosleep(20);
+            target = cleared;
+            const int want = min(nchunks, d + 3);
+            if (cleared < want) {
+                // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
+                // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
+                const int al = prog_left ? allowed(*reinterpret_cast<const volatile uint32_t *>(prog_left), EJ) : nchunks;
+                const int ad = prog_down ? allowed(*reinterpret_cast<const volatile uint32_t *>(prog_down), EK) : nchunks;
+                target = max(cleared, min(want, min(al, ad)));
+            }
         }
+        d = __shfl_sync(0xffffffffu, d, 0);
+        target = __shfl_sync(0xffffffffu, target, 0);
+        const bool idle = (d == published) && (target == cleared);
+        published = d;
+        while (cleared < target) { bar_go_arrive(cleared); ++cleared; }
+        if (idle) __nanosleep(40);
     }
 }
 
