@@ -158,31 +158,34 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
         return c < 0 ? 0 : c;
     };
     while (published < nchunks) {
-        // one round trip to L2 per iteration: publish what is finished, then clear as many chunks as the
-        // producers' flags allow (at most 3 beyond the finished ones, see above)
-        int d = 0, target = 0;
-        if (lane == 0) {
-            d = sh.done;
-            if (d > published) {
-                __threadfence();                           // release: the chunks' stores happen-before the flag
-                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
-            }
-            target = cleared;
-            const int want = min(nchunks, d + 3);
-            if (cleared < want) {
-                // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
-                // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-                const int al = prog_left ? allowed(*reinterpret_cast<const volatile uint32_t *>(prog_left), EJ) : nchunks;
-                const int ad = prog_down ? allowed(*reinterpret_cast<const volatile uint32_t *>(prog_down), EK) : nchunks;
-                target = max(cleared, min(want, min(al, ad)));
-            }
+        // Lane 1 polls the producers' flags, lane 0 publishes: the flag loads are issued first and are in
+        // flight while lane 0 fences and stores (a fence only waits for its own thread's accesses), so one
+        // iteration costs max(L2 round trip, fence) and clears as many chunks as the flags allow (at most 3
+        // beyond the finished ones, see above).
+        const int d = sh.done;                              // every lane reads the same word
+        const int want = min(nchunks, d + 3);
+        uint32_t fl = 0xffffffffu, fd = 0xffffffffu;
+        const bool poll = (lane == 1) && (cleared < want);
+        if (poll) {
+            // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
+            // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
+            if (prog_left) fl = *reinterpret_cast<const volatile uint32_t *>(prog_left);
+            if (prog_down) fd = *reinterpret_cast<const volatile uint32_t *>(prog_down);
         }
-        d = __shfl_sync(0xffffffffu, d, 0);
-        target = __shfl_sync(0xffffffffu, target, 0);
+        if (lane == 0 && d > published) {
+            __threadfence();                               // release: the chunks' stores happen-before the flag
+            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+        }
+        int target = cleared;
+        if (poll) {
+            const int al = prog_left ? allowed(fl, EJ) : nchunks, ad = prog_down ? allowed(fd, EK) : nchunks;
+            target = max(cleared, min(want, min(al, ad)));
+        }
+        target = __shfl_sync(0xffffffffu, target, 1);
         const bool idle = (d == published) && (target == cleared);
         published = d;
         while (cleared < target) { bar_go_arrive(cleared); ++cleared; }
-        if (idle) __nanosleep(40);
+        if (idle) __nanosleep(20);
     }
 }
 
