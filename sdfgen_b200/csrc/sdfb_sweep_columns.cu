@@ -149,43 +149,34 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
     const uint32_t ebase = P.epoch << 16;
     const int nchunks = P.steps / PUBLISH;
     int cleared = 0, published = 0;                        // counts of chunks
-    // chunks a producer that has completed `p` steps allows: chunk c needs min(steps, (c+1)*PUBLISH-1+E+3) steps
-    auto allowed = [&](uint32_t flag, int E) -> int {
-        if (flag < ebase) return 0;                        // the producer has not started this sweep yet
-        const int p = (int)(flag - ebase);
-        if (p >= P.steps) return nchunks;
-        const int c = (p - (E + 2)) / PUBLISH;             // largest c+1 with (c+1)*PUBLISH + E + 2 <= p
-        return c < 0 ? 0 : c;
-    };
     while (published < nchunks) {
-        // Lane 1 polls the producers' flags, lane 0 publishes: the flag loads are issued first and are in
-        // flight while lane 0 fences and stores (a fence only waits for its own thread's accesses), so one
-        // iteration costs max(L2 round trip, fence) and clears as many chunks as the flags allow (at most 3
-        // beyond the finished ones, see above).
-        const int d = sh.done;                              // every lane reads the same word
-        const int want = min(nchunks, d + 3);
-        uint32_t fl = 0xffffffffu, fd = 0xffffffffu;
-        const bool poll = (lane == 1) && (cleared < want);
-        if (poll) {
-            // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
-            // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-            if (prog_left) fl = *reinterpret_cast<const volatile uint32_t *>(prog_left);
-            if (prog_down) fd = *reinterpret_cast<const volatile uint32_t *>(prog_down);
+        int act = 0, d = 0;                                // 1: clear the next chunk, 2: publish finished chunks
+        if (lane == 0) {
+            d = sh.done;
+            if (cleared < nchunks && cleared < d + 3) {
+                const int s1 = (cleared + 1) * PUBLISH;
+                const uint32_t fl = prog_left ? *reinterpret_cast<const volatile uint32_t *>(prog_left) : 0xffffffffu;
+                const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
+                // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
+                // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
+                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) act = 1;
+            }
+            if (!act && d > published) act = 2;
         }
-        if (lane == 0 && d > published) {
-            __threadfence();                               // release: the chunks' stores happen-before the flag
-            *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+        act = __shfl_sync(0xffffffffu, act, 0);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (act == 1) {
+            bar_go_arrive(cleared);
+            ++cleared;
+        } else if (act == 2) {
+            if (lane == 0) {
+                __threadfence();                           // release: the chunk's stores happen-before the flag
+                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+            }
+            published = d;
+        } else {
+            __nanosleep(20);
         }
-        int target = cleared;
-        if (poll) {
-            const int al = prog_left ? allowed(fl, EJ) : nchunks, ad = prog_down ? allowed(fd, EK) : nchunks;
-            target = max(cleared, min(want, min(al, ad)));
-        }
-        target = __shfl_sync(0xffffffffu, target, 1);
-        const bool idle = (d == published) && (target == cleared);
-        published = d;
-        while (cleared < target) { bar_go_arrive(cleared); ++cleared; }
-        if (idle) __nanosleep(20);
     }
 }
 
