@@ -152,3 +152,47 @@ def test_slab_plans_band_and_sign_match_full_grid():
         phi, _, _ = p.download(phi=True)
         assert _same(phi, r.phi[sl])          # nsweeps=0 -> signed band-only phi
         p.close()
+
+
+def test_full_size_512_properties():
+    """BASELINE configs[2] at full size (512^3, 1,310,720 triangles), where the CPU oracle would take ~10 min:
+    size-independent checks.  (1) the production column schedule equals the trivially ordered per-level
+    schedule bit for bit (phi, closest_tri, counts); (2) every voxel's |phi| is exactly the reference
+    distance to the triangle it names (sampled, checked with the CPU oracle's point_triangle_distance);
+    (3) signs and distances agree with the analytic sphere; (4) a second run on the same plan is identical."""
+    w = meshes.workload("c2_icosphere_512")
+    n = 512
+    res = {}
+    for sched, flags in SCHEDULES:
+        p = _lib.Plan(n, n, n, flags=flags)
+        p.set_mesh_host(w["vertices"], w["triangles"])
+        p.run(w["origin"], w["dx"], 1)
+        phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
+        if sched == "columns":
+            p.run(w["origin"], w["dx"], 1)
+            phi2, tri2, _ = p.download(phi=True, tri=True)
+            assert _same(phi, phi2) and _same(tri, tri2)
+        res[sched] = (phi, tri, cnt)
+        p.close()
+    a, b = res["columns"], res["levels"]
+    assert _same(a[0], b[0]) and _same(a[1], b[1]) and _same(a[2], b[2])
+    phi, tri, cnt = a
+    assert int(cnt.sum()) > 0 and int((tri < 0).sum()) == 0
+    # (2) sampled self-consistency against the CPU oracle's distance function
+    rng = np.random.default_rng(1)
+    v, t, o, dx = w["vertices"], w["triangles"], w["origin"], np.float32(w["dx"])
+    for c in rng.choice(phi.size, 400, replace=False):
+        k, rem = divmod(int(c), n * n)
+        j, i = divmod(rem, n)
+        gx = np.array([i, j, k], np.float32) * dx + o
+        d = oracle.port.point_triangle_distance(gx, *v[t[tri[c]]])
+        assert np.float32(d).view(np.uint32) == np.abs(phi[c]).view(np.uint32)
+    # (3) analytic sphere of radius 0.4 centred at the origin (faceting error << dx/2 at level 8)
+    idx = rng.choice(phi.size, 200000, replace=False)
+    k, rem = np.divmod(idx, n * n)
+    j, i = np.divmod(rem, n)
+    pts = np.stack([i, j, k], 1).astype(np.float64) * float(dx) + o.astype(np.float64)
+    exact = np.linalg.norm(pts, axis=1) - 0.4
+    far = np.abs(exact) > float(dx)
+    assert np.array_equal(phi[idx][far] < 0, exact[far] < 0)
+    assert np.abs(phi[idx] - exact).max() < 0.75 * float(dx)
