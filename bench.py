@@ -45,6 +45,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic():
+    """DRAM bytes per sweep launch from the committed ncu --set full captures (profiles/), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None
+    try:
+        return float(json.load(open(files[-1]))["per_launch_bytes_mean"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -235,7 +247,7 @@ def run_single_gpu(args):
                    "sweeps": 16, "schedule": args.schedule, "l2": "grid state (12 B/voxel + 4 B/voxel output) is far larger than the 126 MB L2; no flush needed",
                    "phase_ms": phase, "inside_voxels": inside},
         "roofline": {"bound": "hbm", "kernel": "sweep (one launch per direction, 16 per step)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes_sweep, "launch_ms": sweep_launch_ms,
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak,
                      "path_algorithmic_bytes": path_bytes},
