@@ -60,7 +60,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
     if (rk_first < 1) rk_first = 1;
     if (rk_first > rk_last || ni < 2 || nj < 2) { if (changed_out) *changed_out = 0; return 0; }
     const int NJ = (nj - 1 + EJ - 1) / EJ, NK = (rk_last - rk_first + 1 + EK - 1) / EK;
-    const int steps = (ni + EJ + EK - 2 + SHIFT + 3) / 4 * 4;
+    const int steps = (ni + EJ + EK - 2 + SHIFT + 1) & ~1;
     const uint32_t stamp = (uint32_t)imin(sweep_index + 1, 31);
     uint8_t last[8][7];
     for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
@@ -92,7 +92,7 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
         int A[NLANES], B[NLANES], row_ok[NLANES];
         int64_t c_row[NLANES];
         uint64_t own_next_phi_lo[NLANES];   /* packed like the device: phi bits << 32 | lo */
-        uint32_t halo_w1[NLANES], halo_w2[NLANES], halo_w3[NLANES], halo_next[NLANES], prev_lo[NLANES], r1_old[NLANES], r3_old[NLANES], r5_old[NLANES], r5_old2[NLANES];
+        uint32_t halo_w1[NLANES], halo_next[NLANES], prev_lo[NLANES], r1_old[NLANES], r3_old[NLANES], r5_old[NLANES], r5_old2[NLANES];
         for (int tid = 0; tid < NLANES; ++tid) {
             int a, b;
             if (tid < NCOMPUTE) { a = tid % EJ; b = tid / EJ; }
@@ -116,13 +116,11 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
         for (int s0 = 0; s0 < steps; s0 += PUBLISH) {
             const int s1 = imin(s0 + PUBLISH, steps);
             /* what the wait condition of this chunk guarantees about the producers */
-            const int need_left = imin(steps, s1 - 1 + EJ + 5), need_down = imin(steps, s1 - 1 + EK + 5);
+            const int need_left = imin(steps, s1 - 1 + EJ + 3), need_down = imin(steps, s1 - 1 + EK + 3);
             if (s0 == 0) for (int tid = NCOMPUTE; tid < NLANES; ++tid) if (row_ok[tid]) {
                 int ri0 = 0 - A[tid] - B[tid] - SHIFT;
                 halo_next[tid] = (ri0 >= 0 && ri0 <= ni - 1) ? cells_lo[c_row[tid] + si * ri0] : TRI_NONE;
                 halo_w1[tid] = (ri0 + 1 >= 0 && ri0 + 1 <= ni - 1) ? cells_lo[c_row[tid] + si * (ri0 + 1)] : TRI_NONE;
-                halo_w2[tid] = (ri0 + 2 >= 0 && ri0 + 2 <= ni - 1) ? cells_lo[c_row[tid] + si * (ri0 + 2)] : TRI_NONE;
-                halo_w3[tid] = (ri0 + 3 >= 0 && ri0 + 3 <= ni - 1) ? cells_lo[c_row[tid] + si * (ri0 + 3)] : TRI_NONE;
             }
             for (int s = s0; s < s1; ++s) {
                 const int slot = s & 1, pslot = slot ^ 1;
@@ -130,11 +128,11 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                 for (int tid = NCOMPUTE; tid < NLANES; ++tid) if (row_ok[tid]) {
                     int a = A[tid], b = B[tid], ri = s - a - b - SHIFT;
                     ring[ring_idx(slot, a, b)] = halo_next[tid];
-                    halo_next[tid] = halo_w1[tid]; halo_w1[tid] = halo_w2[tid]; halo_w2[tid] = halo_w3[tid];
-                    int rin = ri + 4;                       /* the load issued at step s is for virtual step s+4 */
-                    if (rin >= 0 && rin <= ni - 1 && s + 4 < steps) {
+                    halo_next[tid] = halo_w1[tid];
+                    int rin = ri + 2;                       /* the load issued at step s is for virtual step s+2 */
+                    if (rin >= 0 && rin <= ni - 1 && s + 2 < steps) {
                         int64_t c = c_row[tid] + si * rin;
-                        halo_w3[tid] = cells_lo[c];
+                        halo_w1[tid] = cells_lo[c];
                         /* flag arithmetic: the producer step of this voxel must be covered by the wait */
                         int rj = rj0 + a, rk = rk0 + b;
                         if (rin >= 1 && rj >= 1 && rk >= rk_first) {           /* a voxel some column updates */
@@ -145,10 +143,10 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
                             else if (b == -1 && a >= 0) guaranteed = need_down;
             /* diagonal column: covered transitively -- the left column ran step need_left-1 only
                                after ITS wait saw the diagonal column at >= need_left-1+EK+2 steps */
-                            else guaranteed = imin(steps, need_left - 1 + EK + 5);
+                            else guaranteed = imin(steps, need_left - 1 + EK + 3);
                             if (!(pstep < guaranteed)) ++emu_flag_violations;
                         }
-                    } else halo_w3[tid] = TRI_NONE;
+                    } else halo_w1[tid] = TRI_NONE;
                 }
                 /* compute lanes: phase 1, candidates */
                 int ncand[NCOMPUTE], upd[NCOMPUTE], in_row_v[NCOMPUTE];

@@ -131,9 +131,9 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
 }
 
 // ---- sync warp: keeps flag polling and progress publication off the step loop's critical path ----------
-// Chunk c = steps [c*PUBLISH, (c+1)*PUBLISH).  A halo lane loads at step s the word of virtual
-// step s+4, produced by column (J-1,K) lane (EJ-1,b) at its step s+4+EJ, so chunk c may run once the left
-// column has completed s1-1+EJ+5 steps (EK for the column below; the diagonal column is covered transitively,
+// Lane 0 only.  Chunk c = steps [c*PUBLISH, (c+1)*PUBLISH).  A halo lane loads at step s the word of virtual
+// step s+2, produced by column (J-1,K) lane (EJ-1,b) at its step s+2+EJ, so chunk c may run once the left
+// column has completed s1-1+EJ+3 steps (EK for the column below; the diagonal column is covered transitively,
 // because the left column itself waited for it).  Chunks are cleared a little ahead of need through sh.go;
 // finished chunks (sh.done, set after the chunk's last step barrier) are fenced and published at once.
 __device__ __forceinline__ void bar_go_arrive(int chunk) { asm volatile("bar.arrive %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
@@ -159,7 +159,7 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
                 const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
                 // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
                 // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 5) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 5)) act = 1;
+                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) act = 1;
             }
             if (!act && d > published) act = 2;
         }
@@ -197,39 +197,40 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     if (row_ok) ptr = cells + g.cidx(P.sd.abs_i(0, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g)) + si * (int64_t)(0 - a - b - SHIFT);
     const int widx = row_ok ? ring_idx(a, b) : 0;
     int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
-    // Raw cells of virtual steps s (register s & 3), each loaded FOUR steps before it is published: an L2 round
-    // trip under load is longer than two steps.  The step loop is unrolled by four so that a register is
-    // reloaded right after it was consumed and never copied: a copy (or a select) of a freshly loaded value
-    // would stall on the load at once.
-    uint64_t w0 = ~0ull, w1 = ~0ull, w2 = ~0ull, w3 = ~0ull;
-    int c = 0;                                             // chunk counter (PUBLISH == 2: two chunks per iteration)
-    auto half = [&](uint64_t &w, const int s, const int slot) {
-        TRACE(P, 8 + (h >> 5), s, 0);
-        if (row_ok) {
-            sh.ring[slot * RSTRIDE + widx] = cell_lo(w);
-            w = ~0ull;
-            if ((unsigned)(ri + 4) < (unsigned)g.ni && s + 4 < P.steps) w = __ldcg(ptr + 4 * si);
-            ++ri; ptr += si;
-            // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
-            if ((s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
+    // Raw cells of virtual steps s (even -> wA, odd -> wB), each loaded two steps before it is published.
+    // The step loop is unrolled by two so that a register is reloaded right after it was consumed and
+    // never copied: a copy (or a select) of a freshly loaded value would stall on the load at once.
+    uint64_t wA = ~0ull, wB = ~0ull;
+    for (int s0 = 0, c = 0; s0 < P.steps; s0 += PUBLISH, ++c) {
+        const int s1 = s0 + PUBLISH;                       // P.steps is a multiple of PUBLISH
+        bar_go_wait(c);                                    // until the sync warp has cleared chunk c
+        if (s0 == 0 && row_ok) {
+            if ((unsigned)ri < (unsigned)g.ni) wA = __ldcg(ptr);
+            if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
         }
-        if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
-        TRACE(P, 8 + (h >> 5), s, 7);
-        bar_step();
-    };
-    for (int s = 0; s < P.steps; s += 4) {                 // P.steps is a multiple of 4
-        bar_go_wait(c++);                                  // until the sync warp has cleared this chunk
-        if (s == 0 && row_ok) {
-            if ((unsigned)ri < (unsigned)g.ni) w0 = __ldcg(ptr);
-            if ((unsigned)(ri + 1) < (unsigned)g.ni) w1 = __ldcg(ptr + si);
-            if ((unsigned)(ri + 2) < (unsigned)g.ni) w2 = __ldcg(ptr + 2 * si);
-            if ((unsigned)(ri + 3) < (unsigned)g.ni) w3 = __ldcg(ptr + 3 * si);
+        for (int s = s0; s < s1; s += 2) {                 // PUBLISH is even
+            TRACE(P, 8 + (h >> 5), s, 0);
+            if (row_ok) {
+                sh.ring[widx] = cell_lo(wA);               // even step -> slot 0
+                wA = ~0ull;
+                if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
+            }
+            if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
+            TRACE(P, 8 + (h >> 5), s, 7);
+            bar_step();
+            TRACE(P, 8 + (h >> 5), s + 1, 0);
+            if (row_ok) {
+                sh.ring[RSTRIDE + widx] = cell_lo(wB);     // odd step -> slot 1
+                wB = ~0ull;
+                if ((unsigned)(ri + 3) < (unsigned)g.ni && s + 3 < P.steps) wB = __ldcg(ptr + 3 * si);
+                ri += 2; ptr += 2 * si;
+                // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
+                if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
+            }
+            if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
+            TRACE(P, 8 + (h >> 5), s + 1, 7);
+            bar_step();
         }
-        half(w0, s, 0);
-        half(w1, s + 1, 1);
-        bar_go_wait(c++);
-        half(w2, s + 2, 0);
-        half(w3, s + 3, 1);
     }
 }
 
@@ -432,8 +433,6 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     if (row_ok && (unsigned)(ri + 2) < (unsigned)ni) own = *(self_ptr + 2 * si);       // the cell two steps ahead
     if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)ni)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(self_ptr + 48 * si));
-    if (row_ok && (s & 3) == 2 && (unsigned)(ri + 10) < (unsigned)ni)      // ... and into L1 a few steps ahead of the load
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(self_ptr + 10 * si));
     uint32_t cur = cell_lo(self);
     const bool update = row_ok && (unsigned)(ri - 1) < (unsigned)(ni - 1);            // 1 <= ri <= ni-1
     // The last voxel of a row lies on the far i face: only sweeps with the same di visit it (thr_edge).
@@ -600,8 +599,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     P.rk_first = rk_lo; P.rk_last = rk_hi;
     P.NJ = (g.nj - 1 + EJ - 1) / EJ;
     P.NK = (rk_hi - rk_lo + 1 + EK - 1) / EK;
-    static_assert(PUBLISH == 2, "the halo loop is written for two chunks of two steps per iteration");
-    P.steps = (g.ni + EJ + EK - 2 + SHIFT + 3) / 4 * 4;   // whole chunks; the halo loop is unrolled by four
+    P.steps = (g.ni + EJ + EK - 2 + SHIFT + PUBLISH - 1) / PUBLISH * PUBLISH;   // whole chunks (PUBLISH is even: the step loops are unrolled by two)
     P.stamp = (uint32_t)min(sweep_index + 1, 31);
     // the epoch grows with every launch on a plan between resets of the progress array (host side)
     P.epoch = epoch;
