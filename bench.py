@@ -99,49 +99,57 @@ def build_workload(name, grid):
 
 
 def cpu_reference_run(w, n, threads):
-    """One timed run of the reference CPU path on the mesh of workload w at an n^3 grid."""
+    """One timed run of the reference CPU path on the mesh of workload w, on the same domain at n cells per
+    unit length (n x n x n*copies for the stacked multi-GPU workload)."""
     import oracle
-    from sdfgen_b200 import meshes
     L = 1.0
+    copies = max(1, w["nk"] // w["ni"])
     dx = np.float32(L / n)
     origin = (np.float32(-0.5 * L) + np.float32(0.37) * dx) * np.ones(3, np.float32)
     kind = "reference" if oracle.have_ref() else "port"
     t0 = time.perf_counter()
     if kind == "reference":
-        oracle.ref.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n, 1, num_threads=threads)
+        oracle.ref.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n * copies, 1, num_threads=threads)
     else:
-        oracle.port.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n, 1)
+        oracle.port.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n * copies, 1)
     dt = time.perf_counter() - t0
-    return dt, kind
+    return dt, kind, n * n * n * copies
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only), on a bounded
+    sample of the same workload; stops early when the time budget is used up (reports the steps it timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
-    w = build_workload(args.workload, args.grid)
+    from sdfgen_b200 import meshes
+    w = build_workload(args.workload, args.grid) if args.gpus == 1 else meshes.stacked_workload(args.gpus, n=args.grid or 512)
     n = min(CPU_SAMPLE_GRID, w["ni"])
     kind = "reference" if oracle.have_ref() else "port"
     cores = oracle.ref.hardware_concurrency() if kind == "reference" else 1
-    for _ in range(max(0, min(args.warmup, 1))):
+    budget_s, t_start = 150.0, time.perf_counter()
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
         cpu_reference_run(w, n, 0)
-    times = []
+    times, vox = [], 0
     for _ in range(args.steps):
-        dt, kind = cpu_reference_run(w, n, 0)
+        dt, kind, vox = cpu_reference_run(w, n, 0)
         times.append(dt)
+        if time.perf_counter() - t_start + dt > budget_s:
+            break
     total = sum(times)
-    value = (n ** 3) * len(times) / total / 1e9
+    value = vox * len(times) / total / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "triangles": int(w["triangles"].shape[0]), "grid": [w["ni"], w["nj"], w["nk"]],
-                   "exact_band": 1, "sample_grid": [n, n, n]},
+                   "exact_band": 1, "sample_grid": [n, n, n * max(1, w["nk"] // w["ni"])]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"same mesh on a {n}^3 grid per step (bounded sample of the {w['ni']}^3 workload), "
-                                   f"sdfgen::cpu::make_level_set3 num_threads=0 (auto), wall clock"},
+                         "sample": f"same mesh and domain at {n} cells per unit length per step (bounded sample of the "
+                                   f"{w['ni']}x{w['nj']}x{w['nk']} workload), sdfgen::cpu::make_level_set3 num_threads=0 "
+                                   f"(auto), wall clock; {len(times)} of {args.steps} requested steps fit the time budget"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,9 +241,9 @@ def run_single_gpu(args):
     if not args.no_cpu_baseline:
         import oracle
         n = min(CPU_SAMPLE_GRID, ni)
-        dt, kind = cpu_reference_run(w, n, 0)
+        dt, kind, vox = cpu_reference_run(w, n, 0)
         cores = oracle.ref.hardware_concurrency() if kind == "reference" else 1
-        cpu = {"value": n ** 3 / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+        cpu = {"value": vox / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"same mesh on a {n}^3 grid, one run ({dt:.1f} s), sdfgen::cpu::make_level_set3 "
                          f"num_threads=0 (auto) built in place from the reference sources"}
 
@@ -273,7 +281,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.workload is None:
-        args.workload = "c2_icosphere_512" if args.gpus == 1 else "c3_torus_1024"
+        args.workload = "c2_icosphere_512"      # N > 1 uses meshes.stacked_workload(N): one C2 block per GPU
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

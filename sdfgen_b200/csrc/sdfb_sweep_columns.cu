@@ -633,6 +633,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cta_queue ? k_sweep_columns<true> : k_sweep_columns<false>, NTHREADS, 0);
     if (occ < 1) occ = 1;
+    if (getenv("SDFB_MAX_OCC")) occ = min(occ, atoi(getenv("SDFB_MAX_OCC")));   // experiment knob
     int grid = sms * occ;
     int ncols = P.NJ * P.NK;
     if (grid > ncols) grid = ncols;
