@@ -181,7 +181,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     p->g.dx = 1.f; p->g.ox = p->g.oy = p->g.oz = 0.f; p->g.band = 1;
     const size_t V = (size_t)p->g.slab_voxels();
     cudaError_t e;
-    if ((e = cudaMalloc(&p->cells, (size_t)p->g.cell_count() * sizeof(uint64_t))) != cudaSuccess ||
+    if ((e = cudaMalloc(&p->cells, ((size_t)p->g.cell_count() + 8) * sizeof(uint64_t))) != cudaSuccess ||   // +8: bulk prefetches round up to 16 B
         (e = cudaMalloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMalloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
         ((flags & SDFB_OUT_KFASTEST) && (e = cudaMalloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||

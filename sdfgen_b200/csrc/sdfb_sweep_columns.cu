@@ -88,6 +88,24 @@ __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" :
 #define TRACE(P, warp, s, slot) do { } while (0)
 #endif
 
+// L2 prefetch of a run of cells of one row with ONE bulk request (TMA prefetch, no data returned).  The sweeps
+// walk ~85,000 rows concurrently, 8 bytes per row and step; fetching them sector by sector makes every DRAM
+// access a row miss.  `first` .. `first + (count-1)*dir` are relative positions along the row pointed to by p0.
+constexpr int PF_CELLS = 64;          // cells per prefetch (512 B)
+constexpr int PF_AHEAD = 96;          // how far ahead of the walker the prefetched run starts
+__device__ __forceinline__ void prefetch_run(const uint64_t *p0, int64_t si, int first, int ni)
+{
+    int lo = first, hi = first + PF_CELLS - 1;                 // relative positions, clipped to the row
+    if (hi > ni - 1) hi = ni - 1;
+    if (lo < 0) lo = 0;
+    if (lo > hi) return;
+    const uint64_t *a = p0 + si * (int64_t)lo, *b = p0 + si * (int64_t)hi;
+    const uint64_t *beg = si > 0 ? a : b;                        // lowest address of the run
+    uintptr_t addr = reinterpret_cast<uintptr_t>(beg) & ~(uintptr_t)15;
+    uint32_t bytes = (uint32_t)((hi - lo + 1) * 8 + 16) & ~15u;  // 16-byte granules covering the run
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
+}
+
 struct ColShared {
     uint32_t ring[2 * RSTRIDE];
     uint32_t q_ent[NCOMPUTE / 32][QCAP];      // (owner lane << 27) | tri
@@ -225,7 +243,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
                 if ((unsigned)(ri + 3) < (unsigned)g.ni && s + 3 < P.steps) wB = __ldcg(ptr + 3 * si);
                 ri += 2; ptr += 2 * si;
                 // non-binding L2 prefetch far ahead (the line may still be rewritten by its producer; L2 stays coherent)
-                if ((s & 2) == 0 && (unsigned)(ri + 48) < (unsigned)g.ni) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 48 * si));
+                if ((s & (PF_CELLS - 1)) == 0) prefetch_run(ptr - si * (int64_t)ri, si, ri + PF_AHEAD, g.ni);
             }
             if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
             TRACE(P, 8 + (h >> 5), s + 1, 7);
@@ -431,8 +449,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     const uint64_t self = own;
     uint64_t *const self_ptr = st.own_ptr;
     if (row_ok && (unsigned)(ri + 2) < (unsigned)ni) own = *(self_ptr + 2 * si);       // the cell two steps ahead
-    if (row_ok && (s & 3) == 0 && (unsigned)(ri + 48) < (unsigned)ni)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(self_ptr + 48 * si));
+    if (row_ok && (s & (PF_CELLS - 1)) == 0) prefetch_run(self_ptr - si * (int64_t)ri, si, ri + PF_AHEAD, ni);
     uint32_t cur = cell_lo(self);
     const bool update = row_ok && (unsigned)(ri - 1) < (unsigned)(ni - 1);            // 1 <= ri <= ni-1
     // The last voxel of a row lies on the far i face: only sweeps with the same di visit it (thr_edge).
@@ -509,6 +526,10 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     // own cells by step parity (even -> ownA, odd -> ownB), each loaded two steps before use and reloaded
     // right after it was consumed (no copies of fresh loads, see halo_column)
     uint64_t ownA = 0, ownB = 0;
+    if (row_ok) {                          // the first stretch of the row, before the periodic prefetch takes over
+        prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, 0, g.ni);
+        prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, PF_CELLS, g.ni);
+    }
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
