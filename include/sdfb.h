@@ -47,8 +47,14 @@ extern "C" {
 #define SDFB_OUT_KFASTEST       0x1u  /* phi/tri/count outputs in C order [ni][nj][nk] (k fastest), the
                                          layout sdfgen_ext.generate_sdf returns (sdfgen_py.cpp:80-86)
                                          and the .sdf file stores (common/sdf_io.cpp:49-57)          */
-#define SDFB_SWEEP_LEVELS       0x2u  /* debug schedule: one launch per anti-diagonal level (slow,
-                                         trivially exact); default is the pipelined column schedule  */
+/* Sweep schedules.  All reproduce the reference's serial Gauss-Seidel order bit for bit; they differ in how
+ * the work is laid out.  Default: pipelined columns for the first pass of 8 sweeps (most voxels change),
+ * fixed-point relaxation for every later sweep (almost nothing changes).  The flags force one schedule for
+ * all sweeps (cross-checks and experiments). */
+#define SDFB_SWEEP_LEVELS       0x2u  /* one launch per anti-diagonal level (slow, trivially exact)         */
+#define SDFB_SWEEP_STRIPS       0x8u  /* warp pipelines without CTA-wide barriers (experimental)            */
+#define SDFB_SWEEP_RELAX        0x10u /* fixed-point relaxation for every sweep                             */
+#define SDFB_SWEEP_COLUMNS      0x20u /* pipelined columns for every sweep                                  */
 #define SDFB_NO_SIGN            0x4u  /* stop before the sign pass (phi stays unsigned)              */
 
 const char *sdfb_version(void);

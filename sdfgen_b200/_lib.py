@@ -8,10 +8,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdfb.so")
+LIB_PATH = os.environ.get("SDFB_LIB_PATH") or os.path.join(_HERE, "libsdfb.so")   # override: development builds only
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
-OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN = 0x1, 0x2, 0x4
+OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN, SWEEP_STRIPS, SWEEP_RELAX, SWEEP_COLUMNS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 
 _lib = None
 

@@ -73,6 +73,7 @@ struct sdfb_plan {
     uint32_t *progress = nullptr;    // column-schedule flags
     size_t progress_words = 0;
     uint32_t epoch = 0;              // column-schedule launch counter since the flags were last zeroed
+    void *relax = nullptr;           // scratch of the relaxation schedule (lazily allocated, zeroed once)
     // mesh
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
@@ -191,6 +192,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
     }
     p->progress_words = sweep_columns_progress_words(p->g);
+    if (sweep_strips_progress_words(p->g) > p->progress_words) p->progress_words = sweep_strips_progress_words(p->g);
     if (p->progress_words && (e = cudaMalloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
         sdfb_plan_destroy(p);
         cudaGetLastError();
@@ -211,7 +213,7 @@ int sdfb_plan_destroy(sdfb_plan *p)
     cudaDeviceSynchronize();
     free_mesh(p);
     cudaFree(p->cells); cudaFree(p->counts); cudaFree(p->phi); cudaFree(p->phi_k); cudaFree(p->scratch);
-    cudaFree(p->changed); cudaFree(p->progress);
+    cudaFree(p->changed); cudaFree(p->progress); cudaFree(p->relax);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
     delete p;
     cudaGetLastError();
@@ -279,15 +281,28 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     if (first < 0 || count < 0) return fail(SDFB_ERR_INVALID, "bad sweep range");
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
+    // first sweep index handled by the relaxation schedule: the reference's second pass and everything after it
+    int relax_from = (p->flags & SDFB_SWEEP_RELAX) ? 0 : ((p->flags & (SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS)) ? 1 << 30 : 8);
+    if (getenv("SDFB_RELAX_FROM") && !(p->flags & (SDFB_SWEEP_RELAX | SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS))) relax_from = atoi(getenv("SDFB_RELAX_FROM"));
     for (int s = first; s < first + count; ++s) {
         if (p->flags & SDFB_SWEEP_LEVELS) {
             g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
+        } else if (s >= relax_from && s + 1 < 31 && sweep_relax_supported(p->g)) {
+            if (!p->relax) {
+                const size_t bytes = sweep_relax_scratch_bytes(p->g);
+                CU(cudaMalloc(&p->relax, bytes));
+                CU(cudaMemsetAsync(p->relax, 0, bytes, st));
+            }
+            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st);
         } else {
             if (p->epoch >= 65000u) {   // progress words are epoch<<16 | steps: start over before it wraps
                 CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
                 p->epoch = 0;
             }
-            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
+            if (p->flags & SDFB_SWEEP_STRIPS)
+                g_launches += launch_sweep_strips(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
+            else
+                g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
         }
     }
     CU(cudaGetLastError());

@@ -41,6 +41,15 @@ int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32
 int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st);
 int launch_relayout_i32(const int32_t *src, const Grid &g, int32_t *dst_kfastest, cudaStream_t st);
 
+int launch_sweep_strips(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
+                        unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st);
+
+bool sweep_relax_supported(const Grid &g);
+size_t sweep_relax_scratch_bytes(const Grid &g);
+int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
+                       unsigned long long *changed, void *scratch, cudaStream_t st);
+
 size_t sweep_columns_progress_words(const Grid &g);
+size_t sweep_strips_progress_words(const Grid &g);
 
 }  // namespace sdfb

@@ -624,18 +624,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     P.stamp = (uint32_t)min(sweep_index + 1, 31);
     // the epoch grows with every launch on a plan between resets of the progress array (host side)
     P.epoch = epoch;
-    for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
-        P.last[c][m] = 0;
-        if (sweep_index + 1 > 31) continue;           // stamps saturate: no memo beyond 31 sweeps
-        const bool ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
-        for (int e = sweep_index - 1; e >= 0; --e) {
-            SweepDir d = SweepDir::of(e);
-            // sweep e examined offset m (same direction along the offset's axes) and visited a voxel of class c
-            // (same direction along every axis on whose far face the voxel lies)
-            const bool same_i = d.di == P.sd.di, same_j = d.dj == P.sd.dj, same_k = d.dk == P.sd.dk;
-            if ((!(ci || (c & 1)) || same_i) && (!(cj || (c & 2)) || same_j) && (!(ck || (c & 4)) || same_k)) { P.last[c][m] = (uint8_t)(e + 1); break; }
-        }
-    }
+    memo_last_table(sweep_index, P.sd, P.last);
 #ifdef SDFB_TRACE
     static unsigned long long *trace_buf = nullptr;
     const size_t trace_n = (size_t)11 * 8192 * 8;

@@ -31,4 +31,23 @@ struct SweepDir {
     }
 };
 
+// Stamp memo table shared by the pipelined schedules.  last[c][m] = stamp (sweep index + 1) of the latest
+// earlier sweep in which a voxel of class c examined neighbour offset m, 0 if none.  Class bits: 1 = last
+// voxel of its row (ri = ni-1), 2 = last row (rj = nj-1), 4 = last plane (rk = nk-1): such voxels lie on a
+// grid face and are only visited by sweeps whose direction along that axis equals the current one.  Offset m
+// (cpu_lib/makelevelset3.cpp:143-149) steps along i for m in {0,2,4,6}, along j for {1,2,5,6}, along k for m >= 3.
+inline void memo_last_table(int sweep_index, const SweepDir &cur, uint8_t (&last)[8][8])
+{
+    for (int c = 0; c < 8; ++c) for (int m = 0; m < 8; ++m) last[c][m] = 0;
+    if (sweep_index + 1 > 31) return;                 // stamps saturate: no memo beyond 31 sweeps
+    for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
+        const bool ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
+        for (int e = sweep_index - 1; e >= 0; --e) {
+            const SweepDir d = SweepDir::of(e);
+            const bool same_i = d.di == cur.di, same_j = d.dj == cur.dj, same_k = d.dk == cur.dk;
+            if ((!(ci || (c & 1)) || same_i) && (!(cj || (c & 2)) || same_j) && (!(ck || (c & 4)) || same_k)) { last[c][m] = (uint8_t)(e + 1); break; }
+        }
+    }
+}
+
 }  // namespace sdfb

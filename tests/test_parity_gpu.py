@@ -20,7 +20,8 @@ from sdfgen_b200 import _lib, meshes
 
 pytestmark = pytest.mark.gpu
 
-SCHEDULES = [("columns", 0), ("levels", _lib.SWEEP_LEVELS)]
+SCHEDULES = [("default", 0), ("columns", _lib.SWEEP_COLUMNS), ("relax", _lib.SWEEP_RELAX), ("strips", _lib.SWEEP_STRIPS),
+             ("levels", _lib.SWEEP_LEVELS)]
 
 
 def _bits(a):
