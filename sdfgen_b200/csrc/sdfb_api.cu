@@ -74,6 +74,8 @@ struct sdfb_plan {
     size_t progress_words = 0;
     uint32_t epoch = 0;              // column-schedule launch counter since the flags were last zeroed
     void *relax = nullptr;           // scratch of the relaxation schedule (lazily allocated, zeroed once)
+    int last_sweep = -1;             // highest sweep index run since the last band: the relaxation schedule tells the
+                                     // cells it changed by this sweep's stamp, so an index must not repeat
     // mesh
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
@@ -270,7 +272,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
-    p->have_band = true; p->have_sign = false; p->timed = false;
+    p->have_band = true; p->have_sign = false; p->timed = false; p->last_sweep = -1;
     return SDFB_OK;
 }
 
@@ -287,7 +289,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     for (int s = first; s < first + count; ++s) {
         if (p->flags & SDFB_SWEEP_LEVELS) {
             g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
-        } else if (s >= relax_from && s + 1 < 31 && sweep_relax_supported(p->g)) {
+        } else if (s >= relax_from && s + 1 < 31 && s > p->last_sweep && sweep_relax_supported(p->g)) {
             if (!p->relax) {
                 const size_t bytes = sweep_relax_scratch_bytes(p->g);
                 CU(cudaMalloc(&p->relax, bytes));
@@ -305,6 +307,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                 g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
         }
     }
+    if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[2], st));
     p->have_sign = false;

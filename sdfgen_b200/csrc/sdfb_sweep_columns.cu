@@ -43,9 +43,17 @@ namespace sdfb {
 
 namespace {
 
-constexpr int EJ = 16, EK = 16;              // column extent (rows x planes)
-constexpr int NCOMPUTE = EJ * EK;            // 256 compute lanes = 8 warps
-constexpr int NHALO = 64;                    // 2 halo warps
+// 8 x 16 columns at 4 CTAs per SM measured ~5 % faster than 16 x 16 at 2 (same voxels in flight, more independent
+// barrier domains); 16 x 8 and 8 x 8 were slower.
+#ifndef SDFB_EJ
+#define SDFB_EJ 8
+#endif
+#ifndef SDFB_EK
+#define SDFB_EK 16
+#endif
+constexpr int EJ = SDFB_EJ, EK = SDFB_EK;    // column extent (rows x planes)
+constexpr int NCOMPUTE = EJ * EK;            // compute lanes (16 x 16: 8 warps)
+constexpr int NHALO = (EJ + EK + 1 + 31) / 32 * 32;   // halo lanes, whole warps
 constexpr int NSTEPPERS = NCOMPUTE + NHALO;  // lanes that take part in the per-step barrier
 constexpr int NTHREADS = NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
 #ifndef SDFB_PUBLISH
@@ -544,7 +552,7 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 }
 
 #ifndef SDFB_MINB
-#define SDFB_MINB 2
+#define SDFB_MINB 4
 #endif
 template <bool CTA_QUEUE>
 __global__ void __launch_bounds__(NTHREADS, SDFB_MINB)

@@ -36,7 +36,6 @@ namespace {
 
 constexpr int RX_WARPS = 8;                  // warps per CTA; in round 0 warp w handles row j0 + w
 constexpr int RX_THREADS = RX_WARPS * 32;
-constexpr int QCAP = 7 * 32;
 
 struct RelaxParams {
     Grid g;
@@ -55,41 +54,46 @@ struct RelaxParams {
     uint8_t last[8][8];
 };
 
+// Per-warp batch: voxels are filtered as they come (one per lane and call), their candidate triangles are
+// appended to the warp's queue, and the queue is evaluated when it is nearly full -- with all 32 lanes busy,
+// whatever the number of candidates per voxel -- before each pending voxel replays its own results.
+constexpr int QCAP_B = 416;                  // queue entries per warp; a call adds at most 7 * 32
+constexpr int PCAP_B = 96;                   // pending voxels per warp; a call adds at most 32
+constexpr int SOLO_CAP = 2048;               // entries of the in-CTA work lists of the tail rounds
+struct Pending {
+    uint32_t c;                              // cell index
+    float px, py, pz;                        // world position
+    uint32_t info;                           // queue offset (16 bits) | candidates << 16 | may-push flags i,j,k << 20 | was_changed << 23
+    uint32_t cur_lo, cur_hi;                 // the cell as the filter read it (nobody else writes it in this round)
+    uint32_t base_lo, base_hi;               // the cell at the start of the sweep
+};
 struct RelaxShared {
-    uint32_t q_ent[RX_WARPS][QCAP];          // (owner lane << 27) | tri
-    float q_d[RX_WARPS][QCAP];
-    float px[RX_WARPS][32], py[RX_WARPS][32], pz[RX_WARPS][32];   // world position of each lane's voxel
+    uint32_t q_ent[RX_WARPS][QCAP_B];        // triangle
+    float q_d[RX_WARPS][QCAP_B];             // owner (index into pend) until evaluated, then the distance
+    Pending pend[RX_WARPS][PCAP_B];
     uint32_t thr[8][8];
     uint32_t tmin[8];                        // lowest threshold of each class: the cheap "nothing is fresh" test
+    uint32_t slist[2][SOLO_CAP];             // tail rounds (one CTA): the work lists live here
+    unsigned int scount[3];
 };
 
 __device__ __forceinline__ uint64_t ld_cg64(const uint64_t *p) { return __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
 __device__ __forceinline__ uint32_t ld_cg32(const uint64_t *cell) { return __ldcg(reinterpret_cast<const uint32_t *>(cell)); }
 
-// Re-evaluates one voxel per lane (all 32 lanes must call; `valid` masks lanes without a voxel).
-// Cells are read through L2: other SMs rewrite them during the launch.
-__device__ __forceinline__ void relax_voxels(const RelaxParams &P, RelaxShared &sh, int warp, int lane, bool valid,
-                                             int64_t c, int ri, int rj, int rk, int push_parity, unsigned int *push_count,
-                                             int &net_changed, unsigned &evals)
+// Filter one voxel per lane (all 32 lanes must call; `valid` masks lanes without a voxel) and append it to the
+// warp's batch.  own = the voxel's {stamp|tri} word at the START of the sweep, nb = its neighbours' current words,
+// was_changed = the cell was already rewritten in this sweep.  nq / np = entries in the candidate queue / pending
+// list (warp-uniform).
+__device__ __forceinline__ void relax_filter(const RelaxParams &P, RelaxShared &sh, int warp, int lane, bool valid,
+                                             int64_t c, int ri, int rj, int rk, uint64_t cur64, uint64_t base64,
+                                             const uint32_t (&nb)[7], bool was_changed, int &nq, int &np)
 {
     const Grid &g = P.g;
-    uint32_t *const q_ent = sh.q_ent[warp];
-    float *const q_d = sh.q_d[warp];
-    const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
-    uint64_t cur64 = 0, base = 0;
-    uint32_t nb[7];
+    const uint32_t own = cell_lo(base64);
     uint32_t live = 0;
-    bool was_changed = false;
+    bool pend = false;
     if (valid) {
-        const uint64_t *cp = P.cells + c;
-        cur64 = ld_cg64(cp);
-        nb[0] = ld_cg32(cp + si); nb[1] = ld_cg32(cp + sj); nb[2] = ld_cg32(cp + si + sj); nb[3] = ld_cg32(cp + sk);
-        nb[4] = ld_cg32(cp + si + sk); nb[5] = ld_cg32(cp + sj + sk); nb[6] = ld_cg32(cp + si + sj + sk);
-        const uint64_t old64 = ld_cg64(P.oldbuf + c);                 // speculative: only meaningful if the cell changed in this sweep
-        was_changed = lo_stamp(cell_lo(cur64)) == P.stamp;
-        base = was_changed ? old64 : cur64;
         const int cls = (ri == g.ni - 1 ? 1 : 0) | (rj == g.nj - 1 ? 2 : 0) | (rk == g.nk - 1 ? 4 : 0);
-        const uint32_t own = cell_lo(base);
         const uint32_t mx = max(max(max(nb[0], nb[1]), max(nb[2], nb[3])), max(max(nb[4], nb[5]), nb[6]));
         if (mx >= sh.tmin[cls]) {
             #pragma unroll
@@ -100,48 +104,102 @@ __device__ __forceinline__ void relax_voxels(const RelaxParams &P, RelaxShared &
             }
         }
         if (live) {                           // drop repeats of ANY earlier neighbour's triangle
+            uint32_t t[7];
+            #pragma unroll
+            for (int m = 0; m < 7; ++m) t[m] = nb[m] & TRI_MASK;
             #pragma unroll
             for (int m = 1; m < 7; ++m) {
                 bool dup = false;
                 #pragma unroll
-                for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
+                for (int u = 0; u < m; ++u) dup = dup || (t[u] == t[m]);
                 if (dup) live &= ~(1u << m);
             }
         }
+        // a voxel changed earlier in this sweep must be re-derived even without candidates (it may have to revert)
+        pend = live || was_changed;
     }
+    const uint32_t bp = __ballot_sync(0xffffffffu, pend);
+    if (!bp) return;
     const int ncand = __popc(live);
     const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
                    b2 = __ballot_sync(0xffffffffu, ncand & 4);
-    // a voxel changed earlier in this sweep must be re-derived even without candidates (it may have to revert)
-    if ((b0 | b1 | b2) == 0 && !__any_sync(0xffffffffu, was_changed)) return;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-    const int off = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-    if (live) {
-        sh.px[warp][lane] = lattice(P.sd.abs_i(ri, g), g.dx, g.ox);
-        sh.py[warp][lane] = lattice(P.sd.abs_j(rj, g), g.dx, g.oy);
-        sh.pz[warp][lane] = lattice(P.sd.abs_k(rk, g), g.dx, g.oz);
+    const int off = nq + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+    const int pidx = np + __popc(bp & lt_mask);
+    if (pend) {
+        Pending &pe = sh.pend[warp][pidx];
+        pe.c = (uint32_t)c;
+        pe.px = lattice(P.sd.abs_i(ri, g), g.dx, g.ox);
+        pe.py = lattice(P.sd.abs_j(rj, g), g.dx, g.oy);
+        pe.pz = lattice(P.sd.abs_k(rk, g), g.dx, g.oz);
+        pe.info = (uint32_t)off | ((uint32_t)ncand << 16) | (ri + 1 <= g.ni - 1 ? 1u << 20 : 0u) | (rj + 1 <= g.nj - 1 ? 1u << 21 : 0u) |
+                  (rk + 1 <= P.rk_last ? 1u << 22 : 0u) | (was_changed ? 1u << 23 : 0u);
+        pe.cur_lo = cell_lo(cur64); pe.cur_hi = (uint32_t)(cur64 >> 32);
+        pe.base_lo = cell_lo(base64); pe.base_hi = (uint32_t)(base64 >> 32);
         int q = off;
         #pragma unroll
-        for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) { q_ent[q] = ((uint32_t)lane << 27) | (nb[m] & TRI_MASK); ++q; }
+        for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
+            sh.q_ent[warp][q] = nb[m] & TRI_MASK;
+            sh.q_d[warp][q] = __int_as_float(pidx);
+            ++q;
+        }
     }
+    nq += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    np += __popc(bp);
+}
+
+// The eight {stamp|tri} words a voxel's filter needs, through L1 (round 0: a value read too early is repaired by
+// the re-evaluation its writer schedules) ...
+struct Words { uint64_t own; uint32_t nb[7]; };
+__device__ __forceinline__ void load_words_l1(const uint64_t *cp, int64_t si, int64_t sj, int64_t sk, Words &w)
+{
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(cp);
+    w.own = *cp;
+    w.nb[0] = p[2 * si]; w.nb[1] = p[2 * sj]; w.nb[2] = p[2 * (si + sj)]; w.nb[3] = p[2 * sk];
+    w.nb[4] = p[2 * (si + sk)]; w.nb[5] = p[2 * (sj + sk)]; w.nb[6] = p[2 * (si + sj + sk)];
+}
+// ... or through L2 (later rounds: other SMs rewrite cells during the launch).
+__device__ __forceinline__ void load_words_l2(const uint64_t *cp, int64_t si, int64_t sj, int64_t sk, Words &w)
+{
+    w.own = ld_cg64(cp);
+    w.nb[0] = ld_cg32(cp + si); w.nb[1] = ld_cg32(cp + sj); w.nb[2] = ld_cg32(cp + si + sj); w.nb[3] = ld_cg32(cp + sk);
+    w.nb[4] = ld_cg32(cp + si + sk); w.nb[5] = ld_cg32(cp + sj + sk); w.nb[6] = ld_cg32(cp + si + sj + sk);
+}
+
+// Evaluate the warp's queue, then let every pending voxel replay its results in the reference's order.
+// solo = tail rounds run by one CTA: the next list and its length live in shared memory (entries beyond
+// SOLO_CAP spill to the global list).
+__device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &sh, int warp, int lane, int &nq, int &np,
+                                            int push_parity, unsigned int *push_count, bool solo, int &net_changed, unsigned &evals)
+{
+    if (np == 0) return;
+    const Grid &g = P.g;
+    uint32_t *const q_ent = sh.q_ent[warp];
+    float *const q_d = sh.q_d[warp];
+    const Pending *const pend = sh.pend[warp];
+    const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
     __syncwarp();
-    for (int q = lane; q < total; q += 32) {
-        const uint32_t e = q_ent[q];
-        const int ol = (int)(e >> 27);
-        const F3 x0{sh.px[warp][ol], sh.py[warp][ol], sh.pz[warp][ol]};
-        const TriRec *tr = &P.rec[e & TRI_MASK];
+    for (int q = lane; q < nq; q += 32) {
+        const Pending &pe = pend[__float_as_int(q_d[q])];
+        const F3 x0{pe.px, pe.py, pe.pz};
+        const TriRec *tr = &P.rec[q_ent[q]];
         const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
         q_d[q] = ptd_rec(x0, p, qq, r);
         ++evals;
     }
     __syncwarp();
-    if (valid) {
+    for (int pi = lane; pi < np; pi += 32) {
+        const Pending &pe = pend[pi];
+        const int64_t c = (int64_t)pe.c;
+        const uint32_t info = pe.info;
+        const bool was_changed = (info >> 23) & 1u;
+        const uint64_t cur64 = ((uint64_t)pe.cur_hi << 32) | pe.cur_lo, base = ((uint64_t)pe.base_hi << 32) | pe.base_lo;
         float phi = cell_phi(base);
         uint32_t best = TRI_NONE;
-        for (int q = off; q < off + ncand; ++q) {                     // the reference's order and strict "<"
+        const int q0 = (int)(info & 0xffffu), q1 = q0 + (int)((info >> 16) & 7u);
+        for (int q = q0; q < q1; ++q) {                               // the reference's order and strict "<"
             const float d = q_d[q];
-            if (d < phi) { phi = d; best = q_ent[q] & TRI_MASK; }
+            if (d < phi) { phi = d; best = q_ent[q]; }
         }
         const uint64_t new64 = (best != TRI_NONE) ? pack_cell(phi, (P.stamp << 27) | best) : base;
         if (new64 != cur64) {
@@ -149,95 +207,35 @@ __device__ __forceinline__ void relax_voxels(const RelaxParams &P, RelaxShared &
             P.cells[c] = new64;
             net_changed += (best != TRI_NONE ? 1 : 0) - (was_changed ? 1 : 0);
             // schedule the (up to seven) downstream neighbours that this launch updates
-            const bool pi = ri + 1 <= g.ni - 1, pj = rj + 1 <= g.nj - 1, pk = rk + 1 <= P.rk_last;
+            const bool pi_ok = (info >> 20) & 1u, pj_ok = (info >> 21) & 1u, pk_ok = (info >> 22) & 1u;
             uint32_t fresh = 0;                                       // bit m: neighbour m was not yet scheduled
             #pragma unroll
             for (int m = 1; m < 8; ++m) {                             // the atomics are independent: all in flight at once
                 const bool a = m & 1, b = m & 2, cc = m & 4;
-                if ((a && !pi) || (b && !pj) || (cc && !pk)) continue;
+                if ((a && !pi_ok) || (b && !pj_ok) || (cc && !pk_ok)) continue;
                 const int64_t d = c - (a ? si : 0) - (b ? sj : 0) - (cc ? sk : 0);
                 const uint32_t bit = 1u << (d & 31);
                 const uint32_t prev = atomicOr(&P.bitmap[push_parity][d >> 5], bit);
                 fresh |= (prev & bit) ? 0u : (1u << m);
             }
             if (fresh) {
-                unsigned idx = atomicAdd(push_count, (unsigned)__popc(fresh));
+                unsigned idx = atomicAdd(push_count, (unsigned)__popc(fresh));     // shared memory in solo mode
                 #pragma unroll
                 for (int m = 1; m < 8; ++m) if ((fresh >> m) & 1u) {
                     const bool a = m & 1, b = m & 2, cc = m & 4;
                     const int64_t d = c - (a ? si : 0) - (b ? sj : 0) - (cc ? sk : 0);
-                    if (idx < P.list_cap) P.list[push_parity][idx] = (uint32_t)d;
+                    if (solo && idx < (unsigned)SOLO_CAP) sh.slist[push_parity][idx] = (uint32_t)d;
+                    else if (idx - (solo ? (unsigned)SOLO_CAP : 0u) < P.list_cap) P.list[push_parity][idx - (solo ? (unsigned)SOLO_CAP : 0u)] = (uint32_t)d;
                     ++idx;
                 }
             }
         }
     }
     __syncwarp();
+    nq = 0; np = 0;
 }
 
-// ---- kernel 1: streaming scan --------------------------------------------------------------------------------
-// Marks (bitmap of round 0) every voxel that has at least one neighbour triangle to evaluate: one thread per
-// voxel, lanes along i, 8 rows per CTA so that the rows a CTA shares are served by L1.  Nothing is written to
-// the cells here, so the non-coherent path is fine.
-constexpr int SCAN_ROWS = 8;
-__global__ void __launch_bounds__(SCAN_ROWS * 32) k_relax_scan(RelaxParams P)
-{
-    __shared__ uint32_t thr[8][8];
-    __shared__ uint32_t tmin[8];
-    const Grid &g = P.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 64) {
-        const uint32_t l = P.last[tid >> 3][tid & 7];
-        thr[tid >> 3][tid & 7] = ((tid & 7) == 7) ? 0xffffffffu : (l ? (l + 1u) << 27 : 0u);
-    }
-    __syncthreads();
-    if (tid < 8) {
-        uint32_t t = 0xffffffffu;
-        for (int m = 0; m < 7; ++m) t = min(t, thr[tid][m]);
-        tmin[tid] = t;
-    }
-    __syncthreads();
-    const int rj = 1 + blockIdx.x * SCAN_ROWS + warp, rk = P.rk_first + blockIdx.y;
-    if (rj > g.nj - 1) return;                                        // warp-uniform
-    const int64_t row = g.cidx(0, P.sd.abs_j(rj, g), P.sd.abs_k(rk, g));
-    const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
-    const int cls_row = (rj == g.nj - 1 ? 2 : 0) | (rk == g.nk - 1 ? 4 : 0);
-    bool any_work = false;
-    #pragma unroll 4
-    for (int i0 = 0; i0 < g.ni; i0 += 32) {
-        const int i = i0 + lane;
-        const int ri = P.sd.di > 0 ? i : g.ni - 1 - i;
-        bool any_live = false;
-        if (i < g.ni && ri >= 1) {
-            const uint32_t *cp = reinterpret_cast<const uint32_t *>(P.cells + row + i);     // low words: {stamp | tri}
-            uint32_t nb[7];
-            const uint32_t own = __ldg(cp);
-            nb[0] = __ldg(cp + 2 * si); nb[1] = __ldg(cp + 2 * sj); nb[2] = __ldg(cp + 2 * (si + sj)); nb[3] = __ldg(cp + 2 * sk);
-            nb[4] = __ldg(cp + 2 * (si + sk)); nb[5] = __ldg(cp + 2 * (sj + sk)); nb[6] = __ldg(cp + 2 * (si + sj + sk));
-            const int cls = cls_row | (ri == g.ni - 1 ? 1 : 0);
-            const uint32_t mx = max(max(max(nb[0], nb[1]), max(nb[2], nb[3])), max(max(nb[4], nb[5]), nb[6]));
-            if (mx >= tmin[cls]) {
-                // (repeats of an earlier neighbour's triangle are not removed here: marking too much is harmless)
-                #pragma unroll
-                for (int m = 0; m < 7; ++m) {
-                    const uint32_t x = nb[m];
-                    any_live = any_live || (((x & TRI_MASK) != TRI_NONE) && (((x ^ own) & TRI_MASK) != 0) && (x >= thr[cls][m]));
-                }
-            }
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, any_live);
-        if (bal) {
-            const int64_t c0 = row + i0;
-            const int shf = (int)(c0 & 31);
-            if (lane == 0) atomicOr(&P.bitmap[0][c0 >> 5], bal << shf);
-            if (lane == 1 && shf && (bal >> (32 - shf))) atomicOr(&P.bitmap[0][(c0 >> 5) + 1], bal >> (32 - shf));
-            any_work = true;
-        }
-    }
-    if (any_work && lane == 0) *reinterpret_cast<volatile unsigned int *>(&P.count[0]) = 1u;          // "round 0 has work"
-}
-
-// ---- kernel 2: the rounds ---------------------------------------------------------------------------------------
+// ---- the kernel: round 0 over all voxels, then the rounds ---------------------------------------------------------------------------------------
 constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by one CTA (a CTA barrier per round
                                              // instead of a grid barrier)
 
@@ -246,7 +244,8 @@ constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by
 #endif
 __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(RelaxParams P)
 {
-    __shared__ RelaxShared sh;
+    extern __shared__ __align__(16) unsigned char relax_smem[];
+    RelaxShared &sh = *reinterpret_cast<RelaxShared *>(relax_smem);
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) {
@@ -266,27 +265,86 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     if (P.debug && blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     const int64_t gwarp = (int64_t)blockIdx.x * RX_WARPS + warp, nwarps = (int64_t)gridDim.x * RX_WARPS;
 
-    // Round r reads the list of parity r&1 (length count[r%3]) and fills the other one (count[(r+1)%3]);
-    // count[(r+2)%3] was consumed in round r-1 and is refilled in round r+1: reset it now.  Once a list is
-    // short, CTA 0 finishes alone (a CTA barrier per round instead of a grid barrier); a list that grows again
-    // is still handled correctly, just by that CTA.
     const Grid &g = P.g;
-    const int64_t plane = g.plane();
+    const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
+    int nq = 0, np = 0;
+
+    // ---- round 0: every voxel the sweep updates.  CTA = 8 consecutive rows of one plane (warp = row, lanes
+    // along i); the words of the next 32 voxels are loaded while the current ones are filtered. -------------
+    {
+        const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
+        const int jblocks = (nrows + RX_WARPS - 1) / RX_WARPS;
+        const int64_t nitems = (int64_t)jblocks * nplanes;
+        for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+            const int rk = P.rk_first + (int)(it / jblocks);
+            const int rj = 1 + (int)(it % jblocks) * RX_WARPS + warp;
+            if (rj > g.nj - 1) continue;                              // warp-uniform
+            const uint64_t *row = P.cells + g.cidx(0, P.sd.abs_j(rj, g), P.sd.abs_k(rk, g));
+            const int i_skip = P.sd.di > 0 ? 0 : g.ni - 1;            // the ri = 0 voxel is only read
+            Words wa, wb;
+            bool va = lane < g.ni && lane != i_skip, vb = false;
+            if (va) load_words_l1(row + lane, si, sj, sk, wa);
+            for (int i0 = 0; i0 < g.ni; i0 += 64) {
+                {
+                    const int i = i0 + 32 + lane;
+                    vb = i < g.ni && i != i_skip;
+                    if (vb) load_words_l1(row + i, si, sj, sk, wb);
+                }
+                {
+                    const int i = i0 + lane;
+                    relax_filter(P, sh, warp, lane, va, (row - P.cells) + i, P.sd.di > 0 ? i : g.ni - 1 - i, rj, rk, wa.own, wa.own, wa.nb, false, nq, np);
+                    if (nq > QCAP_B - 7 * 32 || np > PCAP_B - 32) relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
+                }
+                if (i0 + 32 >= g.ni) break;
+                {
+                    const int i = i0 + 64 + lane;
+                    va = i < g.ni && i != i_skip;
+                    if (va) load_words_l1(row + i, si, sj, sk, wa);
+                }
+                {
+                    const int i = i0 + 32 + lane;
+                    relax_filter(P, sh, warp, lane, vb, (row - P.cells) + i, P.sd.di > 0 ? i : g.ni - 1 - i, rj, rk, wb.own, wb.own, wb.nb, false, nq, np);
+                    if (nq > QCAP_B - 7 * 32 || np > PCAP_B - 32) relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
+                }
+            }
+        }
+        relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
+    }
+    grid.sync();
+    if (P.debug && blockIdx.x == 0 && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        P.debug[0] = t - t_start; P.debug[2] = P.count[1];
+    }
+
+    // ---- rounds 1, 2, ...: round r reads the list of parity r&1 (length count[r%3]) and fills the other one
+    // (count[(r+1)%3]); count[(r+2)%3] was consumed in round r-1 and is refilled in round r+1: reset it now.
+    // Once a list is short, CTA 0 finishes alone (a CTA barrier per round instead of a grid barrier); a list
+    // that grows again is still handled correctly, just by that CTA. ------------------------------------------
+    const uint32_t plane32 = (uint32_t)g.plane();
     const int64_t nwords = (g.cell_count() + 31) >> 5;
-    int r = 0;
+    int r = 1;
     bool solo = false;
     for (;; ++r) {
-        const unsigned n = *reinterpret_cast<volatile unsigned int *>(&P.count[r % 3]);
+        const int par = r & 1;
+        unsigned n = solo ? *reinterpret_cast<volatile unsigned int *>(&sh.scount[r % 3])
+                          : *reinterpret_cast<volatile unsigned int *>(&P.count[r % 3]);
         if (n == 0) break;
-        if (!solo && r > 0 && n <= SOLO_MAX) {                        // uniform over the grid
+        if (P.debug && blockIdx.x == 0 && tid == 0 && r < 250) {
+            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            P.debug[4 + 2 * r] = n; P.debug[5 + 2 * r] = t - t_start;
+        }
+        if (!solo && n <= SOLO_MAX) {                                 // uniform over the grid
             solo = true;
             if (blockIdx.x != 0) break;
+            for (unsigned t = tid; t < n; t += RX_THREADS) sh.slist[par][t] = __ldcg(&P.list[par][t]);     // import the list
+            if (tid == 0) sh.scount[(r + 1) % 3] = 0;
+            __syncthreads();
         }
-        if (blockIdx.x == 0 && tid == 0) P.count[(r + 2) % 3] = 0;
-        unsigned int *const push_count = &P.count[(r + 1) % 3];
-        const int par = r & 1;
-        // the work list: the bitmap in round 0 (filled by the scan kernel) and when a list overflowed, else the list
-        const bool use_bitmap = (r == 0) || n > P.list_cap;
+        if (solo) { if (tid == 0) sh.scount[(r + 2) % 3] = 0; }
+        else if (blockIdx.x == 0 && tid == 0) P.count[(r + 2) % 3] = 0;
+        unsigned int *const push_count = solo ? &sh.scount[(r + 1) % 3] : &P.count[(r + 1) % 3];
+        // the bitmap is the work list when a list overflowed
+        const bool use_bitmap = n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
         const int64_t w = solo ? warp : gwarp, nw = solo ? RX_WARPS : nwarps;
         const int64_t limit = use_bitmap ? nwords : (int64_t)n;
         for (int64_t pos = w * 32; pos < limit; pos += nw * 32) {
@@ -310,27 +368,34 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
                 } else {
                     valid = pos + lane < (int64_t)n;
                     if (valid) {
-                        c = (int64_t)__ldcg(&P.list[par][pos + lane]);
+                        const int64_t idx = pos + lane;
+                        if (solo) c = idx < SOLO_CAP ? (int64_t)sh.slist[par][idx] : (int64_t)__ldcg(&P.list[par][idx - SOLO_CAP]);
+                        else c = (int64_t)__ldcg(&P.list[par][idx]);
                         atomicAnd(&P.bitmap[par][c >> 5], ~(1u << (c & 31)));
                     }
                 }
                 int ri = 0, rj = 0, rk = 0;
-                if (valid) {
-                    const int64_t p = c / plane, rem = c - p * plane;
-                    const int j = (int)(rem / g.ni), i = (int)(rem - (int64_t)j * g.ni), k = (int)p - 1 + g.k_lo;
+                Words wd;
+                uint64_t base64 = 0;
+                bool was_changed = false;
+                if (valid) {                                          // cell indices fit 32 bits (sweep_relax_supported)
+                    const uint32_t p = (uint32_t)c / plane32, rem = (uint32_t)c - p * plane32;
+                    const int j = (int)(rem / (uint32_t)g.ni), i = (int)(rem - (uint32_t)j * (uint32_t)g.ni), k = (int)p - 1 + g.k_lo;
                     ri = P.sd.di > 0 ? i : g.ni - 1 - i;
                     rj = P.sd.dj > 0 ? j : g.nj - 1 - j;
                     rk = P.sd.rel_k(k, g);
+                    load_words_l2(P.cells + c, si, sj, sk, wd);
+                    const uint64_t old64 = ld_cg64(P.oldbuf + c);     // speculative: only meaningful if the cell changed in this sweep
+                    was_changed = lo_stamp(cell_lo(wd.own)) == P.stamp;
+                    base64 = was_changed ? old64 : wd.own;
                 }
-                relax_voxels(P, sh, warp, lane, valid, c, ri, rj, rk, par ^ 1, push_count, net_changed, evals);
+                relax_filter(P, sh, warp, lane, valid, c, ri, rj, rk, wd.own, base64, wd.nb, was_changed, nq, np);
+                if (nq > QCAP_B - 7 * 32 || np > PCAP_B - 32) relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
             }
         }
-        if (solo) __syncthreads();                                    // orders the CTA's global writes and reads
+        relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
+        if (solo) __syncthreads();                                    // orders the CTA's writes (global and shared) and reads
         else grid.sync();
-        if (r == 0 && P.debug && blockIdx.x == 0 && tid == 0) {
-            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            P.debug[0] = t - t_start; P.debug[2] = P.count[1];
-        }
     }
     if (P.debug && blockIdx.x == 0 && tid == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -385,26 +450,31 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax_rounds, RX_THREADS, 0);
+    const size_t smem = sizeof(RelaxShared);
+    cudaFuncSetAttribute(k_relax_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax_rounds, RX_THREADS, smem);
     if (occ < 1) occ = 1;
     static unsigned long long *dbg = nullptr;
     if (getenv("SDFB_RELAX_DEBUG")) {
-        if (!dbg) cudaMalloc(&dbg, 4 * sizeof(unsigned long long));
-        cudaMemsetAsync(dbg, 0, 4 * sizeof(unsigned long long), st);
+        if (!dbg) cudaMalloc(&dbg, 512 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbg, 0, 512 * sizeof(unsigned long long), st);
         P.debug = dbg;
     }
-    const dim3 sgrid((g.nj - 1 + SCAN_ROWS - 1) / SCAN_ROWS, rk_hi - rk_lo + 1);
-    k_relax_scan<<<sgrid, SCAN_ROWS * 32, 0, st>>>(P);
     void *args[] = {&P};
-    cudaLaunchCooperativeKernel((const void *)k_relax_rounds, dim3(sms * occ), dim3(RX_THREADS), args, 0, st);
+    cudaLaunchCooperativeKernel((const void *)k_relax_rounds, dim3(sms * occ), dim3(RX_THREADS), args, smem, st);
     if (P.debug) {
-        unsigned long long h[4];
+        unsigned long long h[512];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        if (atoi(getenv("SDFB_RELAX_DEBUG")) > 1) {
+            fprintf(stderr, "[relax] sweep %2d rounds (n @ us):", sweep_index);
+            for (int r = 1; r < 250 && h[4 + 2 * r]; ++r) fprintf(stderr, " %llu@%.0f", h[4 + 2 * r], h[5 + 2 * r] * 1e-3);
+            fprintf(stderr, "\n");
+        }
         fprintf(stderr, "[relax] sweep %2d: round 0 %.3f ms, total %.3f ms, first list %llu, rounds %llu, grid %d x %d\n", sweep_index,
                 h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], sms * occ, RX_THREADS);
     }
-    return 2;
+    return 1;
 }
 
 }  // namespace sdfb

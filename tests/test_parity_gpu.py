@@ -157,26 +157,31 @@ def test_slab_plans_band_and_sign_match_full_grid():
 
 def test_full_size_512_properties():
     """BASELINE configs[2] at full size (512^3, 1,310,720 triangles), where the CPU oracle would take ~10 min:
-    size-independent checks.  (1) the production column schedule equals the trivially ordered per-level
-    schedule bit for bit (phi, closest_tri, counts); (2) every voxel's |phi| is exactly the reference
+    size-independent checks.  (1) the production schedule (pipelined columns for the first pass, relaxation for the
+    second) and the all-columns schedule equal the trivially ordered per-level schedule bit for bit (phi,
+    closest_tri, counts); (2) every voxel's |phi| is exactly the reference
     distance to the triangle it names (sampled, checked with the CPU oracle's point_triangle_distance);
     (3) signs and distances agree with the analytic sphere; (4) a second run on the same plan is identical."""
     w = meshes.workload("c2_icosphere_512")
     n = 512
     res = {}
     for sched, flags in SCHEDULES:
+        if sched not in ("default", "columns", "levels"):
+            continue
         p = _lib.Plan(n, n, n, flags=flags)
         p.set_mesh_host(w["vertices"], w["triangles"])
         p.run(w["origin"], w["dx"], 1)
         phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
-        if sched == "columns":
+        if sched == "default":
             p.run(w["origin"], w["dx"], 1)
             phi2, tri2, _ = p.download(phi=True, tri=True)
             assert _same(phi, phi2) and _same(tri, tri2)
         res[sched] = (phi, tri, cnt)
         p.close()
-    a, b = res["columns"], res["levels"]
+    a, b = res["default"], res["levels"]
     assert _same(a[0], b[0]) and _same(a[1], b[1]) and _same(a[2], b[2])
+    c = res["columns"]
+    assert _same(c[0], b[0]) and _same(c[1], b[1]) and _same(c[2], b[2])
     phi, tri, cnt = a
     assert int(cnt.sum()) > 0 and int((tri < 0).sum()) == 0
     # (2) sampled self-consistency against the CPU oracle's distance function
