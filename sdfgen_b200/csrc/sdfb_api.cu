@@ -83,6 +83,7 @@ struct sdfb_plan {
     uint64_t tri_own_cap = 0, xyz_own_cap = 0;
     TriRec *rec = nullptr;
     uint32_t *units = nullptr;
+    TriExt *ext = nullptr;
     uint64_t *prefix = nullptr, *block_sums = nullptr;
     uint64_t rec_cap = 0;
     bool have_mesh = false, have_band = false, have_sign = false;
@@ -94,9 +95,9 @@ namespace {
 
 void free_mesh(sdfb_plan *p)
 {
-    cudaFree(p->tri_own); cudaFree(p->xyz_own); cudaFree(p->rec); cudaFree(p->units);
+    cudaFree(p->tri_own); cudaFree(p->xyz_own); cudaFree(p->rec); cudaFree(p->units); cudaFree(p->ext);
     cudaFree(p->prefix); cudaFree(p->block_sums);
-    p->tri_own = nullptr; p->xyz_own = nullptr; p->rec = nullptr; p->units = nullptr;
+    p->tri_own = nullptr; p->xyz_own = nullptr; p->rec = nullptr; p->units = nullptr; p->ext = nullptr;
     p->tri_own_cap = 0; p->xyz_own_cap = 0;
     p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0; p->have_mesh = false;
 }
@@ -104,11 +105,12 @@ void free_mesh(sdfb_plan *p)
 int ensure_mesh_capacity(sdfb_plan *p, uint64_t ntri)
 {
     if (ntri <= p->rec_cap && p->rec) return SDFB_OK;
-    cudaFree(p->rec); cudaFree(p->units); cudaFree(p->prefix); cudaFree(p->block_sums);
-    p->rec = nullptr; p->units = nullptr; p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0;
+    cudaFree(p->rec); cudaFree(p->units); cudaFree(p->ext); cudaFree(p->prefix); cudaFree(p->block_sums);
+    p->rec = nullptr; p->units = nullptr; p->ext = nullptr; p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0;
     uint64_t cap = ntri ? ntri : 1;
     CU(cudaMalloc(&p->rec, cap * sizeof(TriRec)));
     CU(cudaMalloc(&p->units, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&p->ext, cap * sizeof(TriExt)));
     CU(cudaMalloc(&p->prefix, (cap + 1) * sizeof(uint64_t)));
     CU(cudaMalloc(&p->block_sums, (cap / 2048 + 2) * sizeof(uint64_t)));
     p->rec_cap = cap;
@@ -269,7 +271,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     CU(cudaMemsetAsync(p->counts, 0, (size_t)p->g.slab_voxels() * sizeof(int32_t), st));
     CU(cudaMemsetAsync(p->changed, 0, 2 * sizeof(unsigned long long), st));
     if (p->progress) { CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st)); p->epoch = 0; }
-    g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
+    g_launches += launch_band(p->rec, p->ntri, p->g, p->units, p->ext, p->prefix, p->block_sums, p->cells, p->counts, p->init_phi, st);
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
     p->have_band = true; p->have_sign = false; p->timed = false; p->last_sweep = -1;

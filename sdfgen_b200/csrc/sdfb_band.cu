@@ -78,14 +78,20 @@ __device__ __forceinline__ void tri_boxes(const TriRec &t, const Grid &g, TriBox
 
 __device__ __forceinline__ uint32_t units_of(uint64_t n) { return (uint32_t)((n + UNIT - 1) / UNIT); }
 
-// units[t] = band units + crossing units of triangle t
-__global__ void k_count_units(const TriRec *__restrict__ rec, uint64_t ntri, Grid g, uint32_t *__restrict__ units)
+// units[t] = band units + crossing units of triangle t; the integer extents are kept for k_band (the nine fp64
+// divisions behind them cost more than the 48 bytes)
+__global__ void k_count_units(const TriRec *__restrict__ rec, uint64_t ntri, Grid g, uint32_t *__restrict__ units,
+                              TriExt *__restrict__ ext)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntri) return;
     TriBoxes b;
     tri_boxes(rec[t], g, b);
     units[t] = units_of(b.band_voxels()) + units_of(b.cross_points());
+    TriExt e;
+    e.i0 = b.i0; e.i1 = b.i1; e.j0 = b.j0; e.j1 = b.j1; e.k0 = b.k0; e.k1 = b.k1;
+    e.cj0 = b.cj0; e.cj1 = b.cj1; e.ck0 = b.ck0; e.ck1 = b.ck1; e.pad0 = 0; e.pad1 = 0;
+    ext[t] = e;
 }
 
 // ---- exclusive prefix sum of uint32 -> uint64, three passes ------------------------------------
@@ -177,32 +183,40 @@ __global__ void __launch_bounds__(256) k_scan_final(const uint32_t *__restrict__
 }
 
 // ---- the band + crossing-count kernel ----------------------------------------------------------
-// Persistent grid; each warp takes work units round-robin.  prefix[t] <= unit < prefix[t+1].
-__global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, uint64_t ntri, Grid g,
+// Persistent grid; each warp takes a CONTIGUOUS range of work units, so the triangle of a unit is found by
+// one binary search per warp (prefix[t] <= unit < prefix[t+1]) and then by walking forward.
+__global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, const TriExt *__restrict__ ext, uint64_t ntri, Grid g,
                                               const uint64_t *__restrict__ prefix,
                                               uint64_t *__restrict__ cells, int32_t *__restrict__ counts,
                                               float init_phi)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t total = prefix[ntri];
-    for (uint64_t unit = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); unit < total; unit += warps) {
-        // binary search: largest t with prefix[t] <= unit
-        uint64_t lo = 0, hi = ntri;          // invariant: prefix[lo] <= unit < prefix[hi]
+    const uint64_t per = (total + warps - 1) / warps;
+    const uint64_t u0 = wid * per, u1 = min(total, u0 + per);
+    if (u0 >= u1) return;
+    uint64_t t;
+    {
+        uint64_t lo = 0, hi = ntri;          // invariant: prefix[lo] <= u0 < prefix[hi]
         while (hi - lo > 1) {
             uint64_t mid = (lo + hi) >> 1;
-            if (__ldg(&prefix[mid]) <= unit) lo = mid; else hi = mid;
+            if (__ldg(&prefix[mid]) <= u0) lo = mid; else hi = mid;
         }
-        const uint64_t t = lo;
+        t = lo;
+    }
+    uint64_t t_end = __ldg(&prefix[t + 1]);  // first unit of the next triangle
+    for (uint64_t unit = u0; unit < u1; ++unit) {
+        while (t_end <= unit) { ++t; t_end = __ldg(&prefix[t + 1]); }      // skips triangles without units
         const uint32_t local = (uint32_t)(unit - __ldg(&prefix[t]));
         const TriRec tr = rec[t];
-        TriBoxes b;
-        tri_boxes(tr, g, b);
-        const uint64_t nvox = b.band_voxels();
+        const TriExt e = ext[t];
+        const uint64_t nvox = (e.k1 < e.k0) ? 0 : (uint64_t)(e.i1 - e.i0 + 1) * (uint64_t)(e.j1 - e.j0 + 1) * (uint64_t)(e.k1 - e.k0 + 1);
         const uint32_t nband = units_of(nvox);
         if (local < nband) {
             // exact band: voxels [local*UNIT, ...) of the box, i fastest so a warp touches few lines
-            const uint32_t wi = b.i1 - b.i0 + 1, wj = b.j1 - b.j0 + 1;
+            const uint32_t wi = e.i1 - e.i0 + 1, wj = e.j1 - e.j0 + 1;
             const uint64_t v0 = (uint64_t)local * UNIT;
             const uint64_t v1 = min(nvox, v0 + UNIT);
             const bool small = nvox <= 0xffffffffull;   // 32-bit div/mod for all but absurd boxes
@@ -210,10 +224,10 @@ __global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, ui
                 uint32_t i, j, k;
                 if (small) {
                     uint32_t vv = (uint32_t)v, r = vv / wi;
-                    i = b.i0 + (vv - r * wi); k = r / wj; j = b.j0 + (r - k * wj); k += b.k0;
+                    i = e.i0 + (vv - r * wi); k = r / wj; j = e.j0 + (r - k * wj); k += e.k0;
                 } else {
                     uint64_t r = v / wi;
-                    i = b.i0 + (uint32_t)(v - r * wi); k = (uint32_t)(r / wj); j = b.j0 + (uint32_t)(r - (uint64_t)k * wj); k += b.k0;
+                    i = e.i0 + (uint32_t)(v - r * wi); k = (uint32_t)(r / wj); j = e.j0 + (uint32_t)(r - (uint64_t)k * wj); k += e.k0;
                 }
                 F3 gx{lattice(i, g.dx, g.ox), lattice(j, g.dx, g.oy), lattice(k, g.dx, g.oz)};
                 float d = ptd_rec(gx, tr);
@@ -225,16 +239,19 @@ __global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, ui
             }
         } else {
             // x-ray crossings: lattice points [ (local-nband)*UNIT, ... ) of the yz range
-            const uint64_t npts = b.cross_points();
-            const uint32_t wj = b.cj1 - b.cj0 + 1;
+            const uint64_t npts = (e.ck1 < e.ck0 || e.cj1 < e.cj0) ? 0 : (uint64_t)(e.cj1 - e.cj0 + 1) * (uint64_t)(e.ck1 - e.ck0 + 1);
+            const uint32_t wj = e.cj1 - e.cj0 + 1;
             const uint64_t a0 = (uint64_t)(local - nband) * UNIT;
             const uint64_t a1 = min(npts, a0 + UNIT);
+            const double fip = grid_coord(tr.p.x, g.ox, g.dx), fjp = grid_coord(tr.p.y, g.oy, g.dx), fkp = grid_coord(tr.p.z, g.oz, g.dx);
+            const double fiq = grid_coord(tr.q.x, g.ox, g.dx), fjq = grid_coord(tr.q.y, g.oy, g.dx), fkq = grid_coord(tr.q.z, g.oz, g.dx);
+            const double fir = grid_coord(tr.r.x, g.ox, g.dx), fjr = grid_coord(tr.r.y, g.oy, g.dx), fkr = grid_coord(tr.r.z, g.oz, g.dx);
             for (uint64_t a = a0 + lane; a < a1; a += 32) {
-                int j = b.cj0 + (int)(a % wj);
-                int k = b.ck0 + (int)(a / wj);
+                int j = e.cj0 + (int)(a % wj);
+                int k = e.ck0 + (int)(a / wj);
                 double ba, bb, bc;
-                if (point_in_triangle_2d((double)j, (double)k, b.fjp, b.fkp, b.fjq, b.fkq, b.fjr, b.fkr, ba, bb, bc)) {
-                    double fi = __dadd_rn(__dadd_rn(__dmul_rn(ba, b.fip), __dmul_rn(bb, b.fiq)), __dmul_rn(bc, b.fir));
+                if (point_in_triangle_2d((double)j, (double)k, fjp, fkp, fjq, fkq, fjr, fkr, ba, bb, bc)) {
+                    double fi = __dadd_rn(__dadd_rn(__dmul_rn(ba, fip), __dmul_rn(bb, fiq)), __dmul_rn(bc, fir));
                     int ii = d2i_trunc(ceil(fi));
                     if (ii < 0) atomicAdd(&counts[g.vidx(0, j, k)], 1);
                     else if (ii < g.ni) atomicAdd(&counts[g.vidx(ii, j, k)], 1);
@@ -262,16 +279,16 @@ int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, TriRec
     return 1;
 }
 
-int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units, uint64_t *prefix,
+int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units, TriExt *ext, uint64_t *prefix,
                 uint64_t *block_sums, uint64_t *cells, int32_t *counts, float init_phi, cudaStream_t st)
 {
     if (ntri == 0) return 0;
     unsigned nb = (unsigned)((ntri + SCAN_TILE - 1) / SCAN_TILE);
-    k_count_units<<<(unsigned)((ntri + 255) / 256), 256, 0, st>>>(rec, ntri, g, units);
+    k_count_units<<<(unsigned)((ntri + 255) / 256), 256, 0, st>>>(rec, ntri, g, units, ext);
     k_scan_reduce<<<nb, 256, 0, st>>>(units, ntri, block_sums);
     k_scan_block_sums<<<1, 1024, 0, st>>>(block_sums, nb);
     k_scan_final<<<nb, 256, 0, st>>>(units, ntri, block_sums, nb, prefix);
-    k_band<<<148 * 8, 256, 0, st>>>(rec, ntri, g, prefix, cells, counts, init_phi);
+    k_band<<<148 * 8, 256, 0, st>>>(rec, ext, ntri, g, prefix, cells, counts, init_phi);
     return 5;
 }
 

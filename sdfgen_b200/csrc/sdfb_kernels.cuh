@@ -24,12 +24,16 @@ struct Grid {
     __host__ __device__ int64_t vidx(int i, int j, int k) const { return (int64_t)i + (int64_t)ni * ((int64_t)j + (int64_t)nj * (int64_t)(k - k_lo)); }
 };
 
+// Integer extents of one triangle on the grid (sdfb_band.cu): exact-band box and yz lattice range of the x-ray test,
+// both inclusive and clipped to the slab's planes.
+struct __align__(16) TriExt { int i0, i1, j0, j1, k0, k1, cj0, cj1, ck0, ck1, pad0, pad1; };
+
 struct Launches { uint64_t n = 0; };
 
 // all launchers enqueue on `st` and return the number of kernels launched
 int launch_init(uint64_t *cells, int64_t ncells, float init_phi, cudaStream_t st);
 int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, TriRec *rec, cudaStream_t st);
-int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units, uint64_t *prefix,
+int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units, TriExt *ext, uint64_t *prefix,
                 uint64_t *block_sums, uint64_t *cells, int32_t *counts, float init_phi, cudaStream_t st);
 int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                         unsigned long long *changed, cudaStream_t st);

@@ -43,8 +43,8 @@ namespace sdfb {
 
 namespace {
 
-// 8 x 16 columns at 4 CTAs per SM measured ~5 % faster than 16 x 16 at 2 (same voxels in flight, more independent
-// barrier domains); 16 x 8 and 8 x 8 were slower.
+// 8 x 16 columns at 3-4 CTAs per SM measured ~6 % faster than 16 x 16 at 2 (more independent barrier domains);
+// 16 x 8 and 8 x 8 were slower.  Two queue entries per lane and trip (ILP) measured 25 % SLOWER, with or without spills.
 #ifndef SDFB_EJ
 #define SDFB_EJ 8
 #endif
@@ -130,7 +130,8 @@ __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restric
     uint32_t *const q_ent = &sh.q_ent[0][0];
     float *const q_d = &sh.q_d[0][0];
     unsigned evals = 0;
-    for (int q = first; q < total; q += NSTEPPERS) {
+    int q = first;
+    for (; q < total; q += NSTEPPERS) {
         const int ot = __float_as_int(q_d[q]);                         // owner lane, replaced by the distance
         const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
         const TriRec *tr = &rec[q_ent[q]];
@@ -552,7 +553,7 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 }
 
 #ifndef SDFB_MINB
-#define SDFB_MINB 4
+#define SDFB_MINB 3
 #endif
 template <bool CTA_QUEUE>
 __global__ void __launch_bounds__(NTHREADS, SDFB_MINB)

@@ -270,12 +270,27 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     int nq = 0, np = 0;
 
     // ---- round 0: every voxel the sweep updates.  CTA = 8 consecutive rows of one plane (warp = row, lanes
-    // along i); the words of the next 32 voxels are loaded while the current ones are filtered. -------------
+    // along the row); the words of the next 32 voxels are loaded while the current ones are filtered. -------
     {
         const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
         const int jblocks = (nrows + RX_WARPS - 1) / RX_WARPS;
         const int64_t nitems = (int64_t)jblocks * nplanes;
+        // each warp asks L2 for the row of its NEXT item (one bulk prefetch per 2 KB) while it works on the current
+        // one: the few warps an SM holds cannot keep enough loads in flight to hide DRAM latency themselves
+        auto prefetch_row = [&](int64_t item) {
+            if (item >= nitems) return;
+            const int prk = P.rk_first + (int)(item / jblocks), prj = 1 + (int)(item % jblocks) * RX_WARPS + warp;
+            if (prj > g.nj - 1) return;
+            const uintptr_t beg = reinterpret_cast<uintptr_t>(P.cells + g.cidx(0, P.sd.abs_j(prj, g), P.sd.abs_k(prk, g))) & ~(uintptr_t)15;
+            const uint32_t bytes = ((uint32_t)g.ni * 8u + 16u) & ~15u;
+            for (uint32_t o = (uint32_t)lane * 2048u; o < bytes; o += 32u * 2048u) {
+                const uint32_t len = min(2048u, bytes - o);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg + o), "r"(len) : "memory");
+            }
+        };
+        prefetch_row(blockIdx.x);
         for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+            prefetch_row(it + gridDim.x);
             const int rk = P.rk_first + (int)(it / jblocks);
             const int rj = 1 + (int)(it % jblocks) * RX_WARPS + warp;
             if (rj > g.nj - 1) continue;                              // warp-uniform
