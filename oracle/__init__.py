@@ -84,6 +84,9 @@ class _Port:
             L.sdfo_emu_sweep_columns.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
                                                  C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
             L.sdfo_emu_flag_violations.restype = C.c_long
+            L.sdfo_emu_sweep_relax.restype = C.c_long
+            L.sdfo_emu_sweep_relax.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_long), C.POINTER(C.c_long)]
             self._lib = L
         return self._lib
 
@@ -109,6 +112,30 @@ class _Port:
         lo = clo[plane:plane * (nkl + 1)]
         tri = np.where((lo & 0x07FFFFFF) == 0x07FFFFFF, -1, (lo & 0x07FFFFFF).astype(np.int64)).astype(np.int32)
         return cphi[plane:plane * (nkl + 1)].copy(), tri, evals, changed, int(self.lib().sdfo_emu_flag_violations())
+
+    def emu_sweep_mixed(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16, relax_from=8, seed=1):
+        """CPU emulation of the production schedule mix: column emulation for sweeps < relax_from, relaxation
+        emulation (oracle/relax_emu.c, seeded random order) from there on.
+        Returns (phi_swept, tri_final, evals_per_sweep, changed_per_sweep, rounds_per_sweep)."""
+        v, t, o = _prep(vertices, triangles, origin)
+        plane = ni * nj
+        init = np.float32(np.float32(ni + nj + nk) * np.float32(dx))
+        cphi = np.full(plane * (nk + 2), init, np.float32)
+        clo = np.full(plane * (nk + 2), 0xFFFFFFFF, np.uint32)
+        cphi[plane:plane * (nk + 1)] = phi_band
+        tb = np.asarray(tri_band)
+        clo[plane:plane * (nk + 1)] = np.where(tb < 0, np.uint32(0xFFFFFFFF), tb.astype(np.uint32))
+        evals, changed, rounds = [], [], []
+        for s in range(nsweeps):
+            ch, rd = C.c_long(), C.c_long()
+            if s < relax_from:
+                e = self.lib().sdfo_emu_sweep_columns(t, v, cphi, clo, o, dx, ni, nj, nk, 0, nk, s, C.byref(ch))
+            else:
+                e = self.lib().sdfo_emu_sweep_relax(t, v, cphi, clo, o, dx, ni, nj, nk, 0, nk, s, seed + s, C.byref(ch), C.byref(rd))
+            evals.append(int(e)); changed.append(int(ch.value)); rounds.append(int(rd.value))
+        lo = clo[plane:plane * (nk + 1)]
+        tri = np.where((lo & 0x07FFFFFF) == 0x07FFFFFF, -1, (lo & 0x07FFFFFF).astype(np.int64)).astype(np.int32)
+        return cphi[plane:plane * (nk + 1)].copy(), tri, evals, changed, rounds
 
     def make_level_set3(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1):
         """Signed phi only (flat, i fastest)."""

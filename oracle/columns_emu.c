@@ -17,7 +17,7 @@
 
 float sdfo_point_triangle_distance(const float *x0, const float *x1, const float *x2, const float *x3);
 
-#define EJ 16
+#define EJ 8
 #define EK 16
 #define NCOMPUTE (EJ*EK)
 #define NLANES (NCOMPUTE + 64)

@@ -48,7 +48,7 @@ struct RelaxParams {
     const TriRec *rec;
     uint32_t *list[2];                       // cell indices to re-evaluate, by round parity
     uint32_t *bitmap[2];                     // one bit per cell: "is in the list of that parity"
-    unsigned int *count;                     // [3] list lengths, rotating by round % 3
+    unsigned int *count;                     // [0..2] list lengths, rotating by round % 3; [4] grid barrier arrivals
     unsigned long long *debug;               // SDFB_RELAX_DEBUG: {ns round 0, ns total, round-1 list length, rounds}
     unsigned long long *changed;             // [0] cells whose triangle changed (net), [1] distance evaluations
     uint8_t last[8][8];
@@ -235,6 +235,22 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
     nq = 0; np = 0;
 }
 
+// Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one arrival counter that only grows;
+// `target` is the value it reaches when every CTA has arrived at this barrier.  Several times cheaper than
+// cooperative_groups' grid.sync() here, and the rounds are all latency.
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*reinterpret_cast<volatile unsigned int *>(ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // ---- the kernel: round 0 over all voxels, then the rounds ---------------------------------------------------------------------------------------
 constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by one CTA (a CTA barrier per round
                                              // instead of a grid barrier)
@@ -246,7 +262,6 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
 {
     extern __shared__ __align__(16) unsigned char relax_smem[];
     RelaxShared &sh = *reinterpret_cast<RelaxShared *>(relax_smem);
-    cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) {
         const uint32_t l = P.last[tid >> 3][tid & 7];
@@ -325,7 +340,8 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         }
         relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
     }
-    grid.sync();
+    unsigned int bar_target = 0;
+    grid_barrier(&P.count[4], bar_target);
     if (P.debug && blockIdx.x == 0 && tid == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         P.debug[0] = t - t_start; P.debug[2] = P.count[1];
@@ -410,7 +426,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         }
         relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
         if (solo) __syncthreads();                                    // orders the CTA's writes (global and shared) and reads
-        else grid.sync();
+        else grid_barrier(&P.count[4], bar_target);
     }
     if (P.debug && blockIdx.x == 0 && tid == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
