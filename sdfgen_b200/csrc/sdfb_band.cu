@@ -22,10 +22,17 @@ __global__ void k_init_cells(uint64_t *cells, int64_t n, uint64_t init_cell)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // two cells per 16-byte store
+    // two cells per 16-byte store, four stores in flight per thread
     ulonglong2 v = make_ulonglong2(init_cell, init_cell);
     int64_t n2 = n >> 1;
-    for (int64_t c = i; c < n2; c += stride) reinterpret_cast<ulonglong2 *>(cells)[c] = v;
+    int64_t c = i;
+    for (; c + 3 * stride < n2; c += 4 * stride) {
+        reinterpret_cast<ulonglong2 *>(cells)[c] = v;
+        reinterpret_cast<ulonglong2 *>(cells)[c + stride] = v;
+        reinterpret_cast<ulonglong2 *>(cells)[c + 2 * stride] = v;
+        reinterpret_cast<ulonglong2 *>(cells)[c + 3 * stride] = v;
+    }
+    for (; c < n2; c += stride) reinterpret_cast<ulonglong2 *>(cells)[c] = v;
     if (i == 0 && (n & 1)) cells[n - 1] = init_cell;
 }
 
@@ -185,7 +192,10 @@ __global__ void __launch_bounds__(256) k_scan_final(const uint32_t *__restrict__
 // ---- the band + crossing-count kernel ----------------------------------------------------------
 // Persistent grid; each warp takes a CONTIGUOUS range of work units, so the triangle of a unit is found by
 // one binary search per warp (prefix[t] <= unit < prefix[t+1]) and then by walking forward.
-__global__ void __launch_bounds__(256) k_band(const TriRec *__restrict__ rec, const TriExt *__restrict__ ext, uint64_t ntri, Grid g,
+#ifndef SDFB_BAND_MINB
+#define SDFB_BAND_MINB 4
+#endif
+__global__ void __launch_bounds__(256, SDFB_BAND_MINB) k_band(const TriRec *__restrict__ rec, const TriExt *__restrict__ ext, uint64_t ntri, Grid g,
                                               const uint64_t *__restrict__ prefix,
                                               uint64_t *__restrict__ cells, int32_t *__restrict__ counts,
                                               float init_phi)
@@ -288,7 +298,7 @@ int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units
     k_scan_reduce<<<nb, 256, 0, st>>>(units, ntri, block_sums);
     k_scan_block_sums<<<1, 1024, 0, st>>>(block_sums, nb);
     k_scan_final<<<nb, 256, 0, st>>>(units, ntri, block_sums, nb, prefix);
-    k_band<<<148 * 8, 256, 0, st>>>(rec, ext, ntri, g, prefix, cells, counts, init_phi);
+    k_band<<<148 * SDFB_BAND_MINB * 2, 256, 0, st>>>(rec, ext, ntri, g, prefix, cells, counts, init_phi);
     return 5;
 }
 

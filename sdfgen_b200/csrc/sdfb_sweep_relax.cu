@@ -57,9 +57,18 @@ struct RelaxParams {
 // Per-warp batch: voxels are filtered as they come (one per lane and call), their candidate triangles are
 // appended to the warp's queue, and the queue is evaluated when it is nearly full -- with all 32 lanes busy,
 // whatever the number of candidates per voxel -- before each pending voxel replays its own results.
-constexpr int QCAP_B = 416;                  // queue entries per warp; a call adds at most 7 * 32
-constexpr int PCAP_B = 96;                   // pending voxels per warp; a call adds at most 32
-constexpr int SOLO_CAP = 2048;               // entries of the in-CTA work lists of the tail rounds
+#ifndef SDFB_RELAX_QCAP
+#define SDFB_RELAX_QCAP 416
+#endif
+#ifndef SDFB_RELAX_PCAP
+#define SDFB_RELAX_PCAP 96
+#endif
+#ifndef SDFB_RELAX_SOLOCAP
+#define SDFB_RELAX_SOLOCAP 2048
+#endif
+constexpr int QCAP_B = SDFB_RELAX_QCAP;                  // queue entries per warp; a call adds at most 7 * 32
+constexpr int PCAP_B = SDFB_RELAX_PCAP;                   // pending voxels per warp; a call adds at most 32
+constexpr int SOLO_CAP = SDFB_RELAX_SOLOCAP;               // entries of the in-CTA work lists of the tail rounds
 struct Pending {
     uint32_t c;                              // cell index
     float px, py, pz;                        // world position
