@@ -477,6 +477,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     P.stamp = (uint32_t)(sweep_index + 1);
     P.cells = cells; P.rec = rec; P.changed = changed;
     P.list_cap = sweep_relax_list_cap(g);
+    if (getenv("SDFB_RELAX_LIST_CAP")) P.list_cap = min(P.list_cap, (uint32_t)max(1, atoi(getenv("SDFB_RELAX_LIST_CAP"))));   // tests: force the bitmap fallback
     const size_t ncells = (size_t)g.cell_count(), words = (ncells + 31) / 32 + 1;
     char *s = static_cast<char *>(scratch);
     P.count = reinterpret_cast<unsigned int *>(s); s += 64;

@@ -120,6 +120,19 @@ def test_per_sweep_equality_with_oracle():
         p.close()
 
 
+def test_relaxation_work_list_overflow_falls_back_to_bitmap(monkeypatch):
+    """A work list longer than its capacity is processed from the de-duplication bitmap instead: force that path with a
+    tiny capacity (and relaxation for all 16 sweeps, so that the lists are long) and compare with the live oracle."""
+    monkeypatch.setenv("SDFB_RELAX_LIST_CAP", "700")          # above the 512-entry single-CTA threshold, far below the list lengths
+    for name, n in [("c1_blob_256", 40), ("c2_icosphere_512", 33)]:
+        w = meshes.workload(name, n=n, shuffle=True)
+        r = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+        for flags in (_lib.SWEEP_RELAX, 0):
+            g = _staged_gpu(dict(w, band=1), flags)
+            for f in FIELDS:
+                assert _same(g[f], getattr(r, f)), (name, flags, f)
+
+
 def test_edge_shapes_and_reuse():
     """Plan reuse across meshes/origins, exact_band 0, thin grids; each against the live oracle."""
     v, t = meshes.icosphere(2, 0.3)
