@@ -43,6 +43,7 @@ struct RelaxParams {
     int rk_first, rk_last;                   // relative k range updated by this launch (inclusive)
     uint32_t stamp;                          // sweep_index + 1 (< 31)
     uint32_t list_cap;                       // entries per work list
+    int scan_mode;                           // round 0 = streaming scan kernel + bitmap instead of the dense pass
     uint64_t *cells;
     uint64_t *oldbuf;
     const TriRec *rec;
@@ -244,6 +245,70 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
     nq = 0; np = 0;
 }
 
+// ---- optional kernel 0: streaming scan ------------------------------------------------------------------------
+// For sweeps in which almost no voxel has a candidate, round 0 is split: this lean kernel (30 registers, full
+// occupancy) streams over the cells and only MARKS the voxels that have at least one neighbour triangle to evaluate
+// (bitmap of parity 0); the rounds kernel then starts from that bitmap.  One thread per voxel, lanes along i, 8 rows
+// per CTA so that the rows a CTA shares are served by L1.  Nothing is written to the cells here.
+constexpr int SCAN_ROWS = 8;
+__global__ void __launch_bounds__(SCAN_ROWS * 32) k_relax_scan(RelaxParams P)
+{
+    __shared__ uint32_t thr[8][8];
+    __shared__ uint32_t tmin[8];
+    const Grid &g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) {
+        const uint32_t l = P.last[tid >> 3][tid & 7];
+        thr[tid >> 3][tid & 7] = ((tid & 7) == 7) ? 0xffffffffu : (l ? (l + 1u) << 27 : 0u);
+    }
+    __syncthreads();
+    if (tid < 8) {
+        uint32_t t = 0xffffffffu;
+        for (int m = 0; m < 7; ++m) t = min(t, thr[tid][m]);
+        tmin[tid] = t;
+    }
+    __syncthreads();
+    const int rj = 1 + blockIdx.x * SCAN_ROWS + warp, rk = P.rk_first + blockIdx.y;
+    if (rj > g.nj - 1) return;                                        // warp-uniform
+    const int64_t row = g.cidx(0, P.sd.abs_j(rj, g), P.sd.abs_k(rk, g));
+    const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
+    const int cls_row = (rj == g.nj - 1 ? 2 : 0) | (rk == g.nk - 1 ? 4 : 0);
+    bool any_work = false;
+    // (loading only the four rows' words at ri and taking the ri-1 ones from the lane below by shuffle measured slower)
+    #pragma unroll 4
+    for (int i0 = 0; i0 < g.ni; i0 += 32) {
+        const int i = i0 + lane;
+        const int ri = P.sd.di > 0 ? i : g.ni - 1 - i;
+        bool any_live = false;
+        if (i < g.ni && ri >= 1) {
+            const uint32_t *cp = reinterpret_cast<const uint32_t *>(P.cells + row + i);     // low words: {stamp | tri}
+            uint32_t nb[7];
+            const uint32_t own = __ldg(cp);
+            nb[0] = __ldg(cp + 2 * si); nb[1] = __ldg(cp + 2 * sj); nb[2] = __ldg(cp + 2 * (si + sj)); nb[3] = __ldg(cp + 2 * sk);
+            nb[4] = __ldg(cp + 2 * (si + sk)); nb[5] = __ldg(cp + 2 * (sj + sk)); nb[6] = __ldg(cp + 2 * (si + sj + sk));
+            const int cls = cls_row | (ri == g.ni - 1 ? 1 : 0);
+            const uint32_t mx = max(max(max(nb[0], nb[1]), max(nb[2], nb[3])), max(max(nb[4], nb[5]), nb[6]));
+            if (mx >= tmin[cls]) {
+                // (repeats of an earlier neighbour's triangle are not removed here: marking too much is harmless)
+                #pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    const uint32_t x = nb[m];
+                    any_live = any_live || (((x & TRI_MASK) != TRI_NONE) && (((x ^ own) & TRI_MASK) != 0) && (x >= thr[cls][m]));
+                }
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, any_live);
+        if (bal) {
+            const int64_t c0 = row + i0;
+            const int shf = (int)(c0 & 31);
+            if (lane == 0) atomicOr(&P.bitmap[0][c0 >> 5], bal << shf);
+            if (lane == 1 && shf && (bal >> (32 - shf))) atomicOr(&P.bitmap[0][(c0 >> 5) + 1], bal >> (32 - shf));
+            any_work = true;
+        }
+    }
+    if (any_work && lane == 0) *reinterpret_cast<volatile unsigned int *>(&P.count[0]) = 1u;          // "round 0 has work"
+}
+
 // Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one arrival counter that only grows;
 // `target` is the value it reaches when every CTA has arrived at this barrier.  Several times cheaper than
 // cooperative_groups' grid.sync() here, and the rounds are all latency.
@@ -295,7 +360,8 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
 
     // ---- round 0: every voxel the sweep updates.  CTA = 8 consecutive rows of one plane (warp = row, lanes
     // along the row); the words of the next 32 voxels are loaded while the current ones are filtered. -------
-    {
+    unsigned int bar_target = 0;
+    if (!P.scan_mode) {
         const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
         const int jblocks = (nrows + RX_WARPS - 1) / RX_WARPS;
         const int64_t nitems = (int64_t)jblocks * nplanes;
@@ -348,12 +414,11 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             }
         }
         relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
-    }
-    unsigned int bar_target = 0;
-    grid_barrier(&P.count[4], bar_target);
-    if (P.debug && blockIdx.x == 0 && tid == 0) {
-        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        P.debug[0] = t - t_start; P.debug[2] = P.count[1];
+        grid_barrier(&P.count[4], bar_target);
+        if (P.debug && blockIdx.x == 0 && tid == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            P.debug[0] = t - t_start; P.debug[2] = P.count[1];
+        }
     }
 
     // ---- rounds 1, 2, ...: round r reads the list of parity r&1 (length count[r%3]) and fills the other one
@@ -362,7 +427,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     // that grows again is still handled correctly, just by that CTA. ------------------------------------------
     const uint32_t plane32 = (uint32_t)g.plane();
     const int64_t nwords = (g.cell_count() + 31) >> 5;
-    int r = 1;
+    int r = P.scan_mode ? 0 : 1;             // with the scan kernel, round 0 runs here from the bitmap it filled
     bool solo = false;
     for (;; ++r) {
         const int par = r & 1;
@@ -373,7 +438,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             P.debug[4 + 2 * r] = n; P.debug[5 + 2 * r] = t - t_start;
         }
-        if (!solo && n <= SOLO_MAX) {                                 // uniform over the grid
+        if (!solo && r > 0 && n <= SOLO_MAX) {                        // uniform over the grid
             solo = true;
             if (blockIdx.x != 0) break;
             for (unsigned t = tid; t < n; t += RX_THREADS) sh.slist[par][t] = __ldcg(&P.list[par][t]);     // import the list
@@ -384,7 +449,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         else if (blockIdx.x == 0 && tid == 0) P.count[(r + 2) % 3] = 0;
         unsigned int *const push_count = solo ? &sh.scount[(r + 1) % 3] : &P.count[(r + 1) % 3];
         // the bitmap is the work list when a list overflowed
-        const bool use_bitmap = n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
+        const bool use_bitmap = r == 0 || n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
         const int64_t w = solo ? warp : gwarp, nw = solo ? RX_WARPS : nwarps;
         const int64_t limit = use_bitmap ? nwords : (int64_t)n;
         for (int64_t pos = w * 32; pos < limit; pos += nw * 32) {
@@ -436,6 +501,10 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
         if (solo) __syncthreads();                                    // orders the CTA's writes (global and shared) and reads
         else grid_barrier(&P.count[4], bar_target);
+        if (r == 0 && P.debug && blockIdx.x == 0 && tid == 0) {
+            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            P.debug[0] = t - t_start; P.debug[2] = P.count[1];
+        }
     }
     if (P.debug && blockIdx.x == 0 && tid == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -501,6 +570,15 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         cudaMemsetAsync(dbg, 0, 512 * sizeof(unsigned long long), st);
         P.debug = dbg;
     }
+    // sweeps late in the second pass have almost no candidates: stream over the cells with the lean scan kernel
+    const int scan_from = getenv("SDFB_RELAX_SCAN_FROM") ? atoi(getenv("SDFB_RELAX_SCAN_FROM")) : 13;
+    P.scan_mode = sweep_index >= scan_from ? 1 : 0;
+    int launches = 1;
+    if (P.scan_mode) {
+        const dim3 sgrid((g.nj - 1 + SCAN_ROWS - 1) / SCAN_ROWS, rk_hi - rk_lo + 1);
+        k_relax_scan<<<sgrid, SCAN_ROWS * 32, 0, st>>>(P);
+        ++launches;
+    }
     void *args[] = {&P};
     cudaLaunchCooperativeKernel((const void *)k_relax_rounds, dim3(sms * occ), dim3(RX_THREADS), args, smem, st);
     if (P.debug) {
@@ -515,7 +593,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         fprintf(stderr, "[relax] sweep %2d: round 0 %.3f ms, total %.3f ms, first list %llu, rounds %llu, grid %d x %d\n", sweep_index,
                 h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], sms * occ, RX_THREADS);
     }
-    return 1;
+    return launches;
 }
 
 }  // namespace sdfb
