@@ -56,6 +56,9 @@ constexpr int NCOMPUTE = EJ * EK;            // compute lanes (16 x 16: 8 warps)
 constexpr int NHALO = (EJ + EK + 1 + 31) / 32 * 32;   // halo lanes, whole warps
 constexpr int NSTEPPERS = NCOMPUTE + NHALO;  // lanes that take part in the per-step barrier
 constexpr int NTHREADS = NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
+#ifndef SDFB_SYNC_SLEEP
+#define SDFB_SYNC_SLEEP 150
+#endif
 #ifndef SDFB_PUBLISH
 #define SDFB_PUBLISH 2
 #endif
@@ -202,7 +205,7 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
             }
             published = d;
         } else {
-            __nanosleep(20);
+            __nanosleep(SDFB_SYNC_SLEEP);
         }
     }
 }
@@ -552,11 +555,11 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     my_changed += st.changed; my_evals += st.evals;
 }
 
-#ifndef SDFB_MINB
-#define SDFB_MINB 3
-#endif
-template <bool CTA_QUEUE>
-__global__ void __launch_bounds__(NTHREADS, SDFB_MINB)
+// MINB = CTAs per SM the register allocation is bounded for.  3 (93 registers, no spills) is slightly faster where the
+// wavefront is narrow and the kernel latency-bound (512^3: 60.5 vs 61.4 ms for the first pass); 4 (80 registers, a few
+// spills) wins where there is enough work to be throughput-bound (1024^3: 240 vs 263 ms).
+template <bool CTA_QUEUE, int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
                 unsigned long long *__restrict__ changed)
@@ -650,14 +653,19 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     // evaluation-heavy sweeps (the first pass) balance the distance evaluations over the whole column
     const bool cta_queue = getenv("SDFB_CTA_QUEUE") ? atoi(getenv("SDFB_CTA_QUEUE")) != 0 : (sweep_index < 8);
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cta_queue ? k_sweep_columns<true> : k_sweep_columns<false>, NTHREADS, 0);
+    // register bound by the amount of work per launch (see k_sweep_columns)
+    int minb = ((int64_t)g.ni * (g.nj - 1) * (rk_hi - rk_lo + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
+    if (getenv("SDFB_MINB")) minb = atoi(getenv("SDFB_MINB")) >= 4 ? 4 : 3;
+    using kern_t = void (*)(uint64_t *, const TriRec *, ColParams, uint32_t *, uint32_t *, unsigned long long *);
+    const kern_t kern = cta_queue ? (minb == 4 ? k_sweep_columns<true, 4> : k_sweep_columns<true, 3>)
+                                  : (minb == 4 ? k_sweep_columns<false, 4> : k_sweep_columns<false, 3>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, 0);
     if (occ < 1) occ = 1;
     if (getenv("SDFB_MAX_OCC")) occ = min(occ, atoi(getenv("SDFB_MAX_OCC")));   // experiment knob
     int grid = sms * occ;
     int ncols = P.NJ * P.NK;
     if (grid > ncols) grid = ncols;
-    if (cta_queue) k_sweep_columns<true><<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
-    else k_sweep_columns<false><<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
+    kern<<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);
 #ifdef SDFB_TRACE
     if (P.trace) {
         cudaStreamSynchronize(st);
