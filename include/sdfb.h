@@ -131,6 +131,13 @@ int sdfb_plan_counters(sdfb_plan *plan, void *stream, uint64_t out[2]);
 int sdfb_plan_download(sdfb_plan *plan, float *phi_out, int32_t *closest_tri_out,
                        int32_t *intersection_count_out, void *stream);
 
+/* Asynchronous copy of the signed phi of the last sdfb_plan_sign to (pinned) host memory on `copy_stream`, a stream
+ * other than the one the phases run on: the copy starts when that sign pass has finished and overlaps whatever is
+ * enqueued on the compute stream afterwards (the next mesh upload, band and sweeps); the next sdfb_plan_sign waits for
+ * it before it overwrites phi.  The caller synchronises copy_stream (or the device) before reading phi_out.  This is
+ * the streaming form of the D2H copy sdfgen::gpu::make_level_set3 does at gpu_lib/makelevelset3_gpu.cu:747-749. */
+int sdfb_plan_download_phi_async(sdfb_plan *plan, float *phi_out, void *copy_stream);
+
 /* Device time of the phases of the last completed run, in ms: out[0]=band (init+records+band+counts),
  * out[1]=sweeps, out[2]=sign/unpack, out[3]=total.  Blocks until the work has finished. */
 int sdfb_plan_phase_ms(sdfb_plan *plan, float out[4]);

@@ -65,6 +65,8 @@ def lib():
     L.sdfb_plan_counters.argtypes = [vp, vp, C.POINTER(u64 * 2)]
     L.sdfb_plan_download.restype = C.c_int
     L.sdfb_plan_download.argtypes = [vp, vp, vp, vp, vp]
+    L.sdfb_plan_download_phi_async.restype = C.c_int
+    L.sdfb_plan_download_phi_async.argtypes = [vp, vp, vp]
     L.sdfb_plan_phase_ms.restype = C.c_int
     L.sdfb_plan_phase_ms.argtypes = [vp, C.POINTER(f32 * 4)]
     _lib = L
@@ -174,6 +176,11 @@ class Plan:
         c = np.empty(V, np.int32) if counts else None
         check(lib().sdfb_plan_download(self._h, _addr(p), _addr(t), _addr(c), stream or None))
         return p, t, c
+
+    def download_phi_async(self, phi_out, copy_stream):
+        """Enqueue the D2H copy of the last sign pass's phi on `copy_stream` (raw cudaStream_t, not the compute
+        stream); phi_out is a pinned host address or array.  Synchronise that stream before reading."""
+        check(lib().sdfb_plan_download_phi_async(self._h, _addr(phi_out), copy_stream or None))
 
     def phase_ms(self):
         out = (C.c_float * 4)()

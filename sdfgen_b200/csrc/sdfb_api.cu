@@ -88,6 +88,10 @@ struct sdfb_plan {
     uint64_t rec_cap = 0;
     bool have_mesh = false, have_band = false, have_sign = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after band, after sweeps, after sign
+    cudaEvent_t ev_copy = nullptr;   // end of the last asynchronous phi download
+    bool copy_pending = false;
+    void *l2_ptr = nullptr, *l2_stream = nullptr;   // L2 persistence window currently set for the triangle records
+    size_t l2_bytes = 0;
     bool timed = false;
 };
 
@@ -131,7 +135,10 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
         size_t bytes = (size_t)ntri * sizeof(TriRec);
-        if (max_persist > 0 && max_window > 0 && bytes > 0 && !getenv("SDFB_NO_L2_PERSIST")) {
+        // only when the window changes: cudaDeviceSetLimit synchronises the device, which would serialise a stream of
+        // requests (the asynchronous phi download of the previous request is still in flight)
+        if (max_persist > 0 && max_window > 0 && bytes > 0 && !getenv("SDFB_NO_L2_PERSIST") &&
+            (p->l2_ptr != (void *)p->rec || p->l2_bytes != bytes || p->l2_stream != (void *)st)) {
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
             cudaStreamAttrValue attr{};
             attr.accessPolicyWindow.base_ptr = p->rec;
@@ -141,6 +148,7 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
             cudaGetLastError();
+            p->l2_ptr = p->rec; p->l2_bytes = bytes; p->l2_stream = (void *)st;
         }
     }
     p->ntri = ntri; p->nvert = nvert; p->have_mesh = true; p->have_band = false; p->have_sign = false;
@@ -205,6 +213,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     for (auto &ev : p->ev) {
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { sdfb_plan_destroy(p); return fail(SDFB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
     }
+    if ((e = cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming)) != cudaSuccess) { sdfb_plan_destroy(p); return fail(SDFB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
     cudaMemset(p->changed, 0, 2 * sizeof(unsigned long long));
     *out = p;
     return SDFB_OK;
@@ -219,6 +228,7 @@ int sdfb_plan_destroy(sdfb_plan *p)
     cudaFree(p->cells); cudaFree(p->counts); cudaFree(p->phi); cudaFree(p->phi_k); cudaFree(p->scratch);
     cudaFree(p->changed); cudaFree(p->progress); cudaFree(p->relax);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
+    if (p->ev_copy) cudaEventDestroy(p->ev_copy);
     delete p;
     cudaGetLastError();
     return SDFB_OK;
@@ -322,6 +332,7 @@ int sdfb_plan_sign(sdfb_plan *p, void *stream)
     if (!p->have_band) return fail(SDFB_ERR_STATE, "sdfb_plan_sign called before sdfb_plan_band");
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->copy_pending) { CU(cudaStreamWaitEvent(st, p->ev_copy, 0)); p->copy_pending = false; }   // phi is still being read
     g_launches += launch_sign(p->cells, p->counts, p->g, !(p->flags & SDFB_NO_SIGN), false, p->phi, st);
     if (p->flags & SDFB_OUT_KFASTEST)
         g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
@@ -390,6 +401,7 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
     const bool kf = (p->flags & SDFB_OUT_KFASTEST) != 0;
     if (phi_out) {
         if (!p->have_sign) {   // unsigned phi straight from the cells
+            if (p->copy_pending) { CU(cudaStreamWaitEvent(st, p->ev_copy, 0)); p->copy_pending = false; }
             g_launches += launch_sign(p->cells, p->counts, p->g, false, false, p->phi, st);
             if (kf) g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
         }
@@ -413,6 +425,20 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));
+    return SDFB_OK;
+}
+
+int sdfb_plan_download_phi_async(sdfb_plan *p, float *phi_out, void *copy_stream)
+{
+    if (!p || !phi_out) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->have_sign) return fail(SDFB_ERR_STATE, "sdfb_plan_download_phi_async needs a completed sdfb_plan_sign");
+    DeviceGuard dg(p->device);
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    const size_t V = (size_t)p->g.slab_voxels();
+    CU(cudaStreamWaitEvent(cs, p->ev[3], 0));                     // the sign pass that produced phi
+    CU(cudaMemcpyAsync(phi_out, (p->flags & SDFB_OUT_KFASTEST) ? p->phi_k : p->phi, V * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(p->ev_copy, cs));
+    p->copy_pending = true;
     return SDFB_OK;
 }
 

@@ -561,9 +561,13 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = sizeof(RelaxShared);
-    cudaFuncSetAttribute(k_relax_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax_rounds, RX_THREADS, smem);
-    if (occ < 1) occ = 1;
+    static int occ_cached[64] = {0};          // per device: the attribute and the occupancy query are per-launch overhead
+    if (dev < 0 || dev >= 64 || !occ_cached[dev]) {
+        cudaFuncSetAttribute(k_relax_rounds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_relax_rounds, RX_THREADS, smem);
+        if (occ < 1) occ = 1;
+        if (dev >= 0 && dev < 64) occ_cached[dev] = occ;
+    } else occ = occ_cached[dev];
     static unsigned long long *dbg = nullptr;
     if (getenv("SDFB_RELAX_DEBUG")) {
         if (!dbg) cudaMalloc(&dbg, 512 * sizeof(unsigned long long));

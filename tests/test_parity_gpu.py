@@ -133,6 +133,33 @@ def test_relaxation_work_list_overflow_falls_back_to_bitmap(monkeypatch):
                 assert _same(g[f], getattr(r, f)), (name, flags, f)
 
 
+def test_async_phi_download_overlaps_next_run():
+    """sdfb_plan_download_phi_async: the copy of run i overlaps run i+1 on the same plan and still delivers run i's
+    field (the next sign pass waits for the copy before it overwrites phi)."""
+    import torch
+    w1 = meshes.workload("c1_blob_256", n=64, shuffle=True)
+    v2, t2 = meshes.icosphere(3, 0.3)
+    p = _lib.Plan(64, 64, 64)
+    cs = torch.cuda.Stream()
+    outs = [torch.empty(64 ** 3, dtype=torch.float32).pin_memory() for _ in range(2)]
+    ref = []
+    for v, t in ((w1["vertices"], w1["triangles"]), (v2, t2)):
+        q = _lib.Plan(64, 64, 64)
+        q.set_mesh_host(v, t)
+        q.run(w1["origin"], w1["dx"], 1)
+        ref.append(q.download(phi=True)[0].copy())
+        q.close()
+    assert not _same(ref[0], ref[1])
+    for rep in range(3):
+        for idx, (v, t) in enumerate(((w1["vertices"], w1["triangles"]), (v2, t2))):
+            p.set_mesh_host(v, t)
+            p.run(w1["origin"], w1["dx"], 1)
+            p.download_phi_async(outs[idx].data_ptr(), cs.cuda_stream)
+    torch.cuda.synchronize()
+    assert _same(outs[0].numpy(), ref[0]) and _same(outs[1].numpy(), ref[1])
+    p.close()
+
+
 def test_edge_shapes_and_reuse():
     """Plan reuse across meshes/origins, exact_band 0, thin grids; each against the live oracle."""
     v, t = meshes.icosphere(2, 0.3)
