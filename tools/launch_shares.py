@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel for the LAST bench step.
-usage: launch_shares.py launches.csv launches_per_step"""
+usage: launch_shares.py launches.csv"""
 import csv, re, sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5 and r[0].isdigit()]
-per_step = int(sys.argv[2])
-rows = rows[-per_step:]
+# one step = from a k_init_cells launch (first kernel of the band phase) to the launch before the next mesh upload /
+# band phase; the LAST step of the run is taken (the e2e legs of bench.py run the same kernels as the device leg)
+starts = [i for i, r in enumerate(rows) if "k_init_cells" in r[4]]
+rows = rows[starts[-1]:]
+per_step = len(rows)
 agg, order = {}, []
 for r in rows:
     name = re.sub(r"^.*::", "", r[4].split("(")[0]).replace("unnamed>", "").strip()
@@ -17,6 +20,6 @@ print("# gpu__time_duration.sum per launch, --clock-control none; times are seri
 for n in sorted(order, key=lambda k: -agg[k][1]):
     print(f"{n:24s} launches {agg[n][0]:3d}  total {agg[n][1]:9.3f} ms  share {100*agg[n][1]/tot:5.1f}%")
 print(f"{'step total':24s} launches {per_step:3d}  total {tot:9.3f} ms\n")
-for kern in ("k_sweep_columns", "k_relax_rounds"):
+for kern in ("k_sweep_columns", "k_relax_rounds", "k_relax_scan"):
     ts = [float(r[-1]) / 1e6 for r in rows if kern in r[4]]
     if ts: print(f"per {kern} launch (ms): " + " ".join(f"{t:.2f}" for t in ts))
