@@ -160,6 +160,48 @@ def test_async_phi_download_overlaps_next_run():
     p.close()
 
 
+def test_two_slabs_on_one_gpu_match_the_oracle_slab_engine():
+    """k-slab plans with halo planes, on ONE device: two CudaSlabEngines driven through the same pass loop as
+    sdfgen_b200.dist.run_sharded (halo exchange, halo_refresh, 8 sweeps, changed count; 3 passes, so the column AND the
+    relaxation schedule both run on slabs) must equal, bit for bit, two oracle-backed slab engines driven the same way."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_engine import OracleSlabEngine
+    from sdfgen_b200 import dist as sdist
+    w = meshes.stacked_workload(2, n=44, level=4)
+    ni, nj, nk = w["ni"], w["nj"], w["nk"]
+    bounds = [sdist.slab_bounds(nk, 2, r) for r in range(2)]
+
+    def drive(engs):
+        for e in engs:
+            e.band(w["origin"], w["dx"], 1)
+        changed = []
+        for ps in range(3):
+            sends = [e.boundary_planes() for e in engs]
+            recvs = [e.halo_planes() for e in engs]
+            recvs[1][0].copy_(sends[0][1])          # slab 0's last plane  -> slab 1's lower halo
+            recvs[0][1].copy_(sends[1][0])          # slab 1's first plane -> slab 0's upper halo
+            for e in engs:
+                e.halo_refresh()
+                e.sweep(8 * ps, 8)
+            changed.append([e.changed() for e in engs])
+        for e in engs:
+            e.sign()
+        return changed
+
+    gpu = [sdist.CudaSlabEngine(ni, nj, nk, lo, hi, 0) for lo, hi in bounds]
+    for e in gpu:
+        e.set_mesh(w["vertices"], w["triangles"])
+    cpu = [OracleSlabEngine(w["vertices"], w["triangles"], ni, nj, nk, lo, hi) for lo, hi in bounds]
+    ch_gpu, ch_cpu = drive(gpu), drive(cpu)
+    assert ch_gpu == ch_cpu, (ch_gpu, ch_cpu)
+    assert ch_cpu[2][0] + ch_cpu[2][1] > 0 or ch_cpu[1][0] + ch_cpu[1][1] > 0      # the later passes did something
+    for g, c in zip(gpu, cpu):
+        phi, tri, cnt = g.plan.download(phi=True, tri=True, counts=True)
+        assert _same(phi, c.phi) and _same(tri, c.tri()) and _same(cnt, c.counts)
+        g.close()
+
+
 def test_edge_shapes_and_reuse():
     """Plan reuse across meshes/origins, exact_band 0, thin grids; each against the live oracle."""
     v, t = meshes.icosphere(2, 0.3)
