@@ -90,8 +90,6 @@ struct sdfb_plan {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after band, after sweeps, after sign
     cudaEvent_t ev_copy = nullptr;   // end of the last asynchronous phi download
     bool copy_pending = false;
-    void *l2_ptr = nullptr, *l2_stream = nullptr;   // L2 persistence window currently set for the triangle records
-    size_t l2_bytes = 0;
     bool timed = false;
 };
 
@@ -128,29 +126,8 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
     if (rc) return rc;
     g_launches += launch_tri_prep(d_tri, d_xyz, ntri, p->rec, st);
     CU(cudaGetLastError());
-    // Keep the triangle records resident in L2 while the grid streams through it: the sweeps gather them at
-    // random (48 B per evaluation).  Best effort: ignored where persisting L2 is unavailable.
-    {
-        int dev = p->device, max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        size_t bytes = (size_t)ntri * sizeof(TriRec);
-        // only when the window changes: cudaDeviceSetLimit synchronises the device, which would serialise a stream of
-        // requests (the asynchronous phi download of the previous request is still in flight)
-        if (max_persist > 0 && max_window > 0 && bytes > 0 && !getenv("SDFB_NO_L2_PERSIST") &&
-            (p->l2_ptr != (void *)p->rec || p->l2_bytes != bytes || p->l2_stream != (void *)st)) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-            cudaStreamAttrValue attr{};
-            attr.accessPolicyWindow.base_ptr = p->rec;
-            attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-            attr.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-            cudaGetLastError();
-            p->l2_ptr = p->rec; p->l2_bytes = bytes; p->l2_stream = (void *)st;
-        }
-    }
+    // (An L2 persistence window over the records was measured: no effect at C2, and cudaDeviceSetLimit is a
+    // device-wide, synchronising setting a library should not touch -- removed.)
     p->ntri = ntri; p->nvert = nvert; p->have_mesh = true; p->have_band = false; p->have_sign = false;
     return SDFB_OK;
 }
