@@ -88,10 +88,12 @@ constexpr int RSTRIDE = (EK + 1) * (EJ + 1);
 __device__ __forceinline__ int ring_idx(int a, int b) { return (b + 1) * (EJ + 1) + (a + 1); }
 
 // named barriers: 0 = __syncthreads (column hand-over, all 352 threads), 1 = per-step (compute + halo lanes)
-__device__ __forceinline__ void bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NSTEPPERS) : "memory"); }
+// The named barriers are warp-aligned and the compiler does not know that the inline asm is a convergent operation:
+// the __syncwarp() guarantees that the warp is converged when it executes one, whatever divergent code came before.
+__device__ __forceinline__ void bar_step() { __syncwarp(); asm volatile("bar.sync 1, %0;" ::"n"(NSTEPPERS) : "memory"); }
 // 2 = evaluation barrier of the column-wide queue: compute AND halo lanes (the halo warps are nearly idle, so
 // they take a share of the distance evaluations)
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 2, %0;" ::"n"(NSTEPPERS) : "memory"); }
+__device__ __forceinline__ void bar_compute() { __syncwarp(); asm volatile("bar.sync 2, %0;" ::"n"(NSTEPPERS) : "memory"); }
 
 #ifdef SDFB_TRACE
 #define TRACE(P, warp, s, slot) do { if ((P).trace && (threadIdx.x & 31) == 0 && sh.col == (P).trace_col) (P).trace[((size_t)(warp) * 8192 + (s)) * 8 + (slot)] = clock64(); } while (0)
@@ -166,8 +168,8 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
 // column has completed s1-1+EJ+3 steps (EK for the column below; the diagonal column is covered transitively,
 // because the left column itself waited for it).  Chunks are cleared a little ahead of need through sh.go;
 // finished chunks (sh.done, set after the chunk's last step barrier) are fenced and published at once.
-__device__ __forceinline__ void bar_go_arrive(int chunk) { asm volatile("bar.arrive %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
-__device__ __forceinline__ void bar_go_wait(int chunk) { asm volatile("bar.sync %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
+__device__ __forceinline__ void bar_go_arrive(int chunk) { __syncwarp(); asm volatile("bar.arrive %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
+__device__ __forceinline__ void bar_go_wait(int chunk) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(4 + (chunk & 3)), "n"(NHALO + 32) : "memory"); }
 
 // Runs on the whole sync warp (lane 0 reads and writes; the named barriers need the full warp).  "Chunk c may
 // run" is signalled to the halo warps with bar.arrive on barrier 4 + (c & 3): they block in hardware instead
