@@ -10,6 +10,9 @@
 #include <cstdarg>
 #include <atomic>
 #include <new>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/sdfb.h"
 #include "sdfb_kernels.cuh"
@@ -43,6 +46,74 @@ bool device_is_sm100(int dev)
     int major = 0;
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
     return major == 10;    // the only code in libsdfb.so is sm_100a SASS
+}
+
+// ---- host-side helpers for large PAGEABLE outputs (the drop-in call hands us plain malloc'ed memory) ------------
+// cudaMemcpy into untouched pageable memory runs at 4-5 GB/s (first-touch page faults + a single-threaded bounce
+// copy): 110-130 ms for the 537 MB phi of a 512^3 grid, more than the kernels.  So (1) the destination pages are
+// touched by a few threads while the GPU is still computing, and (2) the copy is staged through a pinned ring and
+// spread over the same threads.
+int host_threads()
+{
+    unsigned n = std::thread::hardware_concurrency();
+    return (int)(n == 0 ? 4 : (n > 8 ? 8 : n));
+}
+
+void parallel_for_bytes(char *dst, size_t bytes, void (*fn)(char *, size_t, const char *), const char *src)
+{
+    const int nt = host_threads();
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = (size_t)t * per;
+        if (lo >= bytes) break;
+        const size_t n = bytes - lo < per ? bytes - lo : per;
+        th.emplace_back(fn, dst + lo, n, src ? src + lo : nullptr);
+    }
+    for (auto &x : th) x.join();
+}
+
+void touch_pages(char *dst, size_t n, const char *) { for (size_t o = 0; o < n; o += 4096) reinterpret_cast<volatile char *>(dst)[o] = 0; }
+void copy_bytes(char *dst, size_t n, const char *src) { memcpy(dst, src, n); }
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Device -> pageable host through two pinned staging buffers: the D2H copy of chunk i+1 overlaps the threaded
+// memcpy of chunk i into the destination.  Returns a CUDA error code.
+cudaError_t staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    const size_t CH = (size_t)32 << 20;
+    // the staging ring is allocated once per process (pinning 64 MB costs several ms) and shared under a lock
+    static std::mutex mtx;
+    static char *ring[2] = {nullptr, nullptr};
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::lock_guard<std::mutex> lock(mtx);
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        if (!ring[b]) e = cudaHostAlloc(reinterpret_cast<void **>(&ring[b]), CH, cudaHostAllocPortable);
+        if (e == cudaSuccess && !ev[b]) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    }
+    const size_t nch = (bytes + CH - 1) / CH;
+    auto chunk = [&](size_t i) { return bytes - i * CH < CH ? bytes - i * CH : CH; };
+    if (e == cudaSuccess && nch) {
+        e = cudaMemcpyAsync(ring[0], static_cast<const char *>(src), chunk(0), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[0], st);
+    }
+    for (size_t i = 0; i < nch && e == cudaSuccess; ++i) {
+        if (i + 1 < nch) {                                  // ring[(i+1)&1] was drained in iteration i-1
+            e = cudaMemcpyAsync(ring[(i + 1) & 1], static_cast<const char *>(src) + (i + 1) * CH, chunk(i + 1), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[(i + 1) & 1], st);
+        }
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
+        if (e == cudaSuccess) parallel_for_bytes(static_cast<char *>(dst) + i * CH, chunk(i), copy_bytes, ring[i & 1]);
+    }
+    if (e != cudaSuccess) cudaStreamSynchronize(st);        // nothing may still be writing into the ring when the lock goes
+    return e;
 }
 
 struct DeviceGuard {
@@ -382,7 +453,9 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
             g_launches += launch_sign(p->cells, p->counts, p->g, false, false, p->phi, st);
             if (kf) g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
         }
-        CU(cudaMemcpyAsync(phi_out, kf ? p->phi_k : p->phi, V * sizeof(float), cudaMemcpyDeviceToHost, st));
+        const float *src = kf ? p->phi_k : p->phi;
+        if (V * sizeof(float) >= ((size_t)64 << 20) && is_pageable(phi_out)) CU(staged_d2h(phi_out, src, V * sizeof(float), st));
+        else CU(cudaMemcpyAsync(phi_out, src, V * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (tri_out || (count_out && kf)) {
         if (!p->scratch) CU(cudaMalloc(&p->scratch, V * sizeof(int32_t) * (kf ? 2 : 1)));
@@ -445,6 +518,9 @@ int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, u
     if (rc) return rc;
     rc = sdfb_plan_set_mesh_host(p, tri, ntri, xyz, nvert, nullptr);
     if (!rc) rc = sdfb_plan_run(p, origin, dx, exact_band, nullptr);
+    // everything above is asynchronous: touch the (usually fresh, pageable) output pages while the GPU computes
+    const size_t out_bytes = (size_t)ni * nj * nk * sizeof(float);
+    if (!rc && out_bytes >= ((size_t)64 << 20) && is_pageable(phi_out)) parallel_for_bytes(reinterpret_cast<char *>(phi_out), out_bytes, touch_pages, nullptr);
     if (!rc) rc = sdfb_plan_download(p, phi_out, closest_tri_out, intersection_count_out, nullptr);
     sdfb_plan_destroy(p);
     return rc;
