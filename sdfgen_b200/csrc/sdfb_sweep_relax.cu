@@ -16,7 +16,11 @@
 // pay the full dependency depth ni+nj+nk for them).  Round 0 is then a streaming pass over the cells plus the
 // distance evaluations the stamp memo could not exclude, all at full occupancy; the later rounds touch a few
 // thousand voxels.  One cooperative launch per sweep: round 0 (dense), then rounds over a work list with a
-// grid-wide barrier in between, until a round changes nothing.
+// grid-wide barrier in between, until a round changes nothing; once a list is short, one CTA finishes alone with
+// the lists in shared memory.  For the last sweeps of the pass, which have almost no candidates, a lean scan
+// kernel marks the voxels that have one and round 0 starts from that bitmap instead of the dense pass.
+// Evaluations are batched per warp (filter as the voxels come, evaluate a full queue with all lanes, replay).
+// oracle/relax_emu.c runs the same rules on the CPU in random order against the serial oracle.
 //
 // Bookkeeping: `oldbuf` (8 B per cell, touched only where a cell changes) keeps old[v] for voxels already
 // changed in this sweep -- recognised by their stamp, which is this sweep's; work lists are de-duplicated
@@ -24,11 +28,8 @@
 // pruning rules (own / duplicate triangle, stamp memo) are those of sdfb_sweep_columns.cu.
 #include <cstdio>
 #include <cstdlib>
-#include <cooperative_groups.h>
 #include "sdfb_kernels.cuh"
 #include "sdfb_sweep_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace sdfb {
 
