@@ -356,6 +356,14 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                 CU(cudaMemsetAsync(p->relax, 0, bytes, st));
             }
             g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st);
+            // a sweep that turns out to change a large part of the grid is handed back (cells restored, flag set):
+            // this launch then runs it with the column schedule, and exits at once otherwise
+            if (p->epoch >= 65000u) {
+                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
+                p->epoch = 0;
+            }
+            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st,
+                                               sweep_relax_fallback_flag(p->relax));
         } else {
             if (p->epoch >= 65000u) {   // progress words are epoch<<16 | steps: start over before it wraps
                 CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));

@@ -38,7 +38,8 @@ int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units
 int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                         unsigned long long *changed, cudaStream_t st);
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                         unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st);
+                         unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
+                         const unsigned int *run_if = nullptr);
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st);
 int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st);
@@ -50,6 +51,7 @@ int launch_sweep_strips(uint64_t *cells, const TriRec *rec, const Grid &g, int s
 
 bool sweep_relax_supported(const Grid &g);
 size_t sweep_relax_scratch_bytes(const Grid &g);
+const unsigned int *sweep_relax_fallback_flag(const void *scratch);
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                        unsigned long long *changed, void *scratch, cudaStream_t st);
 

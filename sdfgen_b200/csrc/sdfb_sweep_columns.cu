@@ -75,6 +75,8 @@ struct ColParams {
     uint32_t stamp;                          // sweep_index + 1
     uint32_t epoch;                          // progress values are epoch<<16 | steps_done
     int trace_col;                           // ticket of the column to trace
+    const unsigned int *run_if;              // if set: the launch does nothing unless this word is non-zero (the
+                                             // relaxation schedule's fallback, see sdfb_sweep_relax.cu)
     unsigned long long *trace;               // debug builds (-DSDFB_TRACE) only: per-warp step timestamps
     // last[c][m]: stamp (sweep index + 1) of the latest earlier sweep in which a voxel of class c examined
     // neighbour offset m, 0 if none.  Class bits: 1 = last voxel of its row (ri = ni-1), 2 = last row
@@ -570,6 +572,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
     const int tid = threadIdx.x, lane = tid & 31;
     const int ncols = P.NJ * P.NK;
     unsigned my_changed = 0, my_evals = 0;
+    if (P.run_if && __ldcg(P.run_if) == 0u) return;                   // uniform over the grid; the ticket is untouched
 
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
@@ -623,10 +626,12 @@ size_t sweep_columns_progress_words(const Grid &g)
 }
 
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                         unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st)
+                         unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
+                         const unsigned int *run_if)
 {
     ColParams P{};
     P.g = g;
+    P.run_if = run_if;
     P.sd = SweepDir::of(sweep_index);
     int rk_lo, rk_hi;
     if (!P.sd.owned_rk_range(g, rk_lo, rk_hi)) return 0;

@@ -51,6 +51,7 @@ struct RelaxParams {
     uint32_t *list[2];                       // cell indices to re-evaluate, by round parity
     uint32_t *bitmap[2];                     // one bit per cell: "is in the list of that parity"
     unsigned int *count;                     // [0..2] list lengths, rotating by round % 3; [4] grid barrier arrivals
+    uint32_t heavy_limit;                    // more work-list entries than this in all: give the sweep back to the column schedule
     unsigned long long *debug;               // SDFB_RELAX_DEBUG: {ns round 0, ns total, round-1 list length, rounds}
     unsigned long long *changed;             // [0] cells whose triangle changed (net), [1] distance evaluations
     uint8_t last[8][8];
@@ -327,6 +328,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &ta
 }
 
 // ---- the kernel: round 0 over all voxels, then the rounds ---------------------------------------------------------------------------------------
+constexpr int MAX_GRID_ROUNDS = 256;         // more grid-wide rounds than this cost as much as a column sweep
 constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by one CTA (a CTA barrier per round
                                              // instead of a grid barrier)
 
@@ -382,6 +384,9 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         prefetch_row(blockIdx.x);
         for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
             prefetch_row(it + gridDim.x);
+            // a sweep that changes a large part of the grid is the column schedule's (see the fallback below):
+            // the counter only grows, so every CTA agrees after the barrier whoever notices first
+            if (*reinterpret_cast<volatile unsigned int *>(&P.count[1]) > P.heavy_limit) { nq = np = 0; break; }
             const int rk = P.rk_first + (int)(it / jblocks);
             const int rj = 1 + (int)(it % jblocks) * RX_WARPS + warp;
             if (rj > g.nj - 1) continue;                              // warp-uniform
@@ -430,11 +435,29 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     const int64_t nwords = (g.cell_count() + 31) >> 5;
     int r = P.scan_mode ? 0 : 1;             // with the scan kernel, round 0 runs here from the bitmap it filled
     bool solo = false;
+    unsigned long long work = 0;             // list entries so far (the same number in every CTA)
     for (;; ++r) {
         const int par = r & 1;
         unsigned n = solo ? *reinterpret_cast<volatile unsigned int *>(&sh.scount[r % 3])
                           : *reinterpret_cast<volatile unsigned int *>(&P.count[r % 3]);
         if (n == 0) break;
+        work += n;
+        if (!solo && r >= 1 && (work > P.heavy_limit || r > MAX_GRID_ROUNDS)) {                         // uniform over the grid
+            // ---- fallback: this sweep changes too much for relaxation to pay (every changed voxel re-opens its
+            // downstream neighbours, and a front that crosses an empty region is re-evaluated again and again:
+            // such sweeps take seconds).  Put the cells back as they were before
+            // the sweep (changed cells carry this sweep's stamp and their old value is in oldbuf), empty both
+            // bitmaps and raise the flag that lets the conditional column launch queued behind this one run. -----
+            const int64_t ncell = g.cell_count(), gt = (int64_t)blockIdx.x * RX_THREADS + tid, nt = (int64_t)gridDim.x * RX_THREADS;
+            for (int64_t c = gt; c < ncell; c += nt) {
+                const uint64_t x = ld_cg64(P.cells + c);
+                if (lo_stamp(cell_lo(x)) == P.stamp) P.cells[c] = ld_cg64(P.oldbuf + c);
+            }
+            for (int64_t wi = gt; wi < nwords; wi += nt) { P.bitmap[0][wi] = 0; P.bitmap[1][wi] = 0; }
+            if (blockIdx.x == 0 && tid == 0) P.count[5] = 1u;
+            net_changed = 0;
+            break;
+        }
         if (P.debug && blockIdx.x == 0 && tid == 0 && r < 250) {
             unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             P.debug[4 + 2 * r] = n; P.debug[5 + 2 * r] = t - t_start;
@@ -533,6 +556,9 @@ size_t sweep_relax_scratch_bytes(const Grid &g)
     return cells * 8 + 2 * (size_t)sweep_relax_list_cap(g) * 4 + 2 * words * 4 + 64;
 }
 
+// word that is non-zero after a launch that gave its sweep back (launch_sweep_columns' run_if)
+const unsigned int *sweep_relax_fallback_flag(const void *scratch) { return static_cast<const unsigned int *>(scratch) + 5; }
+
 // `scratch` must be zero-initialised once after allocation (bitmaps and counters return to zero after every sweep).
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                        unsigned long long *changed, void *scratch, cudaStream_t st)
@@ -556,6 +582,10 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     P.list[1] = reinterpret_cast<uint32_t *>(s); s += (size_t)P.list_cap * 4;
     P.bitmap[0] = reinterpret_cast<uint32_t *>(s); s += words * 4;
     P.bitmap[1] = reinterpret_cast<uint32_t *>(s);
+    // light sweeps put well under 1 % of the cells on their work lists (C2: 0.004-0.1 % on the first, less after),
+    // heavy ones most of them, round after round
+    P.heavy_limit = (uint32_t)(ncells / 64);
+    if (getenv("SDFB_RELAX_HEAVY_LIMIT")) P.heavy_limit = (uint32_t)strtoul(getenv("SDFB_RELAX_HEAVY_LIMIT"), nullptr, 10);   // tests: force the fallback
     memo_last_table(sweep_index, P.sd, P.last);
     cudaMemsetAsync(P.count, 0, 64, st);
     int dev = 0, sms = 148, occ = 1;

@@ -133,6 +133,36 @@ def test_relaxation_work_list_overflow_falls_back_to_bitmap(monkeypatch):
                 assert _same(g[f], getattr(r, f)), (name, flags, f)
 
 
+def test_relaxation_hands_heavy_sweeps_back_to_columns(monkeypatch):
+    """A relaxation sweep that meets more work than its limit restores the cells and lets the conditional column launch
+    behind it do the sweep.  Limits 0 (every sweep falls back at once), 300 and 5000 entries (fall back in round 0 or after
+    a few rounds, depending on the sweep) with relaxation asked for all 16 sweeps; fields and change counts must match."""
+    for name, n in [("c1_blob_256", 40), ("c2_icosphere_512", 33)]:
+        w = meshes.workload(name, n=n, shuffle=True)
+        r = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+        ref_changed = None
+        for limit in (None, "0", "300", "5000"):
+            if limit is None:
+                monkeypatch.delenv("SDFB_RELAX_HEAVY_LIMIT", raising=False)
+            else:
+                monkeypatch.setenv("SDFB_RELAX_HEAVY_LIMIT", limit)
+            for flags in (_lib.SWEEP_RELAX, 0):
+                g = _staged_gpu(dict(w, band=1), flags)
+                for f in FIELDS:
+                    assert _same(g[f], getattr(r, f)), (name, limit, flags, f)
+            p = _lib.Plan(n, n, n, flags=_lib.SWEEP_RELAX)
+            p.set_mesh_host(w["vertices"], w["triangles"])
+            p.band(w["origin"], w["dx"], 1)
+            counts = []
+            for s in range(16):
+                p.sweep(s, 1)
+                counts.append(p.changed())
+            p.close()
+            if ref_changed is None:
+                ref_changed = counts
+            assert counts == ref_changed, (name, limit, counts, ref_changed)
+
+
 def test_async_phi_download_overlaps_next_run():
     """sdfb_plan_download_phi_async: the copy of run i overlaps run i+1 on the same plan and still delivers run i's
     field (the next sign pass waits for the copy before it overwrites phi)."""
