@@ -39,6 +39,7 @@ extern "C" {
 #define SDFB_ERR_OOM           -4   /* device or host allocation failed                            */
 #define SDFB_ERR_STATE         -5   /* call order violated (e.g. run before a mesh was set)        */
 #define SDFB_ERR_LIMIT         -6   /* more than SDFB_MAX_TRIANGLES triangles                      */
+#define SDFB_ERR_IO            -7   /* a file could not be opened or written                       */
 
 /* closest-triangle ids share a 32-bit word with a 5-bit sweep stamp */
 #define SDFB_MAX_TRIANGLES     134217726u
@@ -64,6 +65,12 @@ const char *sdfb_last_error(void);
  * sdfgen::is_gpu_available (common/sdfgen_unified.cpp:19-28): available == (count > 0). */
 int sdfb_device_count(void);
 
+/* Device memory of destroyed plans (and of finished one-shot / batch calls) stays in a library-private pool so that
+ * the next plan does not pay cudaMalloc/cudaFree again (tens to hundreds of ms per call); at most SDFB_POOL_RETAIN_MB
+ * (environment, default 16384) are kept across synchronisations.  This hands all of it back to the driver -- the
+ * state sdfgen::gpu::make_level_set3 leaves behind (gpu_lib/makelevelset3_gpu.cu:767-774 frees everything). */
+int sdfb_trim_memory(void);
+
 /* Kernel launches issued by this library in the calling process so far (all plans). */
 uint64_t sdfb_launch_count(void);
 
@@ -80,6 +87,25 @@ int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, u
                          const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
                          int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
                          int32_t *intersection_count_out, uint32_t flags);
+
+/*
+ * Many meshes / grids in one call (the batch API the reference lists as wanted, README.md:216-221; its callers loop
+ * over sdfgen::make_level_set3).  Every item is an independent sdfb_make_level_set3 with host buffers; `concurrency`
+ * items (<= 0: 4, at most 16) are in flight at a time, each on its own stream with its share of the SMs, so that
+ * small grids -- which are launch- and latency-bound one at a time -- overlap.  Results are those of the one-shot
+ * call, bit for bit.  item.status receives each item's code; the call returns the first failing item's code.
+ * flags: as for sdfb_make_level_set3 (SDFB_OUT_KFASTEST ...).
+ */
+typedef struct sdfb_batch_item {
+    const uint32_t *tri;   uint64_t ntri;     /* uint32[ntri][3]                                     */
+    const float    *xyz;   uint64_t nvert;    /* float[nvert][3]                                     */
+    float           origin[3];
+    float           dx;
+    int32_t         ni, nj, nk, exact_band;
+    float          *phi_out;                  /* ni*nj*nk floats, host                               */
+    int32_t         status;                   /* out                                                 */
+} sdfb_batch_item;
+int sdfb_make_level_set3_batch(sdfb_batch_item *items, int32_t n, int32_t concurrency, uint32_t flags);
 
 /* ---- plan API: device-resident state, explicit phases, k-slabs for multi-GPU ---------------- */
 
@@ -137,6 +163,16 @@ int sdfb_plan_download(sdfb_plan *plan, float *phi_out, int32_t *closest_tri_out
  * it before it overwrites phi.  The caller synchronises copy_stream (or the device) before reading phi_out.  This is
  * the streaming form of the D2H copy sdfgen::gpu::make_level_set3 does at gpu_lib/makelevelset3_gpu.cu:747-749. */
 int sdfb_plan_download_phi_async(sdfb_plan *plan, float *phi_out, void *copy_stream);
+
+/* Writes the signed phi of the last sdfb_plan_sign as a binary .sdf file straight from the device: 36-byte header
+ * (3 x int32 dims, 3 x float32 min_box, 3 x float32 min_box + dims*dx) followed by the float32 values, k fastest.
+ * Byte-for-byte the file write_sdf_binary(filename, phi_grid, min_box, dx, &inside) produces
+ * (/root/reference/common/sdf_io.cpp:10-74, called from app/main.cpp:336), without the host-side Array3f: the
+ * k-fastest layout and the inside count (values < 0) are produced on the device and the values stream to the file
+ * through pinned staging buffers while the next chunk is copied.  Whole-grid plans only (k_lo = 0, k_hi = nk).
+ * inside_count_out may be NULL.  Blocking. */
+int sdfb_plan_write_sdf(sdfb_plan *plan, const char *path, const float min_box[3], float dx,
+                        int64_t *inside_count_out, void *stream);
 
 /* Device time of the phases of the last completed run, in ms: out[0]=band (init+records+band+counts),
  * out[1]=sweeps, out[2]=sign/unpack, out[3]=total.  Blocks until the work has finished. */

@@ -24,13 +24,18 @@ from ._lib import Plan, SdfbError
 
 __version__ = "0.1.0"
 
-__all__ = ["generate_sdf", "generate_sdf_debug", "generate_from_mesh", "generate_from_file",
-           "is_gpu_available", "load_mesh", "save_sdf", "load_sdf", "Plan", "SdfbError", "launch_count"]
+__all__ = ["generate_sdf", "generate_sdf_batch", "generate_sdf_file", "generate_sdf_debug", "generate_from_mesh", "generate_from_file",
+           "is_gpu_available", "load_mesh", "save_sdf", "load_sdf", "Plan", "SdfbError", "launch_count", "trim_memory"]
 
 
 def is_gpu_available() -> bool:
     """True when a usable sm_100 device is present (sdfgen::is_gpu_available)."""
     return _lib.lib().sdfb_device_count() > 0
+
+
+def trim_memory() -> None:
+    """Return the device memory libsdfb keeps for reuse between calls to the driver (sdfb_trim_memory)."""
+    _lib.check(_lib.lib().sdfb_trim_memory())
 
 
 def launch_count() -> int:
@@ -81,6 +86,43 @@ def generate_sdf(vertices, triangles, origin, dx, nx, ny, nz, exact_band: int = 
                                          phi.ctypes.data, None, None, _lib.OUT_KFASTEST)
     _lib.check(rc)
     return phi
+
+
+def generate_sdf_batch(items, concurrency: int = 4):
+    """Many independent ``generate_sdf`` problems in one call (sdfb_make_level_set3_batch): ``items`` is a sequence of
+    dicts with the keys of generate_sdf's arguments (vertices, triangles, origin, dx, nx, ny, nz and optionally
+    exact_band); up to ``concurrency`` of them run at a time on separate streams.  Returns the list of (nx, ny, nz)
+    float32 arrays, identical to what generate_sdf returns for each item."""
+    items = list(items)
+    arr = (_lib.BatchItem * max(len(items), 1))()
+    keep, outs = [], []
+    for b, it in zip(arr, items):
+        nx, ny, nz = int(it["nx"]), int(it["ny"]), int(it["nz"])
+        v, t = _validate(it["vertices"], it["triangles"], it["dx"], nx, ny, nz, it.get("backend", "auto"))
+        phi = np.empty((nx, ny, nz), dtype=np.float32)
+        keep.append((v, t))
+        outs.append(phi)
+        b.tri, b.ntri, b.xyz, b.nvert = t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0]
+        b.origin[:] = [float(x) for x in _origin3(it["origin"])]
+        b.dx, b.ni, b.nj, b.nk, b.exact_band = float(it["dx"]), nx, ny, nz, int(it.get("exact_band", 1))
+        b.phi_out, b.status = phi.ctypes.data, 0
+    _lib.check(_lib.lib().sdfb_make_level_set3_batch(arr, len(items), int(concurrency), _lib.OUT_KFASTEST))
+    return outs
+
+
+def generate_sdf_file(vertices, triangles, origin, dx, nx, ny, nz, filename: str, exact_band: int = 1) -> int:
+    """Mesh -> binary .sdf file without the grid ever becoming a host array: what the reference's CLI does with
+    make_level_set3 + write_sdf_binary (app/main.cpp:273,336), with the k-fastest layout and the inside count
+    produced on the device (sdfb_plan_write_sdf).  Returns the inside count (cells with phi < 0)."""
+    v, t = _validate(vertices, triangles, dx, int(nx), int(ny), int(nz), "gpu")
+    o = _origin3(origin)
+    plan = _lib.Plan(int(nx), int(ny), int(nz), flags=_lib.OUT_KFASTEST)
+    try:
+        plan.set_mesh_host(v, t)
+        plan.run(o, float(dx), int(exact_band))
+        return plan.write_sdf(filename, o, float(dx))
+    finally:
+        plan.close()
 
 
 def generate_sdf_debug(vertices, triangles, origin, dx, nx, ny, nz, exact_band: int = 1, flags: int = 0):

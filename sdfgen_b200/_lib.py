@@ -10,10 +10,18 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDFB_LIB_PATH") or os.path.join(_HERE, "libsdfb.so")   # override: development builds only
 
-OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_LIMIT, ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
 OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN, SWEEP_STRIPS, SWEEP_RELAX, SWEEP_COLUMNS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 
 _lib = None
+
+
+class BatchItem(C.Structure):
+    """sdfb_batch_item (include/sdfb.h)."""
+    _fields_ = [("tri", C.c_void_p), ("ntri", C.c_uint64), ("xyz", C.c_void_p), ("nvert", C.c_uint64),
+                ("origin", C.c_float * 3), ("dx", C.c_float),
+                ("ni", C.c_int32), ("nj", C.c_int32), ("nk", C.c_int32), ("exact_band", C.c_int32),
+                ("phi_out", C.c_void_p), ("status", C.c_int32)]
 
 
 class SdfbError(RuntimeError):
@@ -67,6 +75,12 @@ def lib():
     L.sdfb_plan_download.argtypes = [vp, vp, vp, vp, vp]
     L.sdfb_plan_download_phi_async.restype = C.c_int
     L.sdfb_plan_download_phi_async.argtypes = [vp, vp, vp]
+    L.sdfb_trim_memory.restype = C.c_int
+    L.sdfb_trim_memory.argtypes = []
+    L.sdfb_make_level_set3_batch.restype = C.c_int
+    L.sdfb_make_level_set3_batch.argtypes = [C.POINTER(BatchItem), i32, i32, u32]
+    L.sdfb_plan_write_sdf.restype = C.c_int
+    L.sdfb_plan_write_sdf.argtypes = [vp, C.c_char_p, vp, f32, C.POINTER(C.c_int64), vp]
     L.sdfb_plan_phase_ms.restype = C.c_int
     L.sdfb_plan_phase_ms.argtypes = [vp, C.POINTER(f32 * 4)]
     _lib = L
@@ -80,6 +94,8 @@ def check(rc: int):
             raise ValueError(msg)          # the reference raises std::invalid_argument -> ValueError
         if rc == ERR_OOM:
             raise MemoryError(msg)
+        if rc == ERR_IO:
+            raise OSError(msg)
         raise SdfbError(rc, msg)
 
 
@@ -181,6 +197,13 @@ class Plan:
         """Enqueue the D2H copy of the last sign pass's phi on `copy_stream` (raw cudaStream_t, not the compute
         stream); phi_out is a pinned host address or array.  Synchronise that stream before reading."""
         check(lib().sdfb_plan_download_phi_async(self._h, _addr(phi_out), copy_stream or None))
+
+    def write_sdf(self, path, min_box, dx, stream=0) -> int:
+        """Write the signed phi of the last sign pass as a binary .sdf file straight from the device
+        (write_sdf_binary, common/sdf_io.cpp:10-74); returns the inside count."""
+        inside = C.c_int64()
+        check(lib().sdfb_plan_write_sdf(self._h, os.fsencode(path), self._origin(min_box), float(dx), C.byref(inside), stream or None))
+        return int(inside.value)
 
     def phase_ms(self):
         out = (C.c_float * 4)()

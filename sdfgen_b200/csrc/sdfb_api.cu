@@ -83,17 +83,25 @@ bool is_pageable(const void *p)
     return a.type == cudaMemoryTypeUnregistered;
 }
 
-// Device -> pageable host through two pinned staging buffers: the D2H copy of chunk i+1 overlaps the threaded
-// memcpy of chunk i into the destination.  Returns a CUDA error code.
-cudaError_t staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st)
+// Device -> host through two pinned staging buffers: the D2H copy of chunk i+1 overlaps what the sink does with chunk i
+// (a threaded memcpy into pageable memory, or a write to a file).  sink(data, n, offset) returns false to stop.
+// Returns a CUDA error code; *sink_ok tells whether every sink call succeeded.
+// the staging ring is allocated once per process (pinning 64 MB costs several ms) and shared under a lock
+struct StagingRing {
+    std::mutex mtx;
+    char *ring[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+} g_staging;
+
+template <class Sink>
+cudaError_t staged_d2h_sink(const void *src, size_t bytes, cudaStream_t st, Sink sink, bool *sink_ok)
 {
     const size_t CH = (size_t)32 << 20;
-    // the staging ring is allocated once per process (pinning 64 MB costs several ms) and shared under a lock
-    static std::mutex mtx;
-    static char *ring[2] = {nullptr, nullptr};
-    static cudaEvent_t ev[2] = {nullptr, nullptr};
-    std::lock_guard<std::mutex> lock(mtx);
+    std::lock_guard<std::mutex> lock(g_staging.mtx);
+    char **ring = g_staging.ring;
+    cudaEvent_t *ev = g_staging.ev;
     cudaError_t e = cudaSuccess;
+    bool ok = true;
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         if (!ring[b]) e = cudaHostAlloc(reinterpret_cast<void **>(&ring[b]), CH, cudaHostAllocPortable);
         if (e == cudaSuccess && !ev[b]) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
@@ -104,16 +112,89 @@ cudaError_t staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st
         e = cudaMemcpyAsync(ring[0], static_cast<const char *>(src), chunk(0), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(ev[0], st);
     }
-    for (size_t i = 0; i < nch && e == cudaSuccess; ++i) {
+    for (size_t i = 0; i < nch && e == cudaSuccess && ok; ++i) {
         if (i + 1 < nch) {                                  // ring[(i+1)&1] was drained in iteration i-1
             e = cudaMemcpyAsync(ring[(i + 1) & 1], static_cast<const char *>(src) + (i + 1) * CH, chunk(i + 1), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaEventRecord(ev[(i + 1) & 1], st);
         }
         if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
-        if (e == cudaSuccess) parallel_for_bytes(static_cast<char *>(dst) + i * CH, chunk(i), copy_bytes, ring[i & 1]);
+        if (e == cudaSuccess) ok = sink(ring[i & 1], chunk(i), i * CH);
     }
-    if (e != cudaSuccess) cudaStreamSynchronize(st);        // nothing may still be writing into the ring when the lock goes
+    if (e != cudaSuccess || !ok) cudaStreamSynchronize(st); // nothing may still be writing into the ring when the lock goes
+    if (sink_ok) *sink_ok = ok;
     return e;
+}
+
+cudaError_t staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    return staged_d2h_sink(src, bytes, st, [dst](const char *data, size_t n, size_t off) {
+        parallel_for_bytes(static_cast<char *>(dst) + off, n, copy_bytes, data);
+        return true;
+    }, nullptr);
+}
+
+// ---- device memory: a library-private stream-ordered pool per device ---------------------------------------------
+// cudaMalloc/cudaFree cost 30-900 ms per one-shot call on the B200 boxes (a dozen buffers mapped and unmapped every
+// call; 128^3: 40-100 ms per call around 10 ms of kernels, with stalls up to 0.9 s).  All plan memory therefore comes
+// from a cudaMemPool of our own that keeps freed blocks (up to SDFB_POOL_RETAIN_MB, default 16 GiB, above which the
+// driver releases at the next synchronisation); sdfb_trim_memory() hands everything back.  Allocations are made on
+// the pool's own stream and that stream is synchronised at once (it never carries work), so the memory may be used
+// on any stream; frees are enqueued on it after the plan's work has completed (plan_quiesce).
+struct DevicePool {
+    cudaMemPool_t pool = nullptr;
+    cudaStream_t st = nullptr;
+};
+DevicePool g_pools[64];
+std::mutex g_pool_mtx;
+
+cudaError_t pool_for_current_device(DevicePool **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_pool_mtx);
+    DevicePool &dp = g_pools[dev];
+    if (!dp.pool) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if ((e = cudaMemPoolCreate(&pool, &props)) != cudaSuccess) return e;
+        unsigned long long retain = (unsigned long long)16 << 30;
+        if (getenv("SDFB_POOL_RETAIN_MB")) retain = strtoull(getenv("SDFB_POOL_RETAIN_MB"), nullptr, 10) << 20;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &retain)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&dp.st, cudaStreamNonBlocking)) != cudaSuccess) {
+            cudaMemPoolDestroy(pool);
+            return e;
+        }
+        dp.pool = pool;
+    }
+    *out = &dp;
+    return cudaSuccess;
+}
+
+template <class T>
+cudaError_t dev_alloc(T **ptr, size_t bytes)
+{
+    DevicePool *dp = nullptr;
+    cudaError_t e = pool_for_current_device(&dp);
+    if (e != cudaSuccess) return e;
+    void *v = nullptr;
+    if ((e = cudaMallocFromPoolAsync(&v, bytes ? bytes : 1, dp->pool, dp->st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(dp->st)) != cudaSuccess) return e;
+    *ptr = static_cast<T *>(v);
+    return cudaSuccess;
+}
+
+// the caller has made sure nothing on the device still uses the block (plan_quiesce)
+void dev_free(void *ptr)
+{
+    if (!ptr) return;
+    DevicePool *dp = nullptr;
+    if (pool_for_current_device(&dp) == cudaSuccess) cudaFreeAsync(ptr, dp->st);
 }
 
 struct DeviceGuard {
@@ -162,14 +243,25 @@ struct sdfb_plan {
     cudaEvent_t ev_copy = nullptr;   // end of the last asynchronous phi download
     bool copy_pending = false;
     bool timed = false;
+    bool own_stream = false;         // the plan is only ever used on `stream` (one-shot and batch calls): quiescing waits for
+    cudaStream_t stream = nullptr;   // that stream instead of the whole device
+    int max_ctas = 0;                // batch mode: cap on the persistent sweep grids so that several plans share the SMs (0 = no cap)
 };
 
 namespace {
 
+// nothing on the device may still use the plan's buffers when they go back to the pool
+void plan_quiesce(sdfb_plan *p)
+{
+    if (p->own_stream) cudaStreamSynchronize(p->stream); else cudaDeviceSynchronize();
+    if (p->copy_pending && p->ev_copy) { cudaEventSynchronize(p->ev_copy); p->copy_pending = false; }
+}
+
 void free_mesh(sdfb_plan *p)
 {
-    cudaFree(p->tri_own); cudaFree(p->xyz_own); cudaFree(p->rec); cudaFree(p->units); cudaFree(p->ext);
-    cudaFree(p->prefix); cudaFree(p->block_sums);
+    plan_quiesce(p);
+    dev_free(p->tri_own); dev_free(p->xyz_own); dev_free(p->rec); dev_free(p->units); dev_free(p->ext);
+    dev_free(p->prefix); dev_free(p->block_sums);
     p->tri_own = nullptr; p->xyz_own = nullptr; p->rec = nullptr; p->units = nullptr; p->ext = nullptr;
     p->tri_own_cap = 0; p->xyz_own_cap = 0;
     p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0; p->have_mesh = false;
@@ -178,14 +270,15 @@ void free_mesh(sdfb_plan *p)
 int ensure_mesh_capacity(sdfb_plan *p, uint64_t ntri)
 {
     if (ntri <= p->rec_cap && p->rec) return SDFB_OK;
-    cudaFree(p->rec); cudaFree(p->units); cudaFree(p->ext); cudaFree(p->prefix); cudaFree(p->block_sums);
+    if (p->rec) plan_quiesce(p);
+    dev_free(p->rec); dev_free(p->units); dev_free(p->ext); dev_free(p->prefix); dev_free(p->block_sums);
     p->rec = nullptr; p->units = nullptr; p->ext = nullptr; p->prefix = nullptr; p->block_sums = nullptr; p->rec_cap = 0;
     uint64_t cap = ntri ? ntri : 1;
-    CU(cudaMalloc(&p->rec, cap * sizeof(TriRec)));
-    CU(cudaMalloc(&p->units, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&p->ext, cap * sizeof(TriExt)));
-    CU(cudaMalloc(&p->prefix, (cap + 1) * sizeof(uint64_t)));
-    CU(cudaMalloc(&p->block_sums, (cap / 2048 + 2) * sizeof(uint64_t)));
+    CU(dev_alloc(&p->rec, cap * sizeof(TriRec)));
+    CU(dev_alloc(&p->units, cap * sizeof(uint32_t)));
+    CU(dev_alloc(&p->ext, cap * sizeof(TriExt)));
+    CU(dev_alloc(&p->prefix, (cap + 1) * sizeof(uint64_t)));
+    CU(dev_alloc(&p->block_sums, (cap / 2048 + 2) * sizeof(uint64_t)));
     p->rec_cap = cap;
     return SDFB_OK;
 }
@@ -210,6 +303,17 @@ extern "C" {
 const char *sdfb_version(void) { return "sdfgen-b200 0.1 (sm_100a)"; }
 const char *sdfb_last_error(void) { return g_err; }
 uint64_t sdfb_launch_count(void) { return g_launches.load(); }
+
+int sdfb_trim_memory(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mtx);
+    for (auto &dp : g_pools) {
+        if (!dp.pool) continue;
+        CU(cudaStreamSynchronize(dp.st));                         // pending frees
+        CU(cudaMemPoolTrimTo(dp.pool, 0));
+    }
+    return SDFB_OK;
+}
 
 int sdfb_device_count(void)
 {
@@ -242,18 +346,18 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     p->g.dx = 1.f; p->g.ox = p->g.oy = p->g.oz = 0.f; p->g.band = 1;
     const size_t V = (size_t)p->g.slab_voxels();
     cudaError_t e;
-    if ((e = cudaMalloc(&p->cells, ((size_t)p->g.cell_count() + 8) * sizeof(uint64_t))) != cudaSuccess ||   // +8: bulk prefetches round up to 16 B
-        (e = cudaMalloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
-        ((flags & SDFB_OUT_KFASTEST) && (e = cudaMalloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||
-        (e = cudaMalloc(&p->changed, 2 * sizeof(unsigned long long))) != cudaSuccess) {
+    if ((e = dev_alloc(&p->cells, ((size_t)p->g.cell_count() + 8) * sizeof(uint64_t))) != cudaSuccess ||   // +8: bulk prefetches round up to 16 B
+        (e = dev_alloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
+        (e = dev_alloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
+        ((flags & SDFB_OUT_KFASTEST) && (e = dev_alloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||
+        (e = dev_alloc(&p->changed, 3 * sizeof(unsigned long long))) != cudaSuccess) {   // changed, evaluations, inside count
         sdfb_plan_destroy(p);
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
     }
     p->progress_words = sweep_columns_progress_words(p->g);
     if (sweep_strips_progress_words(p->g) > p->progress_words) p->progress_words = sweep_strips_progress_words(p->g);
-    if (p->progress_words && (e = cudaMalloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
+    if (p->progress_words && (e = dev_alloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
         sdfb_plan_destroy(p);
         cudaGetLastError();
         return fail(SDFB_ERR_OOM, "device allocation failed: %s", cudaGetErrorString(e));
@@ -271,10 +375,10 @@ int sdfb_plan_destroy(sdfb_plan *p)
 {
     if (!p) return SDFB_OK;
     DeviceGuard dg(p->device);
-    cudaDeviceSynchronize();
+    plan_quiesce(p);
     free_mesh(p);
-    cudaFree(p->cells); cudaFree(p->counts); cudaFree(p->phi); cudaFree(p->phi_k); cudaFree(p->scratch);
-    cudaFree(p->changed); cudaFree(p->progress); cudaFree(p->relax);
+    dev_free(p->cells); dev_free(p->counts); dev_free(p->phi); dev_free(p->phi_k); dev_free(p->scratch);
+    dev_free(p->changed); dev_free(p->progress); dev_free(p->relax);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
     if (p->ev_copy) cudaEventDestroy(p->ev_copy);
     delete p;
@@ -290,13 +394,15 @@ int sdfb_plan_set_mesh_host(sdfb_plan *p, const uint32_t *tri, uint64_t ntri, co
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (ntri > p->tri_own_cap || !p->tri_own) {      // grow-only staging buffers: repeated calls do not reallocate
-        cudaFree(p->tri_own); p->tri_own = nullptr; p->tri_own_cap = 0;
-        CU(cudaMalloc(&p->tri_own, (ntri ? ntri : 1) * 3 * sizeof(uint32_t)));
+        if (p->tri_own) { plan_quiesce(p); dev_free(p->tri_own); }
+        p->tri_own = nullptr; p->tri_own_cap = 0;
+        CU(dev_alloc(&p->tri_own, (ntri ? ntri : 1) * 3 * sizeof(uint32_t)));
         p->tri_own_cap = ntri ? ntri : 1;
     }
     if (nvert > p->xyz_own_cap || !p->xyz_own) {
-        cudaFree(p->xyz_own); p->xyz_own = nullptr; p->xyz_own_cap = 0;
-        CU(cudaMalloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
+        if (p->xyz_own) { plan_quiesce(p); dev_free(p->xyz_own); }
+        p->xyz_own = nullptr; p->xyz_own_cap = 0;
+        CU(dev_alloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
         p->xyz_own_cap = nvert ? nvert : 1;
     }
     if (ntri) CU(cudaMemcpyAsync(p->tri_own, tri, ntri * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -352,10 +458,10 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
         } else if (s >= relax_from && s + 1 < 31 && s > p->last_sweep && sweep_relax_supported(p->g)) {
             if (!p->relax) {
                 const size_t bytes = sweep_relax_scratch_bytes(p->g);
-                CU(cudaMalloc(&p->relax, bytes));
+                CU(dev_alloc(&p->relax, bytes));
                 CU(cudaMemsetAsync(p->relax, 0, bytes, st));
             }
-            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st);
+            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st, p->max_ctas);
             // a sweep that turns out to change a large part of the grid is handed back (cells restored, flag set):
             // this launch then runs it with the column schedule, and exits at once otherwise
             if (p->epoch >= 65000u) {
@@ -363,7 +469,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                 p->epoch = 0;
             }
             g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st,
-                                               sweep_relax_fallback_flag(p->relax));
+                                               sweep_relax_fallback_flag(p->relax), p->max_ctas);
         } else {
             if (p->epoch >= 65000u) {   // progress words are epoch<<16 | steps: start over before it wraps
                 CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
@@ -372,7 +478,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
             if (p->flags & SDFB_SWEEP_STRIPS)
                 g_launches += launch_sweep_strips(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
             else
-                g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
+                g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, nullptr, p->max_ctas);
         }
     }
     if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;
@@ -466,7 +572,7 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
         else CU(cudaMemcpyAsync(phi_out, src, V * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (tri_out || (count_out && kf)) {
-        if (!p->scratch) CU(cudaMalloc(&p->scratch, V * sizeof(int32_t) * (kf ? 2 : 1)));
+        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t) * (kf ? 2 : 1)));
     }
     if (tri_out) {
         g_launches += launch_unpack_tri(p->cells, p->g, false, p->scratch, st);
@@ -500,6 +606,49 @@ int sdfb_plan_download_phi_async(sdfb_plan *p, float *phi_out, void *copy_stream
     return SDFB_OK;
 }
 
+int sdfb_plan_write_sdf(sdfb_plan *p, const char *path, const float min_box[3], float dx, int64_t *inside_count_out, void *stream)
+{
+    if (!p || !path || !min_box) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->have_sign) return fail(SDFB_ERR_STATE, "sdfb_plan_write_sdf needs a completed sdfb_plan_sign");
+    if (p->g.k_lo != 0 || p->g.k_hi != p->g.nk) return fail(SDFB_ERR_STATE, "sdfb_plan_write_sdf needs a whole-grid plan (this one holds the slab [%d,%d) of %d planes)", p->g.k_lo, p->g.k_hi, p->g.nk);
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t V = (size_t)p->g.slab_voxels();
+    // the file stores k fastest (common/sdf_io.cpp:49-57): take the plan's own k-fastest copy or make one in the scratch
+    const float *src = p->phi_k;
+    if (!src) {
+        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t)));
+        g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, p->scratch, st);
+        src = reinterpret_cast<const float *>(p->scratch);
+    }
+    // inside count = number of values < 0 (-0.0f does not count, common/sdf_io.cpp:53), reduced on the device
+    CU(cudaMemsetAsync(p->changed + 2, 0, sizeof(unsigned long long), st));
+    g_launches += launch_count_negative(src, (int64_t)V, p->changed + 2, st);
+    CU(cudaGetLastError());
+
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SDFB_ERR_IO, "Failed to open file for writing: %s", path);
+    // header: 3 x int32 dims, 3 x float32 bounds_min, 3 x float32 bounds_max = min + n * dx in float (common/sdf_io.cpp:22-45)
+    int32_t dims[3] = {p->g.ni, p->g.nj, p->g.nk};
+    float bounds[6];
+    for (int a = 0; a < 3; ++a) {
+        bounds[a] = min_box[a];
+        volatile float ext = (float)dims[a] * dx;             // product rounded to float before the sum, as in the reference
+        bounds[3 + a] = min_box[a] + ext;
+    }
+    bool ok = fwrite(dims, sizeof(dims), 1, f) == 1 && fwrite(bounds, sizeof(bounds), 1, f) == 1;
+    cudaError_t e = cudaSuccess;
+    if (ok) e = staged_d2h_sink(src, V * sizeof(float), st, [f](const char *data, size_t n, size_t) { return fwrite(data, 1, n, f) == n; }, &ok);
+    if (fclose(f) != 0) ok = false;
+    if (e != cudaSuccess) return fail(SDFB_ERR_CUDA, "copying phi to the host failed: %s", cudaGetErrorString(e));
+    if (!ok) return fail(SDFB_ERR_IO, "Failed to write SDF data to file: %s", path);
+    unsigned long long inside = 0;
+    CU(cudaMemcpyAsync(&inside, p->changed + 2, sizeof(inside), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (inside_count_out) *inside_count_out = (int64_t)inside;
+    return SDFB_OK;
+}
+
 int sdfb_plan_phase_ms(sdfb_plan *p, float out[4])
 {
     if (!p || !out) return fail(SDFB_ERR_INVALID, "null argument");
@@ -524,6 +673,7 @@ int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, u
     sdfb_plan *p = nullptr;
     int rc = sdfb_plan_create(&p, dev, ni, nj, nk, 0, nk, flags);
     if (rc) return rc;
+    p->own_stream = true; p->stream = nullptr;                   // everything below runs on the default stream
     rc = sdfb_plan_set_mesh_host(p, tri, ntri, xyz, nvert, nullptr);
     if (!rc) rc = sdfb_plan_run(p, origin, dx, exact_band, nullptr);
     // everything above is asynchronous: touch the (usually fresh, pageable) output pages while the GPU computes
@@ -532,6 +682,68 @@ int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, u
     if (!rc) rc = sdfb_plan_download(p, phi_out, closest_tri_out, intersection_count_out, nullptr);
     sdfb_plan_destroy(p);
     return rc;
+}
+
+// Many meshes / grids per call (the reference lists a batch API as wanted, README.md:216-221; small grids are
+// launch- and latency-bound, so one grid at a time leaves most SMs idle).  `concurrency` worker threads each own a
+// non-blocking stream and a plan that is reused while consecutive items have the same dimensions; the persistent
+// sweep grids are capped to the worker's share of the SMs so that the kernels of different items really overlap.
+int sdfb_make_level_set3_batch(sdfb_batch_item *items, int32_t n, int32_t concurrency, uint32_t flags)
+{
+    if (n < 0 || (n > 0 && !items)) return fail(SDFB_ERR_INVALID, "bad batch");
+    if (n == 0) return SDFB_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(SDFB_ERR_NO_DEVICE, "no CUDA device is visible; libsdfb has no CPU fallback"); }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || !device_is_sm100(dev)) {
+        cudaGetLastError();
+        return fail(SDFB_ERR_NO_DEVICE, "device %d is not an sm_100 (B200) part; libsdfb ships sm_100a code only", dev);
+    }
+    int W = concurrency <= 0 ? 4 : concurrency;
+    if (W > 16) W = 16;
+    if (W > n) W = n;
+    std::atomic<int32_t> next{0};
+    std::mutex err_mtx;
+    int first_rc = SDFB_OK;
+    char first_msg[sizeof(g_err)] = "";
+    auto worker = [&]() {
+        cudaStream_t st = nullptr;
+        sdfb_plan *p = nullptr;
+        int rc0 = cudaSetDevice(dev) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess
+                      ? SDFB_OK : fail(SDFB_ERR_CUDA, "could not create a stream on device %d", dev);
+        for (;;) {
+            const int32_t i = next.fetch_add(1);
+            if (i >= n) break;
+            sdfb_batch_item &it = items[i];
+            int rc = rc0;
+            if (!rc && !it.phi_out) rc = fail(SDFB_ERR_INVALID, "batch item %d: phi_out is null", i);
+            if (!rc && (!p || p->g.ni != it.ni || p->g.nj != it.nj || p->g.nk != it.nk)) {
+                sdfb_plan_destroy(p); p = nullptr;
+                rc = sdfb_plan_create(&p, dev, it.ni, it.nj, it.nk, 0, it.nk, flags);
+                if (!rc) { p->own_stream = true; p->stream = st; }
+                if (!rc && W > 1) p->max_ctas = (3 * sms) / W > sms / 2 ? (3 * sms) / W : sms / 2;
+            }
+            if (!rc) rc = sdfb_plan_set_mesh_host(p, it.tri, it.ntri, it.xyz, it.nvert, st);
+            if (!rc) rc = sdfb_plan_run(p, it.origin, it.dx, it.exact_band, st);
+            if (!rc) rc = sdfb_plan_download(p, it.phi_out, nullptr, nullptr, st);
+            it.status = rc;
+            if (rc) {
+                std::lock_guard<std::mutex> lock(err_mtx);
+                if (!first_rc) { first_rc = rc; snprintf(first_msg, sizeof(first_msg), "batch item %d: %.480s", i, g_err); }
+            }
+        }
+        sdfb_plan_destroy(p);
+        if (st) cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < W; ++w) th.emplace_back(worker);
+    {
+        DeviceGuard dg(dev);
+        worker();                                                 // the calling thread is worker 0
+    }
+    for (auto &t : th) t.join();
+    if (first_rc) return fail(first_rc, "%s", first_msg);
+    return SDFB_OK;
 }
 
 }  // extern "C"

@@ -39,11 +39,12 @@ int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int s
                         unsigned long long *changed, cudaStream_t st);
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
-                         const unsigned int *run_if = nullptr);
+                         const unsigned int *run_if = nullptr, int max_ctas = 0);
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st);
 int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st);
 int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st);
+int launch_count_negative(const float *v, int64_t n, unsigned long long *out, cudaStream_t st);
 int launch_relayout_i32(const int32_t *src, const Grid &g, int32_t *dst_kfastest, cudaStream_t st);
 
 int launch_sweep_strips(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
@@ -53,7 +54,7 @@ bool sweep_relax_supported(const Grid &g);
 size_t sweep_relax_scratch_bytes(const Grid &g);
 const unsigned int *sweep_relax_fallback_flag(const void *scratch);
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st);
+                       unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas = 0);
 
 size_t sweep_columns_progress_words(const Grid &g);
 size_t sweep_strips_progress_words(const Grid &g);

@@ -64,6 +64,16 @@ __global__ void __launch_bounds__(256) k_relayout(const uint32_t *__restrict__ s
     }
 }
 
+// number of values < 0 (the .sdf writer's "inside" count, common/sdf_io.cpp:53: -0.0f is not inside)
+__global__ void __launch_bounds__(256) k_count_negative(const float *__restrict__ v, int64_t n, unsigned long long *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned mine = 0;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += stride) mine += v[x] < 0.0f ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+}
+
 // Halo planes received from a neighbouring slab: raise the stamp to the maximum so that the sweep's
 // "unchanged since I last looked" memo never skips them (the copy this slab looked at may have been stale).
 __global__ void __launch_bounds__(256) k_halo_refresh(uint64_t *__restrict__ cells, int64_t plane, int64_t far_off)
@@ -81,6 +91,12 @@ __global__ void __launch_bounds__(256) k_halo_refresh(uint64_t *__restrict__ cel
 int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st)
 {
     k_halo_refresh<<<148 * 2, 256, 0, st>>>(cells, g.plane(), g.plane() * (int64_t)(g.nkl() + 1));
+    return 1;
+}
+
+int launch_count_negative(const float *v, int64_t n, unsigned long long *out, cudaStream_t st)
+{
+    k_count_negative<<<148 * 8, 256, 0, st>>>(v, n, out);
     return 1;
 }
 

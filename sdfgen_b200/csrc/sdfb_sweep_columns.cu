@@ -627,7 +627,7 @@ size_t sweep_columns_progress_words(const Grid &g)
 
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
-                         const unsigned int *run_if)
+                         const unsigned int *run_if, int max_ctas)
 {
     ColParams P{};
     P.g = g;
@@ -670,6 +670,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     if (occ < 1) occ = 1;
     if (getenv("SDFB_MAX_OCC")) occ = min(occ, atoi(getenv("SDFB_MAX_OCC")));   // experiment knob
     int grid = sms * occ;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;            // batch mode: several plans share the device
     int ncols = P.NJ * P.NK;
     if (grid > ncols) grid = ncols;
     kern<<<grid, NTHREADS, 0, st>>>(cells, rec, P, progress + 4, progress, changed);

@@ -561,7 +561,7 @@ const unsigned int *sweep_relax_fallback_flag(const void *scratch) { return stat
 
 // `scratch` must be zero-initialised once after allocation (bitmaps and counters return to zero after every sweep).
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st)
+                       unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas)
 {
     RelaxParams P{};
     P.g = g;
@@ -615,7 +615,9 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         ++launches;
     }
     void *args[] = {&P};
-    cudaLaunchCooperativeKernel((const void *)k_relax_rounds, dim3(sms * occ), dim3(RX_THREADS), args, smem, st);
+    int grid = sms * occ;                                            // all CTAs of a cooperative launch are co-resident
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;            // batch mode: several plans share the device
+    cudaLaunchCooperativeKernel((const void *)k_relax_rounds, dim3(grid), dim3(RX_THREADS), args, smem, st);
     if (P.debug) {
         unsigned long long h[512];
         cudaStreamSynchronize(st);
@@ -626,7 +628,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
             fprintf(stderr, "\n");
         }
         fprintf(stderr, "[relax] sweep %2d: round 0 %.3f ms, total %.3f ms, first list %llu, rounds %llu, grid %d x %d\n", sweep_index,
-                h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], sms * occ, RX_THREADS);
+                h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], grid, RX_THREADS);
     }
     return launches;
 }

@@ -89,6 +89,87 @@ def test_reference_testmesh_known_answer_sha256(golden_dir):
     assert np.array_equal(nzi, z["counts_nonzero_idx"]) and np.array_equal(cnt[nzi], z["counts_nonzero_val"])
 
 
+def test_batch_call_equals_one_call_per_item(golden_dir):
+    """sdfb_make_level_set3_batch: mixed grid sizes and meshes, more items than workers, every concurrency; each result
+    equals the one-shot call's bit for bit, and a bad item fails alone."""
+    z = np.load(os.path.join(golden_dir, "c0_testmesh.npz"))
+    ni, nj, nk = (int(x) for x in z["dims"])
+    c0 = dict(vertices=z["vertices"], triangles=z["triangles"], origin=tuple(z["origin"]), dx=float(z["dx"]), nx=ni, ny=nj, nz=nk)
+    items = [c0]
+    for name, n, band in [("c1_blob_256", 40, 1), ("c2_icosphere_512", 33, 2), ("c1_blob_256", 40, 1), ("c3_torus_1024", 24, 1)]:
+        w = meshes.workload(name, n=n, shuffle=True)
+        items.append(dict(vertices=w["vertices"], triangles=w["triangles"], origin=tuple(w["origin"]), dx=w["dx"],
+                          nx=n, ny=n + 3, nz=n - 5, exact_band=band))
+    items = items + items[::-1] + [c0, c0]
+    want = [sdfgen_b200.generate_sdf(it["vertices"], it["triangles"], it["origin"], it["dx"], it["nx"], it["ny"], it["nz"],
+                                     exact_band=it.get("exact_band", 1)) for it in items[:5]]
+    want = want + want[::-1] + [want[0], want[0]]
+    for conc in (1, 3, 4, 16):
+        got = sdfgen_b200.generate_sdf_batch(items, concurrency=conc)
+        assert len(got) == len(items)
+        for a, b in zip(got, want):
+            assert a.shape == b.shape and _same(a, b), conc
+    assert sdfgen_b200.generate_sdf_batch([]) == []
+    # one item with an impossible grid: the call reports it, the others are still computed
+    arr = (_lib.BatchItem * 2)()
+    outs = []
+    for b, it in zip(arr, items[:2]):
+        v, t = np.ascontiguousarray(it["vertices"], np.float32), np.ascontiguousarray(it["triangles"], np.uint32)
+        phi = np.empty((it["nx"], it["ny"], it["nz"]), np.float32)
+        outs.append((v, t, phi))
+        b.tri, b.ntri, b.xyz, b.nvert = t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0]
+        b.origin[:] = [float(x) for x in it["origin"]]
+        b.dx, b.ni, b.nj, b.nk, b.exact_band, b.phi_out = it["dx"], it["nx"], it["ny"], it["nz"], 1, phi.ctypes.data
+    arr[0].ni = 40000
+    rc = _lib.lib().sdfb_make_level_set3_batch(arr, 2, 2, _lib.OUT_KFASTEST)
+    assert rc == _lib.ERR_INVALID and arr[0].status == _lib.ERR_INVALID and arr[1].status == _lib.OK
+    assert b"batch item 0" in _lib.lib().sdfb_last_error()
+    assert _same(outs[1][2], want[1])
+
+
+def test_sdf_file_written_from_the_device(golden_dir, tmp_path):
+    """sdfb_plan_write_sdf: (1) the reference CLI's known-answer file for its own test mesh, byte for byte (sha256) and
+    inside count; (2) on ragged grids, with and without the plan's own k-fastest copy, the bytes equal the numpy writer's
+    (mesh_io.save_sdf, checked against the reference format on the CPU) and the file reads back; (3) error paths."""
+    z = np.load(os.path.join(golden_dir, "c0_testmesh.npz"))
+    ni, nj, nk = (int(x) for x in z["dims"])
+    path = str(tmp_path / "c0.sdf")
+    inside = sdfgen_b200.generate_sdf_file(z["vertices"], z["triangles"], tuple(z["origin"]), float(z["dx"]), ni, nj, nk, path)
+    assert inside == 286481
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == "d93ee4cedca50cd0f280adea355210ef95c5954d9732a01d5286fd393261dc23"
+
+    w = meshes.workload("c1_blob_256", n=40, shuffle=True)
+    for dims in [(37, 41, 29), (33, 1, 70), (1, 1, 1)]:
+        ref = sdfgen_b200.generate_sdf(w["vertices"], w["triangles"], tuple(w["origin"]), w["dx"], *dims)
+        want = str(tmp_path / "want.sdf")
+        sdfgen_b200.save_sdf(want, ref, tuple(w["origin"]), w["dx"])
+        for flags in (0, _lib.OUT_KFASTEST):
+            p = _lib.Plan(*dims, flags=flags)
+            p.set_mesh_host(w["vertices"], w["triangles"])
+            p.run(w["origin"], w["dx"], 1)
+            got = str(tmp_path / f"got{flags}.sdf")
+            n_in = p.write_sdf(got, w["origin"], w["dx"])
+            assert n_in == int((ref < 0).sum()), (dims, flags)
+            assert open(got, "rb").read() == open(want, "rb").read(), (dims, flags)
+            assert p.write_sdf(got, w["origin"], w["dx"]) == n_in        # twice: the count starts from zero
+            with pytest.raises(OSError):
+                p.write_sdf(str(tmp_path / "no_such_dir" / "x.sdf"), w["origin"], w["dx"])
+            p.close()
+        back, o, dx = sdfgen_b200.load_sdf(got)[:3]
+        assert _same(np.asarray(back), ref)
+    p = _lib.Plan(8, 8, 8)
+    p.set_mesh_host(w["vertices"], w["triangles"])
+    with pytest.raises(_lib.SdfbError):                                  # nothing computed yet
+        p.write_sdf(str(tmp_path / "x.sdf"), w["origin"], w["dx"])
+    p.close()
+    p = _lib.Plan(8, 8, 8, k_lo=2, k_hi=6)
+    p.set_mesh_host(w["vertices"], w["triangles"])
+    p.run(w["origin"], w["dx"], 1)
+    with pytest.raises(_lib.SdfbError):                                  # slab plans cannot write the k-fastest file
+        p.write_sdf(str(tmp_path / "x.sdf"), w["origin"], w["dx"])
+    p.close()
+
+
 @pytest.mark.parametrize("name,n,shuffle", [("c1_blob_256", 64, True), ("c2_icosphere_512", 48, True),
                                              ("c1_blob_256", 96, False), ("c3_torus_1024", 56, False)])
 def test_live_oracle_downscaled_twins(name, n, shuffle):
