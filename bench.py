@@ -221,46 +221,103 @@ def run_single_gpu(args):
     pass1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     pass2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
 
-    # e2e: pinned host mesh -> H2D -> run -> D2H phi (pinned), every step, through the C ABI.
-    # (a) blocking: one call after the other, as sdfgen::gpu::make_level_set3 is used (latency of a call);
-    # (b) streaming: the D2H copy of step i runs on a copy stream and overlaps the H2D + kernels of step i+1
-    #     (sdfb_plan_download_phi_async, two pinned output buffers) -- every step still moves all its bytes inside
-    #     the timed region; this is the throughput of a stream of requests and the figure reported as e2e.value.
-    def e2e_step():
-        plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=sh)
-        plan.run(w["origin"], w["dx"], 1, stream=sh)
-        plan.download(phi=True, stream=sh, phi_out=phi_pin.data_ptr())     # blocking
+    e2e = None
+    concurrent = None
+    if args.no_e2e:                                            # profiling runs (ncu launch list): the device leg only
+        plan.download(phi=True, stream=sh, phi_out=phi_pin.data_ptr())
+    else:
+        # e2e: pinned host mesh -> H2D -> run -> D2H phi (pinned), every step, through the C ABI.
+        # (a) blocking: one call after the other, as sdfgen::gpu::make_level_set3 is used (latency of a call);
+        # (b) streaming: the D2H copy of step i runs on a copy stream and overlaps the H2D + kernels of step i+1
+        #     (sdfb_plan_download_phi_async, two pinned output buffers) -- every step still moves all its bytes inside
+        #     the timed region; this is the throughput of a stream of requests and the figure reported as e2e.value.
+        def e2e_step():
+            plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=sh)
+            plan.run(w["origin"], w["dx"], 1, stream=sh)
+            plan.download(phi=True, stream=sh, phi_out=phi_pin.data_ptr())     # blocking
 
-    e2e_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.cuda.stream(stream):
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                e2e_step()
+            ev1.record(stream)
+        torch.cuda.synchronize()
+        e2e_wall = (time.perf_counter() - t0) / args.steps
+        e2e_blocking_ms = max(ev0.elapsed_time(ev1) / args.steps, 1e3 * e2e_wall)
+
+        copy_stream = torch.cuda.Stream()
+        phi_pin2 = torch.empty(V, dtype=torch.float32).pin_memory()
+        outs = (phi_pin, phi_pin2)
+
+        def e2e_stream_step(it):
+            plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=sh)
+            plan.run(w["origin"], w["dx"], 1, stream=sh)
+            plan.download_phi_async(outs[it & 1].data_ptr(), copy_stream.cuda_stream)
+
+        e2e_stream_step(0)
+        e2e_stream_step(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(args.steps):
+            e2e_stream_step(it)
+        torch.cuda.synchronize()                                   # the last copy has landed
+        e2e_one_plan_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        assert torch.equal(phi_pin, phi_pin2)                      # both buffers hold the same field
+
+        # (c) streaming with TWO plans in flight (sdfb_plan_set_concurrency(2): each plan's sweep kernels take half the
+        #     SMs, the plans run on their own streams): the sweeps are latency-bound, so two grids side by side finish
+        #     sooner than one after the other.  Requests alternate between the plans; every request still uploads its mesh
+        #     and downloads its field inside the timed region.  First the same thing device-resident, for reference.
+        plan2 = _lib.Plan(ni, nj, nk, flags=flags)
+        stream2 = torch.cuda.Stream()
+        plans, streams = (plan, plan2), (stream, stream2)
+        for p_, s_ in zip(plans, streams):
+            p_.set_concurrency(2)
+            p_.set_mesh_device(d_tri.data_ptr(), T, d_xyz.data_ptr(), NV, stream=s_.cuda_stream, keepalive=(d_tri, d_xyz))
+            p_.run(w["origin"], w["dx"], 1, stream=s_.cuda_stream)
+        torch.cuda.synchronize()
         ev0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()
+        stream2.wait_event(ev0)
+        for it in range(2 * ((args.steps + 1) // 2)):
+            plans[it & 1].run(w["origin"], w["dx"], 1, stream=streams[it & 1].cuda_stream)
+        stream.wait_stream(stream2)
         ev1.record(stream)
-    torch.cuda.synchronize()
-    e2e_wall = (time.perf_counter() - t0) / args.steps
-    e2e_blocking_ms = max(ev0.elapsed_time(ev1) / args.steps, 1e3 * e2e_wall)
+        torch.cuda.synchronize()
+        two_plans_ms = ev0.elapsed_time(ev1) / (2 * ((args.steps + 1) // 2))
 
-    copy_stream = torch.cuda.Stream()
-    phi_pin2 = torch.empty(V, dtype=torch.float32).pin_memory()
-    outs = (phi_pin, phi_pin2)
+        def e2e_two_plans_step(it):
+            p_, s_ = plans[it & 1], streams[it & 1].cuda_stream
+            p_.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=s_)
+            p_.run(w["origin"], w["dx"], 1, stream=s_)
+            p_.download_phi_async(outs[it & 1].data_ptr(), copy_stream.cuda_stream)
 
-    def e2e_stream_step(it):
-        plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=sh)
-        plan.run(w["origin"], w["dx"], 1, stream=sh)
-        plan.download_phi_async(outs[it & 1].data_ptr(), copy_stream.cuda_stream)
-
-    e2e_stream_step(0)
-    e2e_stream_step(1)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(args.steps):
-        e2e_stream_step(it)
-    torch.cuda.synchronize()                                   # the last copy has landed
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    assert torch.equal(phi_pin, phi_pin2)                      # both buffers hold the same field
+        phi_pin.zero_(); phi_pin2.zero_()
+        e2e_two_plans_step(0)
+        e2e_two_plans_step(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for it in range(args.steps):
+            e2e_two_plans_step(it)
+        torch.cuda.synchronize()                                   # the last copy has landed
+        e2e_two_plans_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        assert torch.equal(phi_pin, phi_pin2)
+        plan2.close()
+        e2e_ms = min(e2e_one_plan_ms, e2e_two_plans_ms)
+        e2e_mode = ("streaming, two plans in flight: requests alternate between two plans on their own streams (each plan's sweep kernels take half "
+                    "the SMs); the D2H copy of a request (copy stream, pinned) overlaps the H2D + kernels of the following ones; host wall clock over the timed steps"
+                    if e2e_two_plans_ms < e2e_one_plan_ms else
+                    "streaming: host wall clock over the timed steps; the D2H copy of step i (copy stream, pinned) overlaps the H2D + kernels of step i+1")
+        e2e = {"value": V / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 12 * T + 12 * NV, "d2h_bytes_per_step": 4 * V,
+               "mode": e2e_mode,
+               "one_plan_streaming_ms": e2e_one_plan_ms, "one_plan_streaming_value": V / (e2e_one_plan_ms * 1e-3) / 1e9,
+               "two_plans_streaming_ms": e2e_two_plans_ms, "two_plans_streaming_value": V / (e2e_two_plans_ms * 1e-3) / 1e9,
+               "blocking_call_ms": e2e_blocking_ms, "blocking_call_value": V / (e2e_blocking_ms * 1e-3) / 1e9}
+        concurrent = {"plans": 2, "ms_per_grid": two_plans_ms, "value": V / (two_plans_ms * 1e-3) / 1e9, "unit": UNIT,
+                      "note": "device-resident, two independent grids in flight on one GPU; `value` above is one grid at a time"}
     clocks = sampler.stop()
     inside = int((phi_pin < 0).sum())
     plan.close()
@@ -298,10 +355,8 @@ def run_single_gpu(args):
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak,
                      "path_algorithmic_bytes": path_bytes},
         "cpu_baseline": cpu,
-        "e2e": {"value": V / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": 12 * T + 12 * NV, "d2h_bytes_per_step": 4 * V,
-                "mode": "streaming: host wall clock over the timed steps; the D2H copy of step i (copy stream, pinned) overlaps the H2D + kernels of step i+1",
-                "blocking_call_ms": e2e_blocking_ms, "blocking_call_value": V / (e2e_blocking_ms * 1e-3) / 1e9},
+        "e2e": e2e,
+        "concurrent": concurrent,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -319,6 +374,7 @@ def main():
     ap.add_argument("--grid", type=int, default=None, help="override the grid edge (debug / down-scaled twin)")
     ap.add_argument("--schedule", default="default", choices=["default", "columns", "relax", "strips", "levels"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for the ncu launch list)")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "c2_icosphere_512"      # N > 1 uses meshes.stacked_workload(N): one C2 block per GPU

@@ -120,6 +120,12 @@ int sdfb_plan_create(sdfb_plan **plan, int device, int32_t ni, int32_t nj, int32
                      int32_t k_lo, int32_t k_hi, uint32_t flags);
 int sdfb_plan_destroy(sdfb_plan *plan);
 
+/* Tell the plan that `plans_in_flight` plans run on this device at the same time, each on its own stream: the
+ * persistent sweep kernels then take only their share of the SMs so that the plans' kernels overlap instead of
+ * queueing behind each other (the sweeps are latency-bound: two 512^3 grids in flight finish sooner than one after
+ * the other).  1 = the whole device (default).  Results do not depend on it. */
+int sdfb_plan_set_concurrency(sdfb_plan *plan, int32_t plans_in_flight);
+
 /* Mesh from host memory (copied, may be pageable) or already on the plan's device (borrowed until
  * the next set/destroy).  Builds the per-triangle records. `stream` is a cudaStream_t (NULL = default). */
 int sdfb_plan_set_mesh_host(sdfb_plan *plan, const uint32_t *tri, uint64_t ntri,

@@ -75,6 +75,8 @@ def lib():
     L.sdfb_plan_download.argtypes = [vp, vp, vp, vp, vp]
     L.sdfb_plan_download_phi_async.restype = C.c_int
     L.sdfb_plan_download_phi_async.argtypes = [vp, vp, vp]
+    L.sdfb_plan_set_concurrency.restype = C.c_int
+    L.sdfb_plan_set_concurrency.argtypes = [vp, i32]
     L.sdfb_trim_memory.restype = C.c_int
     L.sdfb_trim_memory.argtypes = []
     L.sdfb_make_level_set3_batch.restype = C.c_int
@@ -197,6 +199,10 @@ class Plan:
         """Enqueue the D2H copy of the last sign pass's phi on `copy_stream` (raw cudaStream_t, not the compute
         stream); phi_out is a pinned host address or array.  Synchronise that stream before reading."""
         check(lib().sdfb_plan_download_phi_async(self._h, _addr(phi_out), copy_stream or None))
+
+    def set_concurrency(self, plans_in_flight: int):
+        """This many plans run on the device at once (own streams): the sweep kernels take their share of the SMs."""
+        check(lib().sdfb_plan_set_concurrency(self._h, int(plans_in_flight)))
 
     def write_sdf(self, path, min_box, dx, stream=0) -> int:
         """Write the signed phi of the last sign pass as a binary .sdf file straight from the device

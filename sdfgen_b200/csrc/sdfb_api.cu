@@ -250,6 +250,10 @@ struct sdfb_plan {
 
 namespace {
 
+// cap on a persistent sweep grid when `plans` plans share the device: its share of the 3 CTAs an SM holds, but
+// never less than half a CTA per SM (more plans than that simply queue)
+int sm_share_ctas(int sms, int plans) { return (3 * sms) / plans > sms / 2 ? (3 * sms) / plans : sms / 2; }
+
 // nothing on the device may still use the plan's buffers when they go back to the pool
 void plan_quiesce(sdfb_plan *p)
 {
@@ -383,6 +387,16 @@ int sdfb_plan_destroy(sdfb_plan *p)
     if (p->ev_copy) cudaEventDestroy(p->ev_copy);
     delete p;
     cudaGetLastError();
+    return SDFB_OK;
+}
+
+int sdfb_plan_set_concurrency(sdfb_plan *p, int32_t plans_in_flight)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (plans_in_flight < 1) return fail(SDFB_ERR_INVALID, "plans_in_flight must be at least 1");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    p->max_ctas = plans_in_flight == 1 ? 0 : sm_share_ctas(sms, plans_in_flight);
     return SDFB_OK;
 }
 
@@ -721,7 +735,7 @@ int sdfb_make_level_set3_batch(sdfb_batch_item *items, int32_t n, int32_t concur
                 sdfb_plan_destroy(p); p = nullptr;
                 rc = sdfb_plan_create(&p, dev, it.ni, it.nj, it.nk, 0, it.nk, flags);
                 if (!rc) { p->own_stream = true; p->stream = st; }
-                if (!rc && W > 1) p->max_ctas = (3 * sms) / W > sms / 2 ? (3 * sms) / W : sms / 2;
+                if (!rc && W > 1) p->max_ctas = sm_share_ctas(sms, W);
             }
             if (!rc) rc = sdfb_plan_set_mesh_host(p, it.tri, it.ntri, it.xyz, it.nvert, st);
             if (!rc) rc = sdfb_plan_run(p, it.origin, it.dx, it.exact_band, st);

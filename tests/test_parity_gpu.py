@@ -127,6 +127,29 @@ def test_batch_call_equals_one_call_per_item(golden_dir):
     assert _same(outs[1][2], want[1])
 
 
+def test_plans_in_flight_share_the_device():
+    """sdfb_plan_set_concurrency: three plans on their own streams, sweep grids capped to a third of the SMs each,
+    enqueued without any synchronisation in between; every result equals the oracle's."""
+    import torch
+    cases = [("c1_blob_256", 72), ("c2_icosphere_512", 64), ("c3_torus_1024", 56)]
+    ws = [meshes.workload(name, n=n, shuffle=True) for name, n in cases]
+    plans = [_lib.Plan(n, n, n) for _, n in cases]
+    streams = [torch.cuda.Stream() for _ in cases]
+    for rep in range(3):
+        for w, p, s in zip(ws, plans, streams):
+            p.set_concurrency(3)
+            p.set_mesh_host(w["vertices"], w["triangles"], stream=s.cuda_stream)
+            p.run(w["origin"], w["dx"], 1, stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    for (name, n), w, p in zip(cases, ws, plans):
+        r = oracle.best().staged(w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+        phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
+        assert _same(phi, r.phi) and _same(tri, r.tri_final) and _same(cnt, r.counts), name
+        with pytest.raises(ValueError):
+            p.set_concurrency(0)
+        p.close()
+
+
 def test_sdf_file_written_from_the_device(golden_dir, tmp_path):
     """sdfb_plan_write_sdf: (1) the reference CLI's known-answer file for its own test mesh, byte for byte (sha256) and
     inside count; (2) on ragged grids, with and without the plan's own k-fastest copy, the bytes equal the numpy writer's

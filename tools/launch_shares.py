@@ -15,7 +15,7 @@ for r in rows:
     if name not in agg: agg[name] = [0, 0.0]; order.append(name)
     agg[name][0] += 1; agg[name][1] += t
 tot = sum(v[1] for v in agg.values())
-print(f"# ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (last step, {per_step} launches)")
+print(f"# ncu launch list of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e` (last step, {per_step} launches)")
 print("# gpu__time_duration.sum per launch, --clock-control none; times are serialised/cold-cache: compare SHARES\n")
 for n in sorted(order, key=lambda k: -agg[k][1]):
     print(f"{n:24s} launches {agg[n][0]:3d}  total {agg[n][1]:9.3f} ms  share {100*agg[n][1]/tot:5.1f}%")

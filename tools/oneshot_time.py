@@ -7,7 +7,7 @@ import sdfgen_b200
 from sdfgen_b200 import meshes
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_icosphere_512"
 w = meshes.workload(name)
-for rep in range(4):
+for rep in range(8):
     t0 = time.perf_counter()
     sdf = sdfgen_b200.generate_sdf(w["vertices"], w["triangles"], tuple(w["origin"]), w["dx"], w["ni"], w["nj"], w["nk"])
     dt = time.perf_counter() - t0
