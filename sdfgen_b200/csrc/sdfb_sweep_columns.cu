@@ -55,7 +55,27 @@ constexpr int EJ = SDFB_EJ, EK = SDFB_EK;    // column extent (rows x planes)
 constexpr int NCOMPUTE = EJ * EK;            // compute lanes (16 x 16: 8 warps)
 constexpr int NHALO = (EJ + EK + 1 + 31) / 32 * 32;   // halo lanes, whole warps
 constexpr int NSTEPPERS = NCOMPUTE + NHALO;  // lanes that take part in the per-step barrier
-constexpr int NTHREADS = NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
+// SDFB_WG: warpgroup register split.  The CTA is padded to two warpgroups (compute warps | halo, sync and two idle
+// warps) and compiled for 64 registers per thread, so that four CTAs fit an SM; the compute warpgroup then takes
+// the registers the other one gives up (setmaxnreg is a warpgroup-wide operation).  The halo warp does not
+// evaluate in this layout.
+#ifndef SDFB_WG
+#define SDFB_WG 0
+#endif
+#ifndef SDFB_WG_COMPUTE_REGS
+#define SDFB_WG_COMPUTE_REGS 96
+#endif
+#ifndef SDFB_WG_LIGHT_REGS
+#define SDFB_WG_LIGHT_REGS 32
+#endif
+#ifndef SDFB_WG_HALO_EVAL
+#define SDFB_WG_HALO_EVAL 0
+#endif
+constexpr bool WG = SDFB_WG != 0;
+constexpr bool HALO_EVAL = !WG || SDFB_WG_HALO_EVAL != 0;   // the halo warp takes a share of the evaluations
+static_assert(!WG || NCOMPUTE == 128, "the warpgroup layout needs exactly four compute warps");
+constexpr int NTHREADS = WG ? 256 : NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
+constexpr int EVAL_LANES = HALO_EVAL ? NSTEPPERS : NCOMPUTE;   // lanes that share the column-wide evaluation queue
 #ifndef SDFB_SYNC_SLEEP
 #define SDFB_SYNC_SLEEP 150
 #endif
@@ -131,14 +151,14 @@ struct ColShared {
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
 };
 
-// Evaluation share of one lane in the column-wide queue: entries first, first+NSTEPPERS, ...
+// Evaluation share of one lane in the column-wide queue: entries first, first+EVAL_LANES, ...
 __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restrict__ rec, ColShared &sh, int first, int total)
 {
     uint32_t *const q_ent = &sh.q_ent[0][0];
     float *const q_d = &sh.q_d[0][0];
     unsigned evals = 0;
     int q = first;
-    for (; q < total; q += NSTEPPERS) {
+    for (; q < total; q += EVAL_LANES) {
         const int ot = __float_as_int(q_d[q]);                         // owner lane, replaced by the distance
         const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
         const TriRec *tr = &rec[q_ent[q]];
@@ -159,7 +179,7 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
     for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
     if (total == 0) return 0u;
     bar_compute();
-    const unsigned e = evaluate_queue_share(rec, sh, NCOMPUTE + h, total);
+    const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, NCOMPUTE + h, total) : 0u;
     bar_compute();
     return e;
 }
@@ -562,21 +582,18 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
 // MINB = CTAs per SM the register allocation is bounded for.  3 (93 registers, no spills) is slightly faster where the
 // wavefront is narrow and the kernel latency-bound (512^3: 60.5 vs 61.4 ms for the first pass); 4 (80 registers, a few
 // spills) wins where there is enough work to be throughput-bound (1024^3: 240 vs 263 ms).
-template <bool CTA_QUEUE, int MINB>
-__global__ void __launch_bounds__(NTHREADS, MINB)
-k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
-                uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
-                unsigned long long *__restrict__ changed)
+// The column loop of one CTA.  GROUP selects the roles compiled in: -1 = all (one register budget for the whole CTA),
+// 0 = the compute warps, 1 = the halo, sync and idle warps (SDFB_WG: each warpgroup runs its own copy of the loop in
+// the branch its setmaxnreg dominates, which is what makes ptxas allocate registers per role).  Every thread of the
+// CTA passes the same two __syncthreads() per column whichever copy it runs.
+template <bool CTA_QUEUE, int GROUP>
+__device__ __forceinline__ void column_loop(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, const ColParams &P,
+                                            ColShared &sh, uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
+                                            int tid, int lane, int ncols, unsigned &my_changed, unsigned &my_evals)
 {
-    __shared__ ColShared sh;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int ncols = P.NJ * P.NK;
-    unsigned my_changed = 0, my_evals = 0;
-    if (P.run_if && __ldcg(P.run_if) == 0u) return;                   // uniform over the grid; the ticket is untouched
-
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
-        if (tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; }
+        if (GROUP != 1 && tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; }
         __syncthreads();
         const int tk = sh.col;
         if (tk >= ncols) break;
@@ -591,16 +608,40 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
             }
         }
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
-        if (tid < NCOMPUTE) {
+        if (GROUP != 1 && tid < NCOMPUTE) {
             compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
-        } else if (tid < NSTEPPERS) {
+        } else if (GROUP != 0 && tid >= NCOMPUTE && tid < NSTEPPERS) {
             halo_column<CTA_QUEUE>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
-        } else {
+        } else if (GROUP != 0 && tid >= NSTEPPERS && tid < NSTEPPERS + 32) {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
             sync_column(P, sh, lane, prog_left, prog_down, &progress[K * P.NJ + J]);
         }
         __syncthreads();        // sh.col is rewritten next; also orders the two roles' exits
+    }
+}
+
+template <bool CTA_QUEUE, int MINB>
+__global__ void __launch_bounds__(NTHREADS, WG ? 4 : MINB)
+k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
+                uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
+                unsigned long long *__restrict__ changed)
+{
+    __shared__ ColShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ncols = P.NJ * P.NK;
+    unsigned my_changed = 0, my_evals = 0;
+    if (P.run_if && __ldcg(P.run_if) == 0u) return;                   // uniform over the grid; the ticket is untouched
+    if (WG) {
+        if (tid < NCOMPUTE) {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(SDFB_WG_COMPUTE_REGS));
+            column_loop<CTA_QUEUE, 0>(cells, rec, P, sh, progress, ticket, tid, lane, ncols, my_changed, my_evals);
+        } else {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SDFB_WG_LIGHT_REGS));
+            column_loop<CTA_QUEUE, 1>(cells, rec, P, sh, progress, ticket, tid, lane, ncols, my_changed, my_evals);
+        }
+    } else {
+        column_loop<CTA_QUEUE, -1>(cells, rec, P, sh, progress, ticket, tid, lane, ncols, my_changed, my_evals);
     }
 
     // ---- teardown: count changes; the last CTA out resets the ticket for the next launch ----------

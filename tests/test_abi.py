@@ -77,3 +77,25 @@ def test_c_abi_argument_checks_without_device():
     assert L.sdfb_plan_destroy(None) == 0
     assert L.sdfb_plan_band(None, None, 1.0, 1, None) == _lib.ERR_INVALID
     assert L.sdfb_make_level_set3(None, 0, None, 0, None, 1.0, 4, 4, 4, 1, None, None, None, 0) == _lib.ERR_INVALID
+    # entry points added for SURVEY 8(f): writer, batch, concurrency, memory pool
+    assert L.sdfb_plan_write_sdf(None, b"/tmp/x.sdf", None, 1.0, None, None) == _lib.ERR_INVALID
+    assert L.sdfb_plan_set_concurrency(None, 2) == _lib.ERR_INVALID
+    assert L.sdfb_make_level_set3_batch(None, 1, 4, 0) == _lib.ERR_INVALID
+    assert L.sdfb_make_level_set3_batch(None, -1, 4, 0) == _lib.ERR_INVALID
+    assert L.sdfb_make_level_set3_batch(None, 0, 4, 0) == 0            # an empty batch is not an error
+    assert L.sdfb_trim_memory() == 0                                   # nothing retained yet
+
+
+def test_batch_item_layout_matches_the_header():
+    """sdfb_batch_item as ctypes sees it = as the C compiler lays it out (offsets from include/sdfb.h compiled with gcc)."""
+    import subprocess, tempfile, os
+    fields = ["tri", "ntri", "xyz", "nvert", "origin", "dx", "ni", "nj", "nk", "exact_band", "phi_out", "status"]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "sdfb.h"\nint main(void){printf("%zu", sizeof(sdfb_batch_item));' + \
+          "".join(f'printf(" %zu", offsetof(sdfb_batch_item, {f}));' for f in fields) + "return 0;}\n"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", inc, "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert out[0] == ctypes.sizeof(_lib.BatchItem)
+    assert out[1:] == [getattr(_lib.BatchItem, f).offset for f in fields]
