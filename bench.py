@@ -373,6 +373,8 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--grid", type=int, default=None, help="override the grid edge (debug / down-scaled twin)")
     ap.add_argument("--schedule", default="default", choices=["default", "columns", "relax", "strips", "levels"])
+    ap.add_argument("--exact", action="store_true",
+                    help="N > 1: also time the exact multi-GPU mode (serial sweep order kept across slabs, dist.run_sharded_exact)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for the ncu launch list)")
     args = ap.parse_args()

@@ -101,6 +101,10 @@ class CudaSlabEngine:
     def halo_refresh(self):
         self.plan.halo_refresh(stream=self.sh)
 
+    def halo_commit(self, lower):
+        """Exact mode: the received plane already sits in the cell array (halo_planes() are views of it) and keeps
+        its stamps; nothing to do on the device."""
+
     def counter_tensor(self, value):
         return self.torch.tensor([value], dtype=self.torch.int64, device=self.device)
 
@@ -149,6 +153,69 @@ def run_sharded(engine, rank, world, origin, dx, exact_band=1, min_passes=2, max
     return stats
 
 
+# ---- exact mode: the serial Gauss-Seidel order kept across slab faces -------------------------------
+
+# k direction of the 8 sweeps of a pass, cpu_lib/makelevelset3.cpp:245-248: +++ --- ++- --+ +-+ -+- +-- -++
+SWEEP_DK = (+1, -1, -1, +1, +1, -1, -1, +1)
+
+
+def run_sharded_exact(engine, rank, world, origin, dx, exact_band=1, passes=2, group=None) -> ShardStats:
+    """Phases A, B, C on one rank's slab with the sweeps in the reference's serial order ACROSS slabs: bit-identical
+    to the single-device result ("exact").
+
+    A sweep only reads cells upstream in k (cpu_lib/makelevelset3.cpp:143-149: offsets 0 or -dk), so slab r may run
+    sweep s as soon as the slab behind it (rank r - dk) has finished sweep s and handed over its boundary plane; the
+    other halo plane is not read by that sweep.  Every rank therefore runs
+
+        for s in 0..15:  recv upstream plane (if any)  ->  sweep s  ->  send own boundary plane downstream (if any)
+
+    which is a dataflow schedule: the send/recv pairs are stream-ordered (NCCL) and the chain of ranks has no cycle,
+    so nothing else synchronises.  Consecutive sweeps with the same dk (1-2, 3-4, 5-6, 7-8, ...) pipeline through the
+    slabs, sweeps with opposite dk turn around at the last slab; 2 sweeps cost world + 1 slab-sweep times instead of
+    2, i.e. the parallel efficiency is 2 / (world + 1).  The received cells keep their stamps (no halo_refresh): they
+    are exactly the cells a single grid would hold at that moment, so the sweep's memo makes the same decisions.
+    This mode buys the exact result for grids that need several GPUs' memory; `run_sharded` buys throughput."""
+    import torch.distributed as dist
+    stats = ShardStats()
+    engine.band(origin, dx, exact_band)
+    for s in range(8 * passes):
+        dk = SWEEP_DK[s % 8]
+        up, down = rank - dk, rank + dk
+        if 0 <= up < world:
+            lo_recv, hi_recv = engine.halo_planes()
+            dist.recv(lo_recv if dk > 0 else hi_recv, src=up, group=group)
+            engine.halo_commit(lower=dk > 0)
+        engine.sweep(s, 1)
+        if 0 <= down < world:
+            lo_send, hi_send = engine.boundary_planes()
+            dist.send(hi_send if dk > 0 else lo_send, dst=down, group=group)
+    stats.passes = passes
+    engine.sign()
+    return stats
+
+
+def run_slabs_exact_local(engines, origin, dx, exact_band=1, passes=2):
+    """The same dependency order for slabs that live in ONE process (several plans on one device): slabs are
+    visited upstream to downstream within each sweep and the boundary plane is copied instead of sent.  Used by the
+    single-GPU tests of the exact mode; `engines` are ordered by k_lo."""
+    for e in engines:
+        e.band(origin, dx, exact_band)
+    n = len(engines)
+    for s in range(8 * passes):
+        dk = SWEEP_DK[s % 8]
+        order = range(n) if dk > 0 else range(n - 1, -1, -1)
+        for r in order:
+            up = r - dk
+            if 0 <= up < n:
+                lo_send, hi_send = engines[up].boundary_planes()
+                lo_recv, hi_recv = engines[r].halo_planes()
+                (lo_recv if dk > 0 else hi_recv).copy_(hi_send if dk > 0 else lo_send)
+                engines[r].halo_commit(lower=dk > 0)
+            engines[r].sweep(s, 1)
+    for e in engines:
+        e.sign()
+
+
 # ---- bench.py --gpus N (N > 1) ---------------------------------------------------------------------
 
 def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
@@ -178,6 +245,10 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
     phi_pins = [torch.empty(Vloc, dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     counter = [0]
+
+    def step_exact():
+        with torch.cuda.stream(stream):
+            return run_sharded_exact(eng, rank, world, w["origin"], w["dx"], 1)
 
     def step(e2e):
         # e2e: every step uploads the mesh from pinned host memory and downloads this rank's slab of phi; the download
@@ -219,6 +290,22 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
 
     dev_ms, st, launches = timed(False)
     e2e_ms, _, _ = timed(True)
+    exact = None
+    if getattr(args, "exact", False):
+        step_exact()                                         # warm-up: first send/recv between neighbours
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_exact()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exact = {"ms_per_step": float(t.item()), "value": ni * nj * nk / (float(t.item()) * 1e-3) / 1e9, "unit": UNIT,
+                 "note": "run_sharded_exact: 16 sweeps in the serial order across slabs, bit-identical to one grid; "
+                         "device-resident, max over ranks"}
     clocks = sampler.stop() if sampler else None
     eng.close()
     V = ni * nj * nk
@@ -243,6 +330,8 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
                     "mode": "streaming: host wall clock; each rank's D2H copy of step i overlaps step i+1"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if exact:
+            line["exact_mode"] = exact
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

@@ -28,6 +28,11 @@ def main():
     phi, tri, cnt = eng.plan.download(phi=True, tri=True, counts=True, stream=eng.sh)
     parts = [None] * world
     dist.gather_object((k_lo, k_hi, phi, tri, cnt), parts if rank == 0 else None, dst=0)
+    # exact mode on the same engine: serial sweep order kept across the slab faces (must be bit-identical to one GPU)
+    sdist.run_sharded_exact(eng, rank, world, w["origin"], w["dx"], 1)
+    phi_x, tri_x, _ = eng.plan.download(phi=True, tri=True, stream=eng.sh)
+    parts_x = [None] * world
+    dist.gather_object((phi_x, tri_x), parts_x if rank == 0 else None, dst=0)
     if rank == 0:
         phi = np.concatenate([p[2] for p in parts]); tri = np.concatenate([p[3] for p in parts]); cnt = np.concatenate([p[4] for p in parts])
         one = _lib.Plan(ni, nj, nk, device=local)
@@ -39,6 +44,9 @@ def main():
                    counts_equal=bool(np.array_equal(cnt, cnt1)), signs_equal=bool(np.array_equal(np.signbit(phi), np.signbit(phi1))),
                    frac_phi_differs=float((diff > 1e-5).mean()), max_dphi_over_dx=float(diff.max()),
                    frac_tri_differs=float((tri != tri1).mean()))
+        phi_x = np.concatenate([p[0] for p in parts_x]); tri_x = np.concatenate([p[1] for p in parts_x])
+        out["exact_mode_phi_equal"] = bool(np.array_equal(phi_x.view(np.uint32), phi1.view(np.uint32)))
+        out["exact_mode_tri_equal"] = bool(np.array_equal(tri_x, tri1))
         print("DIST_RESULT " + json.dumps(out))
     dist.barrier()
     eng.close()

@@ -72,6 +72,14 @@ class OracleSlabEngine:
             self.cphi[sl] = ((x >> 32) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
             self.clo[sl] = lo
 
+    def halo_commit(self, lower):
+        """Exact mode: unpack one received plane as it is (stamps kept)."""
+        p = self.plane
+        key, sl = ("lo_r", slice(0, p)) if lower else ("hi_r", slice((self.nkl + 1) * p, (self.nkl + 2) * p))
+        x = self.stage[key].numpy()
+        self.cphi[sl] = ((x >> 32) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+        self.clo[sl] = (x & 0xFFFFFFFF).astype(np.uint32)
+
     def counter_tensor(self, value):
         return torch.tensor([value], dtype=torch.int64)
 

@@ -88,3 +88,57 @@ def test_run_sharded_gloo(tmp_path, world):
             gx = np.array([i, j, k], np.float32) * np.float32(w["dx"]) + w["origin"]
             d = oracle.port.point_triangle_distance(gx, *v[t[tri[c]]])
             assert np.float32(d).view(np.uint32) == np.abs(phi[c]).view(np.uint32)
+
+
+# ---- exact mode (serial order kept across slab faces) -------------------------------------------------
+
+def _worker_exact(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    from fake_engine import OracleSlabEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = _case()
+    k_lo, k_hi = sdist.slab_bounds(w["nk"], world, rank)
+    eng = OracleSlabEngine(w["vertices"], w["triangles"], w["ni"], w["nj"], w["nk"], k_lo, k_hi)
+    st = sdist.run_sharded_exact(eng, rank, world, w["origin"], w["dx"], 1)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), phi=eng.phi, tri=eng.tri(), counts=eng.counts, passes=st.passes)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_run_sharded_exact_gloo_is_bit_identical_to_one_grid(tmp_path, world):
+    """Dataflow order recv upstream plane -> sweep -> send downstream: every slab's result equals the single-grid
+    serial oracle bit for bit (phi, closest_tri, counts), with exactly the reference's 16 sweeps."""
+    port = 29700 + world + (os.getpid() % 1000)
+    mp.spawn(_worker_exact, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    w = _case()
+    full = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], w["ni"], w["nj"], w["nk"])
+    parts = [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
+    phi = np.concatenate([p["phi"] for p in parts])
+    tri = np.concatenate([p["tri"] for p in parts])
+    cnt = np.concatenate([p["counts"] for p in parts])
+    assert all(int(p["passes"]) == 2 for p in parts)
+    assert np.array_equal(cnt, full.counts)
+    assert np.array_equal(tri, full.tri_final)
+    assert np.array_equal(phi.view(np.uint32), full.phi.view(np.uint32))
+
+
+@pytest.mark.parametrize("bounds", [[(0, 20), (20, 40)], [(0, 1), (1, 4), (4, 23), (23, 40)]])
+def test_exact_order_in_one_process_is_bit_identical_to_one_grid(bounds):
+    """run_slabs_exact_local (slabs visited upstream to downstream inside each sweep), incl. one-plane and thin slabs."""
+    sys.path.insert(0, HERE)
+    from fake_engine import OracleSlabEngine
+    w = _case()
+    assert bounds[-1][1] == w["nk"]
+    engs = [OracleSlabEngine(w["vertices"], w["triangles"], w["ni"], w["nj"], w["nk"], lo, hi) for lo, hi in bounds]
+    sdist.run_slabs_exact_local(engs, w["origin"], w["dx"], 1)
+    full = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], w["ni"], w["nj"], w["nk"])
+    assert np.array_equal(np.concatenate([e.tri() for e in engs]), full.tri_final)
+    assert np.array_equal(np.concatenate([e.phi for e in engs]).view(np.uint32), full.phi.view(np.uint32))
+
+
+def test_sweep_dk_table_matches_the_reference_order():
+    # cpu_lib/makelevelset3.cpp:245-248
+    dirs = [(+1, +1, +1), (-1, -1, -1), (+1, +1, -1), (-1, -1, +1), (+1, -1, +1), (-1, +1, -1), (+1, -1, -1), (-1, +1, +1)]
+    assert sdist.SWEEP_DK == tuple(d[2] for d in dirs)

@@ -29,3 +29,5 @@ def test_two_gpu_slabs_match_single_gpu(n, level):
     # phases A and C shard exactly; swept phi may differ where information crosses the slab face (reported)
     assert out["counts_equal"] and out["signs_equal"]
     assert out["max_dphi_over_dx"] < 0.5 and out["frac_phi_differs"] < 0.05
+    # the exact mode (dist.run_sharded_exact) is bit-identical to the single-GPU result
+    assert out["exact_mode_phi_equal"] and out["exact_mode_tri_equal"]

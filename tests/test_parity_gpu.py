@@ -352,6 +352,34 @@ def _drive_slabs(w, bounds):
         g.close()
 
 
+@pytest.mark.parametrize("sched,flags", [("default", 0), ("columns", _lib.SWEEP_COLUMNS), ("relax", _lib.SWEEP_RELAX)])
+def test_exact_slab_order_on_one_gpu_equals_one_plan(sched, flags):
+    """Exact multi-slab mode (sdfgen_b200.dist.run_slabs_exact_local, the in-process twin of run_sharded_exact): slab
+    plans swept upstream to downstream inside each of the 16 sweeps, boundary planes handed over with their stamps.
+    The concatenated slabs must equal ONE plan on the whole grid and the serial oracle bit for bit (phi, closest_tri,
+    counts), also with a one-plane slab and a slab thinner than a wavefront column."""
+    from sdfgen_b200 import dist as sdist
+    w = meshes.stacked_workload(2, n=40, level=4)
+    ni, nj, nk = w["ni"], w["nj"], w["nk"]
+    full = _staged_gpu(dict(w, band=1), flags=flags)
+    r = oracle.best().staged(w["vertices"], w["triangles"], w["origin"], w["dx"], ni, nj, nk)
+    assert _same(full["phi"], r.phi) and _same(full["tri_final"], r.tri_final)
+    for bounds in ([sdist.slab_bounds(nk, 2, q) for q in range(2)], [(0, 1), (1, 4), (4, 47), (47, nk)]):
+        engs = [sdist.CudaSlabEngine(ni, nj, nk, lo, hi, 0, flags=flags) for lo, hi in bounds]
+        for e in engs:
+            e.set_mesh(w["vertices"], w["triangles"])
+        sdist.run_slabs_exact_local(engs, w["origin"], w["dx"], 1)
+        out = [e.plan.download(phi=True, tri=True, counts=True) for e in engs]
+        for e in engs:
+            e.close()
+        phi = np.concatenate([np.asarray(o[0]).ravel() for o in out])
+        tri = np.concatenate([np.asarray(o[1]).ravel() for o in out])
+        cnt = np.concatenate([np.asarray(o[2]).ravel() for o in out])
+        assert _same(cnt, r.counts), (sched, bounds)
+        assert _same(tri, r.tri_final), (sched, bounds, int((tri != r.tri_final).sum()))
+        assert _same(phi, r.phi), (sched, bounds)
+
+
 def test_edge_shapes_and_reuse():
     """Plan reuse across meshes/origins, exact_band 0, thin grids; each against the live oracle."""
     v, t = meshes.icosphere(2, 0.3)
