@@ -88,3 +88,13 @@ def test_generate_from_mesh_sizing(monkeypatch):
     assert np.allclose(seen["origin"], (-0.25, -0.25, -0.25)) and set(meta) == {"origin", "dx", "bounds", "backend"}
     sdf, meta = sdfgen_b200.generate_from_mesh(v, t, nx=8, ny=8, nz=8, padding=1)
     assert seen["dims"] == (10, 10, 10) and abs(seen["dx"] - 0.25) < 1e-7
+
+
+def test_repository_name_alias_is_the_same_package():
+    """`sdfgenfast_b200` (the repository's name) resolves to the very same module objects as `sdfgen_b200`."""
+    import sdfgenfast_b200
+    import sdfgenfast_b200.dist as d
+    from sdfgen_b200 import dist
+    assert d is dist and sdfgenfast_b200._lib is sdfgen_b200._lib
+    for name in ("generate_sdf", "generate_from_file", "generate_from_mesh", "is_gpu_available", "Plan"):
+        assert getattr(sdfgenfast_b200, name) is getattr(sdfgen_b200, name)
