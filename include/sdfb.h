@@ -149,7 +149,11 @@ int sdfb_plan_run(sdfb_plan *plan, const float origin[3], float dx, int32_t exac
 int sdfb_plan_device_ptrs(sdfb_plan *plan, void **cells, void **counts, void **phi);
 /* Multi-GPU: call after new contents were written into the two halo planes (plane 0 and plane
  * k_hi-k_lo+1 of `cells`) and before the next sdfb_plan_sweep.  Marks the received cells as freshly
- * changed so the sweep re-examines them (their previous copy may have been stale). Asynchronous. */
+ * changed so the sweep re-examines them (their previous copy may have been stale). Asynchronous.
+ * NOT used in the exact multi-slab order: there the caller writes, before sweep s, only the halo plane on the
+ * upstream side of that sweep (k direction + - - + + - - +, cpu_lib/makelevelset3.cpp:245-248) with the neighbour's
+ * boundary plane as it is AFTER the neighbour's sweep s, stamps untouched, and calls sdfb_plan_sweep(plan, s, 1);
+ * the slabs then hold exactly the cells of one whole grid (sdfgen_b200/dist.py: run_sharded_exact). */
 int sdfb_plan_halo_refresh(sdfb_plan *plan, void *stream);
 /* Number of cells whose closest triangle changed during the sweeps since the last sdfb_plan_band or
  * sdfb_plan_changed call (synchronises the stream; used by the multi-GPU fixed-point loop). */

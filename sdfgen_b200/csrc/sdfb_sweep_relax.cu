@@ -448,8 +448,10 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             // such sweeps take seconds).  Put the cells back as they were before
             // the sweep (changed cells carry this sweep's stamp and their old value is in oldbuf), empty both
             // bitmaps and raise the flag that lets the conditional column launch queued behind this one run. -----
-            const int64_t ncell = g.cell_count(), gt = (int64_t)blockIdx.x * RX_THREADS + tid, nt = (int64_t)gridDim.x * RX_THREADS;
-            for (int64_t c = gt; c < ncell; c += nt) {
+            // Owned planes only: in the exact multi-GPU mode a halo cell may carry this sweep's stamp too (the upstream
+            // slab changed it in this very sweep) and has no oldbuf entry here.
+            const int64_t c_end = g.plane() * (g.nkl() + 1), gt = (int64_t)blockIdx.x * RX_THREADS + tid, nt = (int64_t)gridDim.x * RX_THREADS;
+            for (int64_t c = g.plane() + gt; c < c_end; c += nt) {
                 const uint64_t x = ld_cg64(P.cells + c);
                 if (lo_stamp(cell_lo(x)) == P.stamp) P.cells[c] = ld_cg64(P.oldbuf + c);
             }
