@@ -287,12 +287,23 @@ int ensure_mesh_capacity(sdfb_plan *p, uint64_t ntri)
     return SDFB_OK;
 }
 
+// The mesh named a vertex that does not exist.  The reference indexes x[] unchecked there (undefined behaviour,
+// cpu_lib/makelevelset3.cpp:205; python/tests/test_sdfgen.py:826-847 accepts a crash or an exception); the device
+// replaced the index by 0 instead of faulting, and the calls that deliver results refuse to.
+int bad_index_error(const sdfb_plan *p, unsigned long long t)
+{
+    return fail(SDFB_ERR_INVALID, "triangle %llu names a vertex index >= %llu (the vertex count); no result delivered",
+                t, (unsigned long long)p->nvert);
+}
+
 int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint64_t ntri, uint64_t nvert, cudaStream_t st)
 {
     if (ntri > SDFB_MAX_TRIANGLES) return fail(SDFB_ERR_LIMIT, "%llu triangles exceed the limit of %u", (unsigned long long)ntri, SDFB_MAX_TRIANGLES);
     int rc = ensure_mesh_capacity(p, ntri);
     if (rc) return rc;
-    g_launches += launch_tri_prep(d_tri, d_xyz, ntri, p->rec, st);
+    if (ntri && !nvert) return fail(SDFB_ERR_INVALID, "%llu triangles but no vertices", (unsigned long long)ntri);
+    CU(cudaMemsetAsync(p->changed + 3, 0xff, sizeof(unsigned long long), st));     // lowest triangle with a bad vertex index
+    g_launches += launch_tri_prep(d_tri, d_xyz, ntri, nvert, p->rec, p->changed + 3, st);
     CU(cudaGetLastError());
     // (An L2 persistence window over the records was measured: no effect at C2, and cudaDeviceSetLimit is a
     // device-wide, synchronising setting a library should not touch -- removed.)
@@ -354,7 +365,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
         (e = dev_alloc(&p->counts, V * sizeof(int32_t))) != cudaSuccess ||
         (e = dev_alloc(&p->phi, V * sizeof(float))) != cudaSuccess ||
         ((flags & SDFB_OUT_KFASTEST) && (e = dev_alloc(&p->phi_k, V * sizeof(float))) != cudaSuccess) ||
-        (e = dev_alloc(&p->changed, 3 * sizeof(unsigned long long))) != cudaSuccess) {   // changed, evaluations, inside count
+        (e = dev_alloc(&p->changed, 4 * sizeof(unsigned long long))) != cudaSuccess) {   // changed, evaluations, inside count, bad triangle
         sdfb_plan_destroy(p);
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
@@ -371,6 +382,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     }
     if ((e = cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming)) != cudaSuccess) { sdfb_plan_destroy(p); return fail(SDFB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
     cudaMemset(p->changed, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(p->changed + 3, 0xff, sizeof(unsigned long long));
     *out = p;
     return SDFB_OK;
 }
@@ -602,7 +614,10 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
         }
     }
     CU(cudaGetLastError());
+    unsigned long long bad = ~0ull;
+    CU(cudaMemcpyAsync(&bad, p->changed + 3, sizeof(bad), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (bad != ~0ull) return bad_index_error(p, bad);
     return SDFB_OK;
 }
 
@@ -656,10 +671,11 @@ int sdfb_plan_write_sdf(sdfb_plan *p, const char *path, const float min_box[3], 
     if (fclose(f) != 0) ok = false;
     if (e != cudaSuccess) return fail(SDFB_ERR_CUDA, "copying phi to the host failed: %s", cudaGetErrorString(e));
     if (!ok) return fail(SDFB_ERR_IO, "Failed to write SDF data to file: %s", path);
-    unsigned long long inside = 0;
-    CU(cudaMemcpyAsync(&inside, p->changed + 2, sizeof(inside), cudaMemcpyDeviceToHost, st));
+    unsigned long long tail[2] = {0, ~0ull};                         // inside count, lowest triangle with a bad vertex index
+    CU(cudaMemcpyAsync(tail, p->changed + 2, sizeof(tail), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (inside_count_out) *inside_count_out = (int64_t)inside;
+    if (inside_count_out) *inside_count_out = (int64_t)tail[0];
+    if (tail[1] != ~0ull) return bad_index_error(p, tail[1]);
     return SDFB_OK;
 }
 

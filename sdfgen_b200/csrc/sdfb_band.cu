@@ -37,12 +37,22 @@ __global__ void k_init_cells(uint64_t *cells, int64_t n, uint64_t init_cell)
 }
 
 // gather the three vertices of each triangle into its 48-byte record
-__global__ void k_tri_prep(const uint32_t *__restrict__ tri, const float *__restrict__ xyz, uint64_t ntri,
-                           TriRec *__restrict__ rec)
+// A vertex index >= nvert is undefined behaviour in the reference (it indexes x[] unchecked,
+// cpu_lib/makelevelset3.cpp:205); here it must not become an illegal address that kills the CUDA context: the
+// lowest offending triangle id is recorded in *bad (atomicMin, initialised to ~0) and the index is replaced by 0;
+// the blocking calls that hand results to the host report SDFB_ERR_INVALID.
+__global__ void k_tri_prep(const uint32_t *__restrict__ tri, const float *__restrict__ xyz, uint64_t ntri, uint64_t nvert,
+                           TriRec *__restrict__ rec, unsigned long long *__restrict__ bad)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntri) return;
     uint32_t p = tri[3 * t], q = tri[3 * t + 1], r = tri[3 * t + 2];
+    if (p >= nvert || q >= nvert || r >= nvert) {
+        atomicMin(bad, (unsigned long long)t);
+        if (p >= nvert) p = 0;
+        if (q >= nvert) q = 0;
+        if (r >= nvert) r = 0;
+    }
     rec[t] = make_tri_rec(F3{xyz[3 * (size_t)p], xyz[3 * (size_t)p + 1], xyz[3 * (size_t)p + 2]},
                           F3{xyz[3 * (size_t)q], xyz[3 * (size_t)q + 1], xyz[3 * (size_t)q + 2]},
                           F3{xyz[3 * (size_t)r], xyz[3 * (size_t)r + 1], xyz[3 * (size_t)r + 2]});
@@ -282,10 +292,11 @@ int launch_init(uint64_t *cells, int64_t ncells, float init_phi, cudaStream_t st
     return 1;
 }
 
-int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, TriRec *rec, cudaStream_t st)
+int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, uint64_t nvert, TriRec *rec,
+                    unsigned long long *bad, cudaStream_t st)
 {
     if (ntri == 0) return 0;
-    k_tri_prep<<<(unsigned)((ntri + 255) / 256), 256, 0, st>>>(tri, xyz, ntri, rec);
+    k_tri_prep<<<(unsigned)((ntri + 255) / 256), 256, 0, st>>>(tri, xyz, ntri, nvert, rec, bad);
     return 1;
 }
 

@@ -32,7 +32,8 @@ struct Launches { uint64_t n = 0; };
 
 // all launchers enqueue on `st` and return the number of kernels launched
 int launch_init(uint64_t *cells, int64_t ncells, float init_phi, cudaStream_t st);
-int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, TriRec *rec, cudaStream_t st);
+int launch_tri_prep(const uint32_t *tri, const float *xyz, uint64_t ntri, uint64_t nvert, TriRec *rec,
+                    unsigned long long *bad, cudaStream_t st);
 int launch_band(const TriRec *rec, uint64_t ntri, const Grid &g, uint32_t *units, TriExt *ext, uint64_t *prefix,
                 uint64_t *block_sums, uint64_t *cells, int32_t *counts, float init_phi, cudaStream_t st);
 int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,

@@ -83,6 +83,14 @@ constexpr int EVAL_LANES = HALO_EVAL ? NSTEPPERS : NCOMPUTE;   // lanes that sha
 #define SDFB_PUBLISH 2
 #endif
 constexpr int PUBLISH = SDFB_PUBLISH;                   // steps between progress publications
+// SDFB_QATOMIC: the warps of a column reserve their slice of the column-wide queue with one shared-memory atomicAdd
+// instead of exchanging their totals through a barrier: a step with candidates takes 3 CTA barriers instead of 4.
+// The order of the slices in the queue then depends on arrival order, which only changes WHICH lane evaluates an
+// entry; every owner still replays its own entries in the reference's order.
+#ifndef SDFB_QATOMIC
+#define SDFB_QATOMIC 0
+#endif
+constexpr bool QATOMIC = SDFB_QATOMIC != 0;
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -147,6 +155,7 @@ struct ColShared {
     float q_d[NCOMPUTE / 32][QCAP];
     float gx[NCOMPUTE], gy[NCOMPUTE], gz[NCOMPUTE];   // world position of each compute lane's current voxel
     int wtot[NCOMPUTE / 32];                          // candidates per warp in this step (column-wide queue mode)
+    int qn;                                           // SDFB_QATOMIC: entries reserved in this step (zeroed by lane 0 after use)
     int col;
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
 };
@@ -175,6 +184,13 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
 {
     bar_compute();
     int total = 0;
+    if (QATOMIC) {
+        total = *reinterpret_cast<volatile int *>(&sh.qn);            // final: every warp reserved before the barrier
+        if (total == 0) return 0u;
+        const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, NCOMPUTE + h, total) : 0u;
+        bar_compute();
+        return e;
+    }
     #pragma unroll
     for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
     if (total == 0) return 0u;
@@ -414,14 +430,22 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
     const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
                    b2 = __ballot_sync(0xffffffffu, ncand & 4);
     const uint32_t lt_mask = (1u << lane) - 1u;
-    if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-    TRACE(P, warp, s, 1);
-    bar_compute();
-    TRACE(P, warp, s, 2);
     int base = 0, total = 0;
-    #pragma unroll
-    for (int w = 0; w < NCOMPUTE / 32; ++w) { const int t = sh.wtot[w]; base += (w < warp) ? t : 0; total += t; }
-    if (total == 0) return make_uint2(cur, 0u);                       // uniform over the column
+    if (QATOMIC) {
+        const int wt = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        if (wt) {                                                     // uniform over the warp
+            if (lane == 0) base = atomicAdd(&sh.qn, wt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+        }
+    } else {
+        if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        TRACE(P, warp, s, 1);
+        bar_compute();
+        TRACE(P, warp, s, 2);
+        #pragma unroll
+        for (int w = 0; w < NCOMPUTE / 32; ++w) { const int t = sh.wtot[w]; base += (w < warp) ? t : 0; total += t; }
+        if (total == 0) return make_uint2(cur, 0u);                   // uniform over the column
+    }
     const int off = base + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
     if (live) {
         sh.gx[tid] = lattice(P.sd.abs_i(ri, g), g.dx, g.ox);           // gy, gz were stored once per column
@@ -436,10 +460,15 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
     TRACE(P, warp, s, 3);
     bar_compute();
     TRACE(P, warp, s, 4);
+    if (QATOMIC) {
+        total = *reinterpret_cast<volatile int *>(&sh.qn);            // final: every warp reserved before the barrier
+        if (total == 0) return make_uint2(cur, 0u);                   // uniform over the column
+    }
     evals = evaluate_queue_share(rec, sh, tid, total);
     TRACE(P, warp, s, 5);
     bar_compute();
     TRACE(P, warp, s, 6);
+    if (QATOMIC && tid == 0) sh.qn = 0;     // every lane read the total before this barrier; the next reservation comes after bar_step
     if (live) {
         // the reference's order and strict "<": all distances are fetched first (independent loads)
         float dv[7];
@@ -593,7 +622,7 @@ __device__ __forceinline__ void column_loop(uint64_t *__restrict__ cells, const 
 {
     for (;;) {
         // ---- take the next column (anti-diagonal order) --------------------------------------
-        if (GROUP != 1 && tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; }
+        if (GROUP != 1 && tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; sh.qn = 0; }
         __syncthreads();
         const int tk = sh.col;
         if (tk >= ncols) break;

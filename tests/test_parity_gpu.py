@@ -465,3 +465,41 @@ def test_full_size_512_properties():
     far = np.abs(exact) > float(dx)
     assert np.array_equal(phi[idx][far] < 0, exact[far] < 0)
     assert np.abs(phi[idx] - exact).max() < 0.75 * float(dx)
+
+
+def test_out_of_range_vertex_index_is_an_error_not_a_dead_context():
+    """The reference indexes x[] unchecked (cpu_lib/makelevelset3.cpp:205: undefined behaviour; its own test,
+    python/tests/test_sdfgen.py:826-847, accepts a crash or any exception).  On a GPU an illegal address would kill the
+    CUDA context for the whole process, so the device replaces the index and the delivering calls return
+    SDFB_ERR_INVALID naming the first offending triangle; the library keeps working afterwards."""
+    v, t = meshes.unit_cube()
+    o, dx = np.array([-0.5, -0.5, -0.5], np.float32), 0.1
+    good = sdfgen_b200.generate_sdf(v, t, tuple(o), dx, 20, 20, 20)
+    for bad_index in (999, 0xFFFFFFF0):
+        bad = t.copy()
+        bad[7, 2] = bad_index
+        with pytest.raises(ValueError) as e:            # SDFB_ERR_INVALID -> ValueError, like the reference's std::invalid_argument
+            sdfgen_b200.generate_sdf(v, bad, tuple(o), dx, 20, 20, 20)
+        assert "triangle 7 " in str(e.value)
+        again = sdfgen_b200.generate_sdf(v, t, tuple(o), dx, 20, 20, 20)
+        assert _same(good, again)
+    # plan API: the error surfaces at the blocking download, a new mesh on the same plan clears it
+    p = _lib.Plan(20, 20, 20)
+    p.set_mesh_host(v, t)
+    p.run(o, dx, 1)
+    ref_phi = p.download(phi=True)[0].copy()
+    bad = t.copy(); bad[0, 0] = 8
+    p.set_mesh_host(v, bad)
+    p.run(o, dx, 1)
+    with pytest.raises(ValueError):
+        p.download(phi=True)
+    p.set_mesh_host(v, t)
+    p.run(o, dx, 1)
+    phi = p.download(phi=True)[0]
+    p.close()
+    assert _same(phi, ref_phi)
+    # batch: the bad item is reported, by position
+    item = lambda tri: dict(vertices=v, triangles=tri, origin=tuple(o), dx=dx, nx=20, ny=20, nz=20)
+    with pytest.raises(ValueError) as e:
+        sdfgen_b200.generate_sdf_batch([item(t), item(bad), item(t)], concurrency=2)
+    assert "batch item 1" in str(e.value)
