@@ -503,3 +503,66 @@ def test_out_of_range_vertex_index_is_an_error_not_a_dead_context():
     with pytest.raises(ValueError) as e:
         sdfgen_b200.generate_sdf_batch([item(t), item(bad), item(t)], concurrency=2)
     assert "batch item 1" in str(e.value)
+
+
+def test_more_than_2_31_voxels_on_one_gpu():
+    """1300^3 = 2.197e9 voxels > 2^31 (the reference's `int` index overflows there, common/array3.h:59-61; SURVEY 8c
+    "large configs"): everything stays on the device.  (1) the production schedule mix equals the all-columns schedule
+    bit for bit (whole cell words: phi, stamp, closest_tri) and so do the signed outputs; (2) sampled voxels, most of
+    them beyond index 2^31, hold exactly the reference distance to the triangle they name; (3) signs and distances
+    agree with the analytic sphere."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < (120 << 30) and os.environ.get("SDFB_TEST_HUGE") != "1":
+        pytest.skip(f"needs ~80 GB of device memory, {free >> 30} GB free (SDFB_TEST_HUGE=1 forces it)")
+    n = int(os.environ.get("SDFB_TEST_HUGE_N", "1300"))
+    w = meshes.workload("c2_icosphere_512", n=n)
+    V = n ** 3
+    assert V > 2 ** 31
+
+    def view(ptr, count, typestr):
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None}
+        keep = _Arr()
+        return torch.as_tensor(keep, device="cuda"), keep
+
+    snap = {}
+    for sched, flags in (("default", 0), ("columns", _lib.SWEEP_COLUMNS)):
+        p = _lib.Plan(n, n, n, flags=flags)
+        p.set_mesh_host(w["vertices"], w["triangles"])
+        p.run(w["origin"], w["dx"], 1)
+        torch.cuda.synchronize()
+        ms = p.phase_ms()
+        print(f"{sched}: {n}^3 in {ms['total']:.1f} ms = {V / ms['total'] / 1e6:.2f} Gvoxel/s")
+        cells_ptr, counts_ptr, phi_ptr = p.device_ptrs()
+        cells, k1 = view(cells_ptr + 8 * n * n, V, "<i8")         # skip the lower halo plane
+        phi, k2 = view(phi_ptr, V, "<f4")
+        if sched == "default":
+            snap["cells"], snap["phi"] = cells.clone(), phi.clone()
+            counts, k3 = view(counts_ptr, V, "<i4")
+            snap["crossings"] = int(counts.sum(dtype=torch.int64).item())
+        else:
+            assert torch.equal(cells, snap["cells"]), "default and all-columns schedules differ"
+            assert torch.equal(phi.view(torch.int32), snap["phi"].view(torch.int32))
+        del cells, phi
+        p.close()
+    assert snap["crossings"] > 0
+    rng = np.random.default_rng(5)
+    idx = np.concatenate([rng.integers(2 ** 31, V, 300), rng.integers(0, 2 ** 31, 100), [V - 1, 2 ** 31, 2 ** 31 - 1]]).astype(np.int64)
+    t_idx = torch.from_numpy(idx).cuda()
+    cw = snap["cells"][t_idx].cpu().numpy().astype(np.uint64)
+    ph = snap["phi"][t_idx].cpu().numpy()
+    tri = (cw & np.uint64(0x07FFFFFF)).astype(np.int64)
+    assert np.array_equal((cw >> np.uint64(32)).astype(np.uint32), np.abs(ph).view(np.uint32))       # cell phi == |output phi|
+    v, t, o, dx = w["vertices"], w["triangles"], w["origin"], np.float32(w["dx"])
+    k, rem = np.divmod(idx, n * n)
+    j, i = np.divmod(rem, n)
+    for q in range(idx.size):
+        gx = np.array([i[q], j[q], k[q]], np.float32) * dx + o
+        d = oracle.port.point_triangle_distance(gx, *v[t[tri[q]]])
+        assert np.float32(d).view(np.uint32) == np.abs(ph[q]).view(np.uint32), (int(idx[q]), float(d), float(ph[q]))
+    pts = np.stack([i, j, k], 1).astype(np.float64) * float(dx) + o.astype(np.float64)
+    exact = np.linalg.norm(pts, axis=1) - 0.4
+    far = np.abs(exact) > float(dx)
+    assert np.array_equal(ph[far] < 0, exact[far] < 0)
+    assert np.abs(ph - exact).max() < 0.75 * float(dx)
