@@ -91,6 +91,15 @@ constexpr int PUBLISH = SDFB_PUBLISH;                   // steps between progres
 #define SDFB_QATOMIC 0
 #endif
 constexpr bool QATOMIC = SDFB_QATOMIC != 0;
+// SDFB_EVAL_PF: before a lane evaluates a queue entry it starts the record gather of its NEXT entry (L1 prefetch), so
+// the second evaluation round of a step finds its triangle in L1.  SDFB_ENQ_PF: the enqueuing lane prefetches the
+// records of its own candidates into the SM's L1 (every lane of the column shares it) two barriers before they are read.
+#ifndef SDFB_EVAL_PF
+#define SDFB_EVAL_PF 0
+#endif
+#ifndef SDFB_ENQ_PF
+#define SDFB_ENQ_PF 0
+#endif
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -168,6 +177,13 @@ __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restric
     unsigned evals = 0;
     int q = first;
     for (; q < total; q += EVAL_LANES) {
+#if SDFB_EVAL_PF
+        if (q + EVAL_LANES < total) {
+            const char *ra = reinterpret_cast<const char *>(&rec[q_ent[q + EVAL_LANES]]);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
+        }
+#endif
         const int ot = __float_as_int(q_d[q]);                         // owner lane, replaced by the distance
         const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
         const TriRec *tr = &rec[q_ent[q]];
@@ -455,6 +471,11 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
             q_ent[w] = nb[m] & TRI_MASK;
             q_d[w] = __int_as_float(tid);                              // owner, replaced by the distance below
             ++w;
+#if SDFB_ENQ_PF
+            const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
+#endif
         }
     }
     TRACE(P, warp, s, 3);

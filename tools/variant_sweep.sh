@@ -10,7 +10,7 @@ run_bench base
 for v in "$@"; do SDFB_LIB_PATH=$PWD/sdfgen_b200/variants/libsdfb_$v.so run_bench $v; done
 for v in "$@"; do
   SDFB_LIB_PATH=$PWD/sdfgen_b200/variants/libsdfb_$v.so python -m pytest tests/test_parity_gpu.py -x -q \
-    -k "golden_small_cases_bit_exact or downscaled or full_size_512 or two_slabs or per_sweep" > $out/parity_$v.log 2>&1 &
+    -k "${PARITY_K:-golden_small_cases_bit_exact or downscaled or full_size_512 or two_slabs or per_sweep}" > $out/parity_$v.log 2>&1 &
 done
 wait
 for v in base "$@"; do python - "$v" <<'PY'
