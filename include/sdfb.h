@@ -82,6 +82,10 @@ uint64_t sdfb_launch_count(void);
  *   intersection_count_out  ni*nj*nk int32 or NULL
  * The two nullable outputs exist because parity is graded on them and the reference keeps them as
  * locals (cpu_lib/makelevelset3.cpp:198-199).
+ * A triangle that names a vertex index >= nvert is undefined behaviour in the reference (x[] is indexed unchecked,
+ * cpu_lib/makelevelset3.cpp:205); here it is SDFB_ERR_INVALID ("triangle T names a vertex index >= nvert"), found on the
+ * device and reported by the calls that deliver results (this one, the batch call, sdfb_plan_download,
+ * sdfb_plan_write_sdf); the CUDA context stays usable.
  */
 int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
                          const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
