@@ -9,7 +9,9 @@ import oracle
 
 
 class OracleSlabEngine:
-    def __init__(self, vertices, triangles, ni, nj, nk, k_lo, k_hi):
+    def __init__(self, vertices, triangles, ni, nj, nk, k_lo, k_hi, relax_from=None):
+        # relax_from: sweeps >= this index use the relaxation emulator (seeded random order) instead of the column one
+        self.relax_from = relax_from
         self.v = np.ascontiguousarray(vertices, np.float32)
         self.t = np.ascontiguousarray(triangles, np.uint32)
         self.ni, self.nj, self.nk, self.k_lo, self.k_hi = ni, nj, nk, k_lo, k_hi
@@ -40,8 +42,13 @@ class OracleSlabEngine:
         L = oracle.port.lib()
         for s in range(first, first + count):
             ch = C.c_long()
-            L.sdfo_emu_sweep_columns(self.t, self.v, self.cphi, self.clo, self.o, self.dx, self.ni, self.nj, self.nk,
-                                     self.k_lo, self.k_hi, s, C.byref(ch))
+            if self.relax_from is not None and s >= self.relax_from:
+                rd = C.c_long()
+                L.sdfo_emu_sweep_relax(self.t, self.v, self.cphi, self.clo, self.o, self.dx, self.ni, self.nj, self.nk,
+                                       self.k_lo, self.k_hi, s, 7 + s, C.byref(ch), C.byref(rd))
+            else:
+                L.sdfo_emu_sweep_columns(self.t, self.v, self.cphi, self.clo, self.o, self.dx, self.ni, self.nj, self.nk,
+                                         self.k_lo, self.k_hi, s, C.byref(ch))
             self._changed += int(ch.value)
 
     def changed(self):

@@ -124,14 +124,18 @@ def test_run_sharded_exact_gloo_is_bit_identical_to_one_grid(tmp_path, world):
     assert np.array_equal(phi.view(np.uint32), full.phi.view(np.uint32))
 
 
+@pytest.mark.parametrize("relax_from", [None, 8, 0])
 @pytest.mark.parametrize("bounds", [[(0, 20), (20, 40)], [(0, 1), (1, 4), (4, 23), (23, 40)]])
-def test_exact_order_in_one_process_is_bit_identical_to_one_grid(bounds):
-    """run_slabs_exact_local (slabs visited upstream to downstream inside each sweep), incl. one-plane and thin slabs."""
+def test_exact_order_in_one_process_is_bit_identical_to_one_grid(bounds, relax_from):
+    """run_slabs_exact_local (slabs visited upstream to downstream inside each sweep), incl. one-plane and thin slabs;
+    with the column emulator for every sweep, with the production mix (relaxation emulator from sweep 8, chaotic order)
+    and with the relaxation emulator for every sweep: halo cells keep their stamps, the memo decides as on one grid."""
     sys.path.insert(0, HERE)
     from fake_engine import OracleSlabEngine
     w = _case()
     assert bounds[-1][1] == w["nk"]
-    engs = [OracleSlabEngine(w["vertices"], w["triangles"], w["ni"], w["nj"], w["nk"], lo, hi) for lo, hi in bounds]
+    engs = [OracleSlabEngine(w["vertices"], w["triangles"], w["ni"], w["nj"], w["nk"], lo, hi, relax_from=relax_from)
+            for lo, hi in bounds]
     sdist.run_slabs_exact_local(engs, w["origin"], w["dx"], 1)
     full = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], w["ni"], w["nj"], w["nk"])
     assert np.array_equal(np.concatenate([e.tri() for e in engs]), full.tri_final)
