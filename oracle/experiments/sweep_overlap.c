@@ -1,0 +1,123 @@
+/*
+ * sweep_overlap.c -- CPU experiment (TEST INFRASTRUCTURE / design study, never linked into the product).
+ *
+ * Question for the next round: may column (J',K') of sweep s+1 start before sweep s has finished everywhere?
+ * Rule under test: a column of sweep s+1 covers the rows (j,k) of a rectangle R, all i.  It writes the cells of R and
+ * reads R grown by one row on its upstream sides.  Sweep s must (a) have produced its final values there and (b) not
+ * need the pre-(s+1) values of anything sweep s+1 writes; sweep s reads one row around the rows it updates.  Both hold
+ * once sweep s has COMPLETED every row of R grown by one in all four directions, i.e. every sweep-s column that
+ * intersects the grown rectangle.
+ *
+ * The program processes whole columns (EJ x EK rows, all i, serial order inside) in this adversarial order: sweep-s
+ * columns by ticket (anti-diagonals J+K); after each one, every sweep-(s+1) column that has become ready (its own
+ * left/down/diagonal columns of sweep s+1 done, the rule above satisfied) runs at once.  The result must equal the two
+ * serial sweeps bit for bit.  It also reports how early the columns of sweep s+1 became ready.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+float sdfo_point_triangle_distance(const float *x0, const float *x1, const float *x2, const float *x3);
+
+static const int DIRS[8][3] = { {+1,+1,+1}, {-1,-1,-1}, {+1,+1,-1}, {-1,-1,+1}, {+1,-1,+1}, {-1,+1,-1}, {+1,-1,-1}, {-1,+1,+1} };
+
+typedef struct { int ni, nj, nk; float dx, o[3]; const uint32_t *tri; const float *x; float *phi; int32_t *ctri; } G;
+
+static void relax(const G *g, int i, int j, int k, int di, int dj, int dk)      /* cpu_lib/makelevelset3.cpp:104-127 body */
+{
+    const int64_t c0 = (int64_t)i + (int64_t)g->ni * (j + (int64_t)g->nj * k);
+    float gx[3] = { i * g->dx + g->o[0], j * g->dx + g->o[1], k * g->dx + g->o[2] };
+    static const int OFF[7][3] = { {1,0,0}, {0,1,0}, {1,1,0}, {0,0,1}, {1,0,1}, {0,1,1}, {1,1,1} };
+    for (int m = 0; m < 7; ++m) {
+        int64_t c1 = (int64_t)(i - di * OFF[m][0]) + (int64_t)g->ni * ((j - dj * OFF[m][1]) + (int64_t)g->nj * (k - dk * OFF[m][2]));
+        int32_t t = g->ctri[c1];
+        if (t >= 0) {
+            const uint32_t *tv = g->tri + 3 * (size_t)t;
+            float d = sdfo_point_triangle_distance(gx, g->x + 3 * (size_t)tv[0], g->x + 3 * (size_t)tv[1], g->x + 3 * (size_t)tv[2]);
+            if (d < g->phi[c0]) { g->phi[c0] = d; g->ctri[c0] = t; }
+        }
+    }
+}
+
+static void serial_sweep(const G *g, int s)
+{
+    int di = DIRS[s % 8][0], dj = DIRS[s % 8][1], dk = DIRS[s % 8][2];
+    for (int rk = 1; rk < g->nk; ++rk) for (int rj = 1; rj < g->nj; ++rj) for (int ri = 1; ri < g->ni; ++ri)
+        relax(g, di > 0 ? ri : g->ni - 1 - ri, dj > 0 ? rj : g->nj - 1 - rj, dk > 0 ? rk : g->nk - 1 - rk, di, dj, dk);
+}
+
+/* absolute row rectangle [j0,j1] x [k0,k1] of column (J,K) of sweep s */
+static void col_rect(const G *g, int s, int EJ, int EK, int J, int K, int *j0, int *j1, int *k0, int *k1)
+{
+    int dj = DIRS[s % 8][1], dk = DIRS[s % 8][2];
+    int a = 1 + J * EJ, b = a + EJ - 1; if (b > g->nj - 1) b = g->nj - 1;
+    int c = 1 + K * EK, d = c + EK - 1; if (d > g->nk - 1) d = g->nk - 1;
+    if (dj > 0) { *j0 = a; *j1 = b; } else { *j0 = g->nj - 1 - b; *j1 = g->nj - 1 - a; }
+    if (dk > 0) { *k0 = c; *k1 = d; } else { *k0 = g->nk - 1 - d; *k1 = g->nk - 1 - c; }
+}
+
+static void run_column(const G *g, int s, int EJ, int EK, int J, int K)
+{
+    int di = DIRS[s % 8][0], dj = DIRS[s % 8][1], dk = DIRS[s % 8][2];
+    for (int rk = 1 + K * EK; rk < 1 + (K + 1) * EK && rk < g->nk; ++rk)
+        for (int rj = 1 + J * EJ; rj < 1 + (J + 1) * EJ && rj < g->nj; ++rj)
+            for (int ri = 1; ri < g->ni; ++ri)
+                relax(g, di > 0 ? ri : g->ni - 1 - ri, dj > 0 ? rj : g->nj - 1 - rj, dk > 0 ? rk : g->nk - 1 - rk, di, dj, dk);
+}
+
+/*
+ * Runs sweeps s and s+1 on (phi, ctri) in place with the overlapped column order; ref_phi/ref_tri receive the two
+ * serial sweeps applied to a copy.  ready_at[c'] = number of sweep-s columns that had completed when column c' of sweep
+ * s+1 ran (== NJ*NK means "only after sweep s had finished").  Returns 0 if the overlapped result equals the serial one.
+ */
+int sweep_overlap_run(const uint32_t *tri, const float *x, float *phi, int32_t *ctri, float *ref_phi, int32_t *ref_tri,
+                      const float origin[3], float dx, int ni, int nj, int nk, int EJ, int EK, int s, int32_t *ready_at)
+{
+    const int64_t V = (int64_t)ni * nj * nk;
+    G g = { ni, nj, nk, dx, { origin[0], origin[1], origin[2] }, tri, x, ref_phi, ref_tri };
+    memcpy(ref_phi, phi, sizeof(float) * V); memcpy(ref_tri, ctri, 4 * V);
+    serial_sweep(&g, s); serial_sweep(&g, s + 1);
+    g.phi = phi; g.ctri = ctri;
+    const int NJ = (nj - 1 + EJ - 1) / EJ, NK = (nk - 1 + EK - 1) / EK, NC = NJ * NK;
+    uint8_t *done0 = calloc(NC, 1), *done1 = calloc(NC, 1);
+    /* prerequisites of every sweep-(s+1) column in terms of sweep-s columns: [Ja,Jb] x [Ka,Kb] */
+    int *pre = malloc(sizeof(int) * 4 * NC);
+    for (int K = 0; K < NK; ++K) for (int J = 0; J < NJ; ++J) {
+        int j0, j1, k0, k1; col_rect(&g, s + 1, EJ, EK, J, K, &j0, &j1, &k0, &k1);
+        j0 -= 1; j1 += 1; k0 -= 1; k1 += 1;                                  /* grown by one row in all four directions */
+        if (j0 < 0) j0 = 0; if (j1 > nj - 1) j1 = nj - 1; if (k0 < 0) k0 = 0; if (k1 > nk - 1) k1 = nk - 1;
+        /* rows -> sweep-s relative rows -> sweep-s columns (relative row 0 is never updated: no column) */
+        int dj = DIRS[s % 8][1], dk = DIRS[s % 8][2];
+        int ra = dj > 0 ? j0 : nj - 1 - j1, rb = dj > 0 ? j1 : nj - 1 - j0;
+        int rc = dk > 0 ? k0 : nk - 1 - k1, rd = dk > 0 ? k1 : nk - 1 - k0;
+        if (ra < 1) ra = 1; if (rc < 1) rc = 1;
+        int *p = pre + 4 * (K * NJ + J);
+        p[0] = (ra - 1) / EJ; p[1] = rb >= 1 ? (rb - 1) / EJ : -1; p[2] = (rc - 1) / EK; p[3] = rd >= 1 ? (rd - 1) / EK : -1;
+    }
+    int completed0 = 0;
+    for (int d = 0; d <= NJ + NK - 2; ++d) for (int J = 0; J < NJ; ++J) {
+        int K = d - J; if (K < 0 || K >= NK) continue;
+        run_column(&g, s, EJ, EK, J, K); done0[K * NJ + J] = 1; ++completed0;
+        /* run every sweep-(s+1) column that is ready now; repeat until none is (anti-diagonal order keeps it cheap) */
+        for (int again = 1; again; ) {
+            again = 0;
+            for (int K1 = 0; K1 < NK; ++K1) for (int J1 = 0; J1 < NJ; ++J1) {
+                int c1 = K1 * NJ + J1;
+                if (done1[c1]) continue;
+                if (J1 > 0 && !done1[c1 - 1]) continue;
+                if (K1 > 0 && !done1[c1 - NJ]) continue;
+                if (J1 > 0 && K1 > 0 && !done1[c1 - NJ - 1]) continue;
+                const int *p = pre + 4 * c1; int ok = 1;
+                for (int Kq = p[2]; Kq <= p[3] && ok; ++Kq) for (int Jq = p[0]; Jq <= p[1]; ++Jq) if (!done0[Kq * NJ + Jq]) { ok = 0; break; }
+                if (!ok) continue;
+                run_column(&g, s + 1, EJ, EK, J1, K1); done1[c1] = 1; ready_at[c1] = completed0; again = 1;
+            }
+        }
+    }
+    int missing = 0;
+    for (int c1 = 0; c1 < NC; ++c1) missing += !done1[c1];
+    free(done0); free(done1); free(pre);
+    if (missing) return -1;
+    return (memcmp(phi, ref_phi, sizeof(float) * V) || memcmp(ctri, ref_tri, 4 * V)) ? 1 : 0;
+}
