@@ -478,7 +478,25 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     // first sweep index handled by the relaxation schedule: the reference's second pass and everything after it
     int relax_from = (p->flags & SDFB_SWEEP_RELAX) ? 0 : ((p->flags & (SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS)) ? 1 << 30 : 8);
     if (getenv("SDFB_RELAX_FROM") && !(p->flags & (SDFB_SWEEP_RELAX | SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS))) relax_from = atoi(getenv("SDFB_RELAX_FROM"));
-    for (int s = first; s < first + count; ++s) {
+    // EXPERIMENTAL (SDFB_FUSE_PASS=1): the column sweeps of the first pass in one launch, consecutive sweeps overlapping
+    // where the directions allow it (sdfb_sweep_columns.cu: k_sweep_columns_fused)
+    int fused_until = first;
+    if (getenv("SDFB_FUSE_PASS") && atoi(getenv("SDFB_FUSE_PASS")) != 0 &&
+        !(p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_STRIPS | SDFB_SWEEP_RELAX)) && first < 8 && first < relax_from) {
+        int n = (first + count < 8 ? first + count : 8);
+        if (n > relax_from) n = relax_from;
+        n -= first;
+        if (n >= 2) {
+            if (p->epoch + (uint32_t)n >= 65000u) {
+                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
+                p->epoch = 0;
+            }
+            const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
+                                                     &p->epoch, st, p->max_ctas);
+            if (l) { g_launches += l; fused_until = first + n; }
+        }
+    }
+    for (int s = fused_until; s < first + count; ++s) {
         if (p->flags & SDFB_SWEEP_LEVELS) {
             g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
         } else if (s >= relax_from && s + 1 < 31 && s > p->last_sweep && sweep_relax_supported(p->g)) {

@@ -41,6 +41,9 @@ int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int s
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
                          const unsigned int *run_if = nullptr, int max_ctas = 0);
+int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
+                               unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
+                               cudaStream_t st, int max_ctas);
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st);
 int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st);

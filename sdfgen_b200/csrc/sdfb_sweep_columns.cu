@@ -229,6 +229,37 @@ __device__ __forceinline__ void bar_go_wait(int chunk) { __syncwarp(); asm volat
 // run" is signalled to the halo warps with bar.arrive on barrier 4 + (c & 3): they block in hardware instead
 // of spinning.  The sync warp clears at most 3 chunks beyond the finished ones, so when it re-arms a barrier
 // (chunk c+4) its previous phase (chunk c) was consumed long ago.
+// Fused launches (several sweeps in one kernel, see k_sweep_columns_fused): before the column's first chunk is cleared,
+// every column of the PREVIOUS sweep that intersects this column's rows grown by one row in all four directions must
+// be complete (rule validated in oracle/experiments/sweep_overlap.c).  Q = the previous sweep's parameters, prevflags =
+// its progress words.  Runs on the whole sync warp; lanes 0..8 poll one prerequisite column each.
+__device__ __forceinline__ void wait_previous_sweep(const ColParams &P, const ColParams &Q, const uint32_t *prevflags,
+                                                    int lane, int J, int K)
+{
+    const Grid &g = P.g;
+    // this column's rows, relative then absolute, grown by one and clamped to the grid
+    int rja = 1 + J * EJ, rjb = min(rja + EJ - 1, g.nj - 1);
+    int rka = P.rk_first + K * EK, rkb = min(rka + EK - 1, P.rk_last);
+    int j0 = P.sd.dj > 0 ? rja : g.nj - 1 - rjb, j1 = P.sd.dj > 0 ? rjb : g.nj - 1 - rja;
+    int k0 = P.sd.dk > 0 ? rka : g.nk - 1 - rkb, k1 = P.sd.dk > 0 ? rkb : g.nk - 1 - rka;
+    j0 = max(j0 - 1, 0); j1 = min(j1 + 1, g.nj - 1); k0 = max(k0 - 1, 0); k1 = min(k1 + 1, g.nk - 1);
+    // -> rows of the previous sweep (relative), clipped to the rows it updates, -> its columns
+    int qja = Q.sd.dj > 0 ? j0 : g.nj - 1 - j1, qjb = Q.sd.dj > 0 ? j1 : g.nj - 1 - j0;
+    int qka = Q.sd.dk > 0 ? k0 : g.nk - 1 - k1, qkb = Q.sd.dk > 0 ? k1 : g.nk - 1 - k0;
+    qja = max(qja, 1); qjb = min(qjb, g.nj - 1); qka = max(qka, Q.rk_first); qkb = min(qkb, Q.rk_last);
+    if (qja > qjb || qka > qkb) return;                                   // uniform over the warp
+    const int Ja = (qja - 1) / EJ, Jb = (qjb - 1) / EJ, Ka = (qka - Q.rk_first) / EK, Kb = (qkb - Q.rk_first) / EK;
+    const int nJ = Jb - Ja + 1, n = nJ * (Kb - Ka + 1);                   // <= 3 x 3
+    const uint32_t need = (Q.epoch << 16) + (uint32_t)Q.steps;
+    const uint32_t *f = (lane < n) ? &prevflags[(Ka + lane / nJ) * Q.NJ + (Ja + lane % nJ)] : nullptr;
+    for (;;) {
+        const bool ok = !f || *reinterpret_cast<const volatile uint32_t *>(f) >= need;
+        if (__all_sync(0xffffffffu, ok)) break;
+        __nanosleep(SDFB_SYNC_SLEEP);
+    }
+    __threadfence();                    // acquire side: the column's loads (all ld.cg in fused launches) come after this
+}
+
 __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, int lane, const uint32_t *prog_left,
                                             const uint32_t *prog_down, uint32_t *prog_mine)
 {
@@ -509,7 +540,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
 
 // One step of a compute lane.  PAR = step parity: reads exchange slot PAR^1, writes slot PAR.  `own` holds the
 // lane's cell for this step on entry and is reloaded with the cell two steps ahead (see halo_column).
-template <int PAR, bool CTA_QUEUE>
+template <int PAR, bool CTA_QUEUE, bool L2OWN = false>
 __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                              const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
                                              int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
@@ -534,7 +565,9 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     const uint32_t r5 = rr[0], r3 = rr[1], r1 = rr[EJ + 1];
     const uint64_t self = own;
     uint64_t *const self_ptr = st.own_ptr;
-    if (row_ok && (unsigned)(ri + 2) < (unsigned)ni) own = *(self_ptr + 2 * si);       // the cell two steps ahead
+    // the cell two steps ahead.  Fused launches: another SM wrote it in the previous sweep of the SAME launch, so this
+    // SM's L1 may hold a stale line from the sweep before that -> read it from L2
+    if (row_ok && (unsigned)(ri + 2) < (unsigned)ni) own = L2OWN ? __ldcg(self_ptr + 2 * si) : *(self_ptr + 2 * si);
     if (row_ok && (s & (PF_CELLS - 1)) == 0) prefetch_run(self_ptr - si * (int64_t)ri, si, ri + PF_AHEAD, ni);
     uint32_t cur = cell_lo(self);
     const bool update = row_ok && (unsigned)(ri - 1) < (unsigned)(ni - 1);            // 1 <= ri <= ni-1
@@ -574,7 +607,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     bar_step();
 }
 
-template <bool CTA_QUEUE>
+template <bool CTA_QUEUE, bool L2OWN = false>
 __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
                                                const ColParams &P, ColShared &sh, int tid, int rj0, int rk0,
                                                unsigned &my_changed, unsigned &my_evals)
@@ -616,11 +649,11 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
         prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, 0, g.ni);
         prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, PF_CELLS, g.ni);
     }
-    if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = *st.own_ptr;
-    if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = *(st.own_ptr + si);
+    if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = L2OWN ? __ldcg(st.own_ptr) : *st.own_ptr;
+    if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = L2OWN ? __ldcg(st.own_ptr + si) : *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        compute_step<0, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, ownB, st);
-        compute_step<1, CTA_QUEUE>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, ownA, st);
+        compute_step<0, CTA_QUEUE, L2OWN>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, ownB, st);
+        compute_step<1, CTA_QUEUE, L2OWN>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, ownA, st);
         if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
             __threadfence_block();
             sh.done = (s + 2) / PUBLISH;
@@ -707,13 +740,134 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
     }
 }
 
+// ---- fused launch (EXPERIMENTAL, off unless SDFB_FUSE_PASS=1): several consecutive sweeps in ONE kernel ----------------
+// Tickets run through the columns of sweep 0 of the launch, then sweep 1, ...; a CTA that has finished its last column
+// of one sweep simply takes a column of the next and waits (wait_previous_sweep) until the columns of the previous
+// sweep it depends on are complete.  Transitions where only some axes flip overlap; opposite
+// directions serialise by themselves.  Every prerequisite holds a lower ticket, so it is running or done: no deadlock.
+// Progress words are double-buffered by launch-relative sweep parity.  Cells are read through L2 only (L2OWN).
+constexpr int FUSE_MAX = 8;
+struct FusedParams {
+    int n;                       // sweeps in this launch
+    int col_begin[FUSE_MAX + 1]; // first ticket of each sweep
+    int flag_stride;             // words between the two progress arrays
+    ColParams p[FUSE_MAX];
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(NTHREADS, MINB)
+k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, const __grid_constant__ FusedParams FP,
+                      uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket, unsigned long long *__restrict__ changed)
+{
+    __shared__ ColShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ncols = FP.col_begin[FP.n];
+    unsigned my_changed = 0, my_evals = 0;
+    int q = 0;
+    for (;;) {
+        if (tid == 0) { sh.col = (int)atomicAdd(ticket, 1u); sh.done = 0; sh.qn = 0; }
+        __syncthreads();
+        const int tk_all = sh.col;
+        if (tk_all >= ncols) break;
+        while (tk_all >= FP.col_begin[q + 1]) ++q;                       // tickets only grow
+        const ColParams &P = FP.p[q];
+        const int tk = tk_all - FP.col_begin[q];
+        int J, K;
+        {
+            int d = 0, rem = tk;
+            for (;;) {
+                int lo = max(0, d - (P.NK - 1)), hi = min(d, P.NJ - 1);
+                int cnt = hi - lo + 1;
+                if (rem < cnt) { J = lo + rem; K = d - J; break; }
+                rem -= cnt; ++d;
+            }
+        }
+        uint32_t *flags = progress + (q & 1) * FP.flag_stride;
+        const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
+        if (tid < NCOMPUTE) {
+            compute_column<true, true>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+        } else if (tid < NSTEPPERS) {
+            halo_column<true>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+        } else if (tid < NSTEPPERS + 32) {
+            if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, lane, J, K);
+            const uint32_t *prog_left = (J > 0) ? &flags[K * P.NJ + (J - 1)] : nullptr;
+            const uint32_t *prog_down = (K > 0) ? &flags[(K - 1) * P.NJ + J] : nullptr;
+            sync_column(P, sh, lane, prog_left, prog_down, &flags[K * P.NJ + J]);
+        }
+        __syncthreads();
+    }
+    unsigned wsum = my_changed, esum = my_evals;
+    for (int o = 16; o > 0; o >>= 1) { wsum += __shfl_down_sync(0xffffffffu, wsum, o); esum += __shfl_down_sync(0xffffffffu, esum, o); }
+    if (lane == 0 && wsum) atomicAdd(changed, (unsigned long long)wsum);
+    if (lane == 0 && esum) atomicAdd(changed + 1, (unsigned long long)esum);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        unsigned done = atomicAdd(ticket + 1, 1u);
+        if (done == gridDim.x - 1) { ticket[0] = 0; ticket[1] = 0; __threadfence(); }
+    }
+}
+
+bool fill_col_params(ColParams &P, const Grid &g, int sweep_index, uint32_t epoch)
+{
+    P = ColParams{};
+    P.g = g;
+    P.run_if = nullptr;
+    P.sd = SweepDir::of(sweep_index);
+    int rk_lo, rk_hi;
+    if (!P.sd.owned_rk_range(g, rk_lo, rk_hi)) return false;
+    if (g.ni < 2 || g.nj < 2) return false;
+    P.rk_first = rk_lo; P.rk_last = rk_hi;
+    P.NJ = (g.nj - 1 + EJ - 1) / EJ;
+    P.NK = (rk_hi - rk_lo + 1 + EK - 1) / EK;
+    P.steps = (g.ni + EJ + EK - 2 + SHIFT + PUBLISH - 1) / PUBLISH * PUBLISH;
+    P.stamp = (uint32_t)min(sweep_index + 1, 31);
+    P.epoch = epoch;
+    memo_last_table(sweep_index, P.sd, P.last);
+    return true;
+}
+
 }  // namespace
 
-// progress: [2] ticket words + [1] epoch counter slot (host side keeps the epoch) + NJ*NK flags
+// Experimental: sweeps first .. first+count-1 (all of the first pass' kind: column-wide queue) in one launch.
+// Returns the number of launches (1), or 0 if this grid cannot be fused (then the caller launches sweep by sweep);
+// *epoch is advanced by one per sweep.
+int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
+                               unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
+                               cudaStream_t st, int max_ctas)
+{
+    if (WG || count < 2 || count > FUSE_MAX) return 0;
+    FusedParams FP{};
+    FP.n = count;
+    FP.flag_stride = (int)((progress_words - 4) / 2);
+    FP.col_begin[0] = 0;
+    for (int q = 0; q < count; ++q) {
+        if (!fill_col_params(FP.p[q], g, first + q, *epoch + 1 + (uint32_t)q)) return 0;      // a sweep with nothing to update: do not fuse
+        if ((size_t)FP.p[q].NJ * FP.p[q].NK > (size_t)FP.flag_stride) return 0;
+        FP.col_begin[q + 1] = FP.col_begin[q] + FP.p[q].NJ * FP.p[q].NK;
+    }
+    *epoch += (uint32_t)count;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int minb = ((int64_t)g.ni * (g.nj - 1) * (FP.p[0].rk_last - FP.p[0].rk_first + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
+    if (getenv("SDFB_MINB")) minb = atoi(getenv("SDFB_MINB")) >= 4 ? 4 : 3;
+    auto kern = minb == 4 ? k_sweep_columns_fused<4> : k_sweep_columns_fused<3>;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, 0);
+    if (occ < 1) occ = 1;
+    int grid = sms * occ;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid > FP.col_begin[count]) grid = FP.col_begin[count];
+    kern<<<grid, NTHREADS, 0, st>>>(cells, rec, FP, progress + 4, progress, changed);
+    return 1;
+}
+
+// progress: [2] ticket words + [1] epoch counter slot (host side keeps the epoch) + 2 x NJ*NK flags (the second array is
+// used by fused launches only)
 size_t sweep_columns_progress_words(const Grid &g)
 {
     size_t NJ = (size_t)(g.nj + EJ - 1) / EJ + 1, NK = (size_t)(g.nkl() + EK - 1) / EK + 1;
-    return 4 + NJ * NK;
+    return 4 + 2 * NJ * NK;
 }
 
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
