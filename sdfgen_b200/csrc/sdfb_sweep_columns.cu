@@ -229,6 +229,12 @@ __device__ __forceinline__ void bar_go_wait(int chunk) { __syncwarp(); asm volat
 // run" is signalled to the halo warps with bar.arrive on barrier 4 + (c & 3): they block in hardware instead
 // of spinning.  The sync warp clears at most 3 chunks beyond the finished ones, so when it re-arms a barrier
 // (chunk c+4) its previous phase (chunk c) was consumed long ago.
+// Fused launches: the compute lanes must not load their first cells before the previous sweep's columns are complete
+// (in separate launches the cells are final when the kernel starts).  Named barrier 3: the sync warp arrives once the
+// prerequisites hold, the compute lanes wait on it at the top of the column.
+__device__ __forceinline__ void bar_start_arrive() { __syncwarp(); asm volatile("bar.arrive 3, %0;" ::"n"(NCOMPUTE + 32) : "memory"); }
+__device__ __forceinline__ void bar_start_wait() { __syncwarp(); asm volatile("bar.sync 3, %0;" ::"n"(NCOMPUTE + 32) : "memory"); }
+
 // Fused launches (several sweeps in one kernel, see k_sweep_columns_fused): before the column's first chunk is cleared,
 // every column of the PREVIOUS sweep that intersects this column's rows grown by one row in all four directions must
 // be complete (rule validated in oracle/experiments/sweep_overlap.c).  Q = the previous sweep's parameters, prevflags =
@@ -649,6 +655,7 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
         prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, 0, g.ni);
         prefetch_run(st.own_ptr - si * (int64_t)st.ri, si, PF_CELLS, g.ni);
     }
+    if (L2OWN) bar_start_wait();           // fused launches: the previous sweep is complete on the rows this column touches
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = L2OWN ? __ldcg(st.own_ptr) : *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = L2OWN ? __ldcg(st.own_ptr + si) : *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
@@ -790,6 +797,7 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
             halo_column<true>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
         } else if (tid < NSTEPPERS + 32) {
             if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, lane, J, K);
+            bar_start_arrive();
             const uint32_t *prog_left = (J > 0) ? &flags[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &flags[(K - 1) * P.NJ + J] : nullptr;
             sync_column(P, sh, lane, prog_left, prog_down, &flags[K * P.NJ + J]);
