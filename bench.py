@@ -349,7 +349,7 @@ def run_single_gpu(args):
                    "sweeps": 16, "schedule": args.schedule, "l2": "grid state (12 B/voxel + 4 B/voxel output) is far larger than the 126 MB L2; no flush needed",
                    "phase_ms": phase, "sweep_pass_ms": {"first_pass_8_sweeps": pass1_ms, "second_pass_8_sweeps": pass2_ms},
                    "inside_voxels": inside},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_columns (first pass: one launch per direction, 8 per step)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_columns_fused (first pass: the 8 direction sweeps in one launch, consecutive sweeps overlapping; launch_ms and the bytes are per sweep = launch / 8)" if args.schedule == "default" and os.environ.get("SDFB_FUSE_PASS") != "0" else "k_sweep_columns (first pass: one launch per direction, 8 per step)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes_sweep, "launch_ms": sweep_launch_ms,
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak,

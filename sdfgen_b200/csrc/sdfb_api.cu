@@ -478,10 +478,15 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     // first sweep index handled by the relaxation schedule: the reference's second pass and everything after it
     int relax_from = (p->flags & SDFB_SWEEP_RELAX) ? 0 : ((p->flags & (SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS)) ? 1 << 30 : 8);
     if (getenv("SDFB_RELAX_FROM") && !(p->flags & (SDFB_SWEEP_RELAX | SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS))) relax_from = atoi(getenv("SDFB_RELAX_FROM"));
-    // EXPERIMENTAL (SDFB_FUSE_PASS=1): the column sweeps of the first pass in one launch, consecutive sweeps overlapping
-    // where the directions allow it (sdfb_sweep_columns.cu: k_sweep_columns_fused)
+    // The column sweeps of the first pass go out as ONE launch in which consecutive sweeps overlap where their directions
+    // allow it (sdfb_sweep_columns.cu: k_sweep_columns_fused).  SDFB_FUSE_PASS=0 turns it off (one launch per sweep),
+    // =1 also fuses launches of >= 300 M voxels, which otherwise stay on the per-sweep path (their 4-CTA/SM build of the
+    // fused kernel has not been measured yet).
     int fused_until = first;
-    if (getenv("SDFB_FUSE_PASS") && atoi(getenv("SDFB_FUSE_PASS")) != 0 &&
+    const char *fuse_env = getenv("SDFB_FUSE_PASS");
+    const int fuse_mode = fuse_env ? atoi(fuse_env) : -1;                       // -1 default, 0 off, 1 forced
+    const bool big_launch = (int64_t)p->g.ni * (p->g.nj - 1) * p->g.nkl() >= ((int64_t)300 << 20);
+    if (fuse_mode != 0 && (fuse_mode == 1 || !big_launch) &&
         !(p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_STRIPS | SDFB_SWEEP_RELAX)) && first < 8 && first < relax_from) {
         int n = (first + count < 8 ? first + count : 8);
         if (n > relax_from) n = relax_from;

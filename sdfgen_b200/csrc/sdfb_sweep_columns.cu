@@ -747,7 +747,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
     }
 }
 
-// ---- fused launch (EXPERIMENTAL, off unless SDFB_FUSE_PASS=1): several consecutive sweeps in ONE kernel ----------------
+// ---- fused launch (the default for the first pass; SDFB_FUSE_PASS=0 turns it off): consecutive sweeps in ONE kernel ---
 // Tickets run through the columns of sweep 0 of the launch, then sweep 1, ...; a CTA that has finished its last column
 // of one sweep simply takes a column of the next and waits (wait_previous_sweep) until the columns of the previous
 // sweep it depends on are complete.  Transitions where only some axes flip overlap; opposite
@@ -837,7 +837,7 @@ bool fill_col_params(ColParams &P, const Grid &g, int sweep_index, uint32_t epoc
 
 }  // namespace
 
-// Experimental: sweeps first .. first+count-1 (all of the first pass' kind: column-wide queue) in one launch.
+// Sweeps first .. first+count-1 (all of the first pass' kind: column-wide queue) in one launch.
 // Returns the number of launches (1), or 0 if this grid cannot be fused (then the caller launches sweep by sweep);
 // *epoch is advanced by one per sweep.
 int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
