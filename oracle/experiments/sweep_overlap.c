@@ -22,7 +22,39 @@ float sdfo_point_triangle_distance(const float *x0, const float *x1, const float
 
 static const int DIRS[8][3] = { {+1,+1,+1}, {-1,-1,-1}, {+1,+1,-1}, {-1,-1,+1}, {+1,-1,+1}, {-1,+1,-1}, {+1,-1,-1}, {-1,+1,+1} };
 
-typedef struct { int ni, nj, nk; float dx, o[3]; const uint32_t *tri; const float *x; float *phi; int32_t *ctri; } G;
+typedef struct { int ni, nj, nk; float dx, o[3]; const uint32_t *tri; const float *x; float *phi; int32_t *ctri; int k_lo, k_hi; } G;
+
+/* sweep parameters as the CUDA launch computes them (sdfb_sweep_common.cuh: owned_rk_range; sdfb_sweep_columns.cu: fill_col_params) */
+typedef struct { int di, dj, dk, rk_first, rk_last, NJ, NK, ok; } SP;
+static SP sweep_params(const G *g, int s, int EJ, int EK)
+{
+    SP p; p.di = DIRS[s % 8][0]; p.dj = DIRS[s % 8][1]; p.dk = DIRS[s % 8][2];
+    int a = p.dk > 0 ? g->k_lo : g->nk - 1 - g->k_lo, b = p.dk > 0 ? g->k_hi - 1 : g->nk - 1 - (g->k_hi - 1);
+    int lo = a < b ? a : b, hi = a < b ? b : a;
+    if (lo < 1) lo = 1;
+    p.rk_first = lo; p.rk_last = hi; p.ok = lo <= hi && g->ni >= 2 && g->nj >= 2;
+    p.NJ = (g->nj - 1 + EJ - 1) / EJ; p.NK = p.ok ? (hi - lo + 1 + EK - 1) / EK : 0;
+    return p;
+}
+
+/* LITERAL PORT of the device arithmetic of wait_previous_sweep (sdfb_sweep_columns.cu): the columns [Ja,Jb] x [Ka,Kb] of
+ * the previous sweep Q that column (J,K) of sweep P waits for; returns 0 if there are none. */
+static int prereq_device(const G *g, const SP *P, const SP *Q, int EJ, int EK, int J, int K, int *Ja, int *Jb, int *Ka, int *Kb)
+{
+    #define MIN(a, b) ((a) < (b) ? (a) : (b))
+    #define MAX(a, b) ((a) > (b) ? (a) : (b))
+    int rja = 1 + J * EJ, rjb = MIN(rja + EJ - 1, g->nj - 1);
+    int rka = P->rk_first + K * EK, rkb = MIN(rka + EK - 1, P->rk_last);
+    int j0 = P->dj > 0 ? rja : g->nj - 1 - rjb, j1 = P->dj > 0 ? rjb : g->nj - 1 - rja;
+    int k0 = P->dk > 0 ? rka : g->nk - 1 - rkb, k1 = P->dk > 0 ? rkb : g->nk - 1 - rka;
+    j0 = MAX(j0 - 1, 0); j1 = MIN(j1 + 1, g->nj - 1); k0 = MAX(k0 - 1, 0); k1 = MIN(k1 + 1, g->nk - 1);
+    int qja = Q->dj > 0 ? j0 : g->nj - 1 - j1, qjb = Q->dj > 0 ? j1 : g->nj - 1 - j0;
+    int qka = Q->dk > 0 ? k0 : g->nk - 1 - k1, qkb = Q->dk > 0 ? k1 : g->nk - 1 - k0;
+    qja = MAX(qja, 1); qjb = MIN(qjb, g->nj - 1); qka = MAX(qka, Q->rk_first); qkb = MIN(qkb, Q->rk_last);
+    if (qja > qjb || qka > qkb) return 0;
+    *Ja = (qja - 1) / EJ; *Jb = (qjb - 1) / EJ; *Ka = (qka - Q->rk_first) / EK; *Kb = (qkb - Q->rk_first) / EK;
+    return 1;
+}
 
 static void relax(const G *g, int i, int j, int k, int di, int dj, int dk)      /* cpu_lib/makelevelset3.cpp:104-127 body */
 {
@@ -119,5 +151,81 @@ int sweep_overlap_run(const uint32_t *tri, const float *x, float *phi, int32_t *
     for (int c1 = 0; c1 < NC; ++c1) missing += !done1[c1];
     free(done0); free(done1); free(pre);
     if (missing) return -1;
+    return (memcmp(phi, ref_phi, sizeof(float) * V) || memcmp(ctri, ref_tri, 4 * V)) ? 1 : 0;
+}
+
+/* ---- emulation of the fused launch (k_sweep_columns_fused): sweeps first .. first+count-1 on the k-slab [k_lo,k_hi) ----
+ * Tickets run through the columns of the sweeps in launch order; W "CTAs" hold the W lowest untaken tickets; among them
+ * a READY column is picked (the highest ticket first: the most eager overlap) and run atomically.  Ready = in-sweep
+ * left / down / diagonal columns complete + the prerequisites of prereq_device() complete in the PREVIOUS sweep's
+ * progress array; the arrays are double-buffered by launch-relative parity exactly like the device's.  Checks: no
+ * deadlock, the buffer-reuse invariant (when a column of sweep q+2 runs, sweep q is complete everywhere), and the result
+ * against the serial sweeps restricted to the slab (halo planes frozen).  Returns 0 ok, 1 differs, -1 deadlock,
+ * -2 invariant violated, -3 a sweep has nothing to update (the device declines to fuse). */
+static void run_column_sp(const G *g, const SP *p, int EJ, int EK, int J, int K)
+{
+    for (int rk = p->rk_first + K * EK; rk < p->rk_first + (K + 1) * EK && rk <= p->rk_last; ++rk)
+        for (int rj = 1 + J * EJ; rj < 1 + (J + 1) * EJ && rj < g->nj; ++rj)
+            for (int ri = 1; ri < g->ni; ++ri)
+                relax(g, p->di > 0 ? ri : g->ni - 1 - ri, p->dj > 0 ? rj : g->nj - 1 - rj, p->dk > 0 ? rk : g->nk - 1 - rk, p->di, p->dj, p->dk);
+}
+
+int fused_emulation_run(const uint32_t *tri, const float *x, float *phi, int32_t *ctri, float *ref_phi, int32_t *ref_tri,
+                        const float origin[3], float dx, int ni, int nj, int nk, int k_lo, int k_hi, int EJ, int EK,
+                        int first, int count, int W, int64_t *early_out)
+{
+    const int64_t V = (int64_t)ni * nj * nk;
+    G g = { ni, nj, nk, dx, { origin[0], origin[1], origin[2] }, tri, x, ref_phi, ref_tri, k_lo, k_hi };
+    SP sp[8]; int begin[9]; begin[0] = 0;
+    if (count < 2 || count > 8) return -3;
+    for (int q = 0; q < count; ++q) { sp[q] = sweep_params(&g, first + q, EJ, EK); if (!sp[q].ok) return -3; begin[q + 1] = begin[q] + sp[q].NJ * sp[q].NK; }
+    /* serial reference on the slab */
+    memcpy(ref_phi, phi, sizeof(float) * V); memcpy(ref_tri, ctri, 4 * V);
+    for (int q = 0; q < count; ++q)
+        for (int rk = sp[q].rk_first; rk <= sp[q].rk_last; ++rk) for (int rj = 1; rj < nj; ++rj) for (int ri = 1; ri < ni; ++ri)
+            relax(&g, sp[q].di > 0 ? ri : ni - 1 - ri, sp[q].dj > 0 ? rj : nj - 1 - rj, sp[q].dk > 0 ? rk : nk - 1 - rk, sp[q].di, sp[q].dj, sp[q].dk);
+    g.phi = phi; g.ctri = ctri;
+    int stride = 0;
+    for (int q = 0; q < count; ++q) if (sp[q].NJ * sp[q].NK > stride) stride = sp[q].NJ * sp[q].NK;
+    uint32_t *flags = calloc((size_t)2 * stride, 4);            /* epoch*2+1 = complete */
+    int *completed = calloc(count, sizeof(int));
+    int total = begin[count], next_ticket = 0, ntaken = 0, *taken = malloc(sizeof(int) * W), ndone = 0, rc = 0;
+    int64_t early = 0;
+    while (ndone < total && rc == 0) {
+        while (ntaken < W && next_ticket < total) taken[ntaken++] = next_ticket++;
+        int pick = -1;
+        for (int t = 0; t < ntaken; ++t) {
+            int tk = taken[t], q = 0; while (tk >= begin[q + 1]) ++q;
+            const SP *P = &sp[q];
+            int loc = tk - begin[q], J, K, d = 0, rem = loc;
+            for (;;) { int lo = d - (P->NK - 1) > 0 ? d - (P->NK - 1) : 0, hi = d < P->NJ - 1 ? d : P->NJ - 1, cnt = hi - lo + 1; if (rem < cnt) { J = lo + rem; K = d - J; break; } rem -= cnt; ++d; }
+            const uint32_t *fl = flags + (q & 1) * stride, mine = (uint32_t)(first + q + 1) * 2 + 1;
+            int ok = 1;
+            if (J > 0 && fl[K * P->NJ + J - 1] < mine) ok = 0;
+            if (K > 0 && fl[(K - 1) * P->NJ + J] < mine) ok = 0;
+            if (ok && q > 0) {
+                const SP *Q = &sp[q - 1];
+                const uint32_t *pf = flags + ((q - 1) & 1) * stride, need = (uint32_t)(first + q) * 2 + 1;
+                int Ja, Jb, Ka, Kb;
+                if (prereq_device(&g, P, Q, EJ, EK, J, K, &Ja, &Jb, &Ka, &Kb))
+                    for (int Kq = Ka; Kq <= Kb && ok; ++Kq) for (int Jq = Ja; Jq <= Jb; ++Jq) if (pf[Kq * Q->NJ + Jq] < need) { ok = 0; break; }
+            }
+            if (ok && (pick < 0 || taken[t] > taken[pick])) pick = t;
+        }
+        if (pick < 0) { rc = -1; break; }
+        int tk = taken[pick], q = 0; while (tk >= begin[q + 1]) ++q;
+        const SP *P = &sp[q];
+        int loc = tk - begin[q], J, K, d = 0, rem = loc;
+        for (;;) { int lo = d - (P->NK - 1) > 0 ? d - (P->NK - 1) : 0, hi = d < P->NJ - 1 ? d : P->NJ - 1, cnt = hi - lo + 1; if (rem < cnt) { J = lo + rem; K = d - J; break; } rem -= cnt; ++d; }
+        if (q >= 2 && completed[q - 2] != sp[q - 2].NJ * sp[q - 2].NK) { rc = -2; break; }       /* buffer-reuse invariant */
+        if (q >= 1 && completed[q - 1] != sp[q - 1].NJ * sp[q - 1].NK) ++early;
+        run_column_sp(&g, P, EJ, EK, J, K);
+        flags[(q & 1) * stride + K * P->NJ + J] = (uint32_t)(first + q + 1) * 2 + 1;
+        ++completed[q]; ++ndone;
+        taken[pick] = taken[--ntaken];
+    }
+    if (early_out) *early_out = early;
+    free(flags); free(completed); free(taken);
+    if (rc) return rc;
     return (memcmp(phi, ref_phi, sizeof(float) * V) || memcmp(ctri, ref_tri, 4 * V)) ? 1 : 0;
 }
