@@ -1,8 +1,8 @@
 // sdfb_sweep_columns.cu -- the production sweep schedule: pipelined columns.
 //
 // One launch per sweep direction (k_sweep_columns), or the whole first pass in one launch with consecutive sweeps
-// overlapping where their directions allow it (k_sweep_columns_fused, near the end of this file).  In sweep-relative coordinates (ri,rj,rk >= 0, counted from the
-// corner the sweep starts at) the (rj,rk) plane is cut into columns of EJ x EK rows.  A CTA owns one
+// overlapping where their directions allow it (k_sweep_columns_fused, near the end of this file).
+// In sweep-relative coordinates (ri,rj,rk >= 0, counted from the corner the sweep starts at) the (rj,rk) plane is cut into columns of EJ x EK rows.  A CTA owns one
 // column at a time and marches along i: lane (a,b) of the column handles voxel ri = s - a - b - 2 at step
 // s, so lanes are skewed along the anti-diagonal and every one of the seven upstream neighbours
 // (cpu_lib/makelevelset3.cpp:143-149) was produced 1..3 steps earlier by lane (a-1|a, b-1|b):
