@@ -2,6 +2,10 @@
 # Bench and parity-check alternative builds of libsdfb.so (sdfgen_b200/variants/libsdfb_<name>.so, built with other
 # -D options) on the GPU box: device-resident bench leg for each, then the core parity tests for each (in parallel).
 # usage: tools/variant_sweep.sh name1 name2 ...   (results under gpurun_out/variants/)
+# Build a variant first (in the container; the .so travels with the snapshot, it is git-ignored):
+#   cd sdfgen_b200/csrc && mkdir -p ../variants && nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+#     -fmad=false -Xcompiler -fPIC,-Wall,-pthread -shared -cudart static -DSDFB_QATOMIC=1 -o ../variants/libsdfb_qa.so *.cu
+# PARITY_K overrides the pytest -k expression of the parity leg.
 set -u
 cd "$(dirname "$0")/.."
 out=gpurun_out/variants; mkdir -p $out
