@@ -866,6 +866,11 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     if (occ < 1) occ = 1;
     int grid = sms * occ;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    // small grids: a sweep has fewer columns than the device has CTA slots, and CTAs beyond that would only sit on
+    // tickets of later sweeps and poll; keep a quarter more than one sweep can use so that the next sweep starts at once
+    int maxcols = 0;
+    for (int q = 0; q < count; ++q) maxcols = max(maxcols, FP.p[q].NJ * FP.p[q].NK);
+    if (grid > maxcols + maxcols / 4 + 1) grid = maxcols + maxcols / 4 + 1;
     if (grid > FP.col_begin[count]) grid = FP.col_begin[count];
     kern<<<grid, NTHREADS, 0, st>>>(cells, rec, FP, progress + 4, progress, changed);
     return 1;
