@@ -10,9 +10,11 @@ synthetic mesh/grid.  At N=1 the workload is BASELINE configs[2] (1,310,720-tria
 (launched by torch.distributed.run); see sdfgen_b200/dist.py.
 
 value  = voxels / device time with the mesh already resident in HBM and phi left in HBM
-e2e    = same metric through the C ABI with HOST buffers: pinned mesh H2D + run + phi D2H every step
+e2e    = same metric through the drop-in C-ABI call (sdfb_make_level_set3, the slot of sdfgen::gpu::make_level_set3):
+         pageable host mesh in, pageable host phi out, plan creation + H2D + kernels + D2H inside every timed call
 --impl reference times the reference's own multi-threaded CPU implementation (oracle/_ref, compiled in
-place from /root/reference) on a bounded sample of the same workload.
+place from /root/reference) on the SAME configuration at N=1 (full 512^3; as many steps as fit a time budget, at
+least one), and on a stated bounded sample of the 1024^3 workload at N>1.
 """
 from __future__ import annotations
 
@@ -32,7 +34,9 @@ import numpy as np  # noqa: E402
 
 METRIC = "sdf_gvoxels_per_s"
 UNIT = "Gvoxel/s"
-CPU_SAMPLE_GRID = 160            # bounded CPU sample: same mesh on a 160^3 grid
+CPU_BUDGET_S = 150.0             # the reference arm stops starting new steps after this many seconds
+CPU_SAMPLE_GRID_MULTI = 384      # N > 1 (1024^3 torus): bounded sample = the same mesh on a 384^3 grid
+INSTR_PER_EVAL = 190             # SASS instructions of one point_triangle_distance evaluation (cuobjdump of ptd_rec)
 
 
 def measured_peaks():
@@ -50,11 +54,12 @@ def measured_traffic():
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
     if not files:
-        return None
+        return None, None
     try:
-        return float(json.load(open(files[-1]))["per_launch_bytes_mean"])
+        d = json.load(open(files[-1]))
+        return float(d["per_launch_bytes_mean"]), os.path.basename(files[-1]) + ": " + d.get("kernel", "")
     except Exception:
-        return None
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -99,57 +104,58 @@ def build_workload(name, grid):
 
 
 def cpu_reference_run(w, n, threads):
-    """One timed run of the reference CPU path on the mesh of workload w, on the same domain at n cells per
-    unit length (n x n x n*copies for the stacked multi-GPU workload)."""
+    """One timed run of the reference CPU path on the mesh of workload w, on the same domain at n cells per edge."""
     import oracle
     L = 1.0
-    copies = max(1, w["nk"] // w["ni"])
     dx = np.float32(L / n)
     origin = (np.float32(-0.5 * L) + np.float32(0.37) * dx) * np.ones(3, np.float32)
     kind = "reference" if oracle.have_ref() else "port"
     t0 = time.perf_counter()
     if kind == "reference":
-        oracle.ref.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n * copies, 1, num_threads=threads)
+        oracle.ref.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n, 1, num_threads=threads)
     else:
-        oracle.port.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n * copies, 1)
+        oracle.port.make_level_set3(w["vertices"], w["triangles"], origin, float(dx), n, n, n, 1)
     dt = time.perf_counter() - t0
-    return dt, kind, n * n * n * copies
+    return dt, kind, n * n * n
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only), on a bounded
-    sample of the same workload; stops early when the time budget is used up (reports the steps it timed)."""
+    """--impl reference: the reference's own CPU implementation (sdfgen::cpu::make_level_set3, num_threads=0 = all host
+    threads) on the host cores, rank 0 only.  N=1: the GPU arm's own configuration, full size (C2: 512^3, 1.31 M
+    triangles) -- no warm-up run and as many timed steps as fit CPU_BUDGET_S, at least one (a step takes minutes).
+    N>1: the GPU arm's mesh (C3 torus) on a 384^3 grid, a bounded sample of the 1024^3 workload, named as such."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import oracle
-    from sdfgen_b200 import meshes
-    w = build_workload(args.workload, args.grid) if args.gpus == 1 else meshes.stacked_workload(args.gpus, n=args.grid or 512)
-    n = min(CPU_SAMPLE_GRID, w["ni"])
+    multi = args.gpus > 1
+    name = args.workload if (args.workload and not (multi and args.workload == "c2_icosphere_512")) else ("c3_torus_1024" if multi else "c2_icosphere_512")
+    w = build_workload(name, args.grid)
+    n = min(CPU_SAMPLE_GRID_MULTI, w["ni"]) if multi else w["ni"]
+    same = n == w["ni"]
     kind = "reference" if oracle.have_ref() else "port"
     cores = oracle.ref.hardware_concurrency() if kind == "reference" else 1
-    budget_s, t_start = 150.0, time.perf_counter()
-    warm = max(0, min(args.warmup, 1))
-    for _ in range(warm):
-        cpu_reference_run(w, n, 0)
+    t_start = time.perf_counter()
     times, vox = [], 0
-    for _ in range(args.steps):
+    for _ in range(max(1, args.steps)):
         dt, kind, vox = cpu_reference_run(w, n, 0)
         times.append(dt)
-        if time.perf_counter() - t_start + dt > budget_s:
+        if time.perf_counter() - t_start + dt > CPU_BUDGET_S:
             break
     total = sum(times)
     value = vox * len(times) / total / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(times),
-        "warmup": warm, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": 0, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong" if multi else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "triangles": int(w["triangles"].shape[0]), "grid": [w["ni"], w["nj"], w["nk"]],
-                   "exact_band": 1, "sample_grid": [n, n, n * max(1, w["nk"] // w["ni"])]},
+        "config": {"workload": w["name"], "triangles": int(w["triangles"].shape[0]), "vertices": int(w["vertices"].shape[0]),
+                   "grid": [n, n, n], "exact_band": 1, "sweeps": 16, "same_config_as_gpu_arm": same,
+                   "gpu_arm_grid": [w["ni"], w["nj"], w["nk"]]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"same mesh and domain at {n} cells per unit length per step (bounded sample of the "
-                                   f"{w['ni']}x{w['nj']}x{w['nk']} workload), sdfgen::cpu::make_level_set3 num_threads=0 "
-                                   f"(auto), wall clock; {len(times)} of {args.steps} requested steps fit the time budget"},
+                         "sample": (f"the GPU arm's configuration at full size ({n}^3)" if same else
+                                    f"the GPU arm's mesh on a {n}^3 grid: a bounded sample of the {w['ni']}^3 workload") +
+                                   f", sdfgen::cpu::make_level_set3 num_threads=0 (auto), wall clock, no warm-up; "
+                                   f"{len(times)} of {args.steps} requested steps fit the {CPU_BUDGET_S:.0f} s budget"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,12 +173,11 @@ def run_single_gpu(args):
     w = build_workload(args.workload, args.grid)
     ni, nj, nk = w["ni"], w["nj"], w["nk"]
     V, T, NV = ni * nj * nk, int(w["triangles"].shape[0]), int(w["vertices"].shape[0])
-    flags = {"default": 0, "columns": _lib.SWEEP_COLUMNS, "relax": _lib.SWEEP_RELAX, "strips": _lib.SWEEP_STRIPS,
-             "levels": _lib.SWEEP_LEVELS}[args.schedule]
+    flags = {"default": 0, "columns": _lib.SWEEP_COLUMNS, "relax": _lib.SWEEP_RELAX, "levels": _lib.SWEEP_LEVELS}[args.schedule]
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
 
-    # pinned host staging for the e2e leg, device-resident mesh for the kernel leg
+    # pinned host staging for the streaming e2e legs, device-resident mesh for the kernel leg
     tri_pin = torch.from_numpy(w["triangles"].astype(np.uint32).view(np.int32)).pin_memory()
     xyz_pin = torch.from_numpy(w["vertices"]).pin_memory()
     phi_pin = torch.empty(V, dtype=torch.float32).pin_memory()
@@ -183,7 +188,7 @@ def run_single_gpu(args):
     plan.set_mesh_device(d_tri.data_ptr(), T, d_xyz.data_ptr(), NV, stream=sh, keepalive=(d_tri, d_xyz))
 
     # one step = band, first pass of 8 sweeps, second pass of 8 sweeps, sign; events between the phases time the
-    # two sweep kernels separately (they sit on the launching stream, inside the timed region)
+    # two sweep passes separately (they sit on the launching stream, inside the timed region)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def device_step(ev=None):
@@ -197,6 +202,14 @@ def run_single_gpu(args):
 
     for _ in range(args.warmup):
         device_step()
+    torch.cuda.synchronize()
+    # distance evaluations of the first pass (column schedule counter), for the issue roofline: one untimed step
+    plan.band(w["origin"], w["dx"], 1, stream=sh)
+    plan.counters(stream=sh)
+    plan.sweep(0, 8, stream=sh)
+    _, evals_pass1 = plan.counters(stream=sh)
+    plan.sweep(8, 8, stream=sh)
+    plan.sign(stream=sh)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(0)
@@ -220,17 +233,39 @@ def run_single_gpu(args):
         phase[k] /= args.steps
     pass1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     pass2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    chk = plan.verify(stream=sh)      # untimed: every cell holds exactly the distance to the triangle it names
 
     e2e = None
     concurrent = None
     if args.no_e2e:                                            # profiling runs (ncu launch list): the device leg only
         plan.download(phi=True, stream=sh, phi_out=phi_pin.data_ptr())
     else:
-        # e2e: pinned host mesh -> H2D -> run -> D2H phi (pinned), every step, through the C ABI.
-        # (a) blocking: one call after the other, as sdfgen::gpu::make_level_set3 is used (latency of a call);
-        # (b) streaming: the D2H copy of step i runs on a copy stream and overlaps the H2D + kernels of step i+1
-        #     (sdfb_plan_download_phi_async, two pinned output buffers) -- every step still moves all its bytes inside
-        #     the timed region; this is the throughput of a stream of requests and the figure reported as e2e.value.
+        # e2e, headline: the drop-in call itself, as a caller of sdfgen::gpu::make_level_set3 would use it -- pageable
+        # host mesh, a FRESH pageable output array per call, blocking; plan creation, H2D, kernels, D2H and release are
+        # all inside the timed region (sdfb_make_level_set3 through sdfgen_b200.generate_sdf_debug's code path).
+        lib = _lib.lib()
+        tri_np = np.ascontiguousarray(w["triangles"], np.uint32)
+        xyz_np = np.ascontiguousarray(w["vertices"], np.float32)
+        org_np = np.ascontiguousarray(w["origin"], np.float32)
+
+        def drop_in_call():
+            out = np.empty(V, np.float32)                       # untouched pageable memory, as Array3f::resize yields
+            _lib.check(lib.sdfb_make_level_set3(tri_np.ctypes.data, T, xyz_np.ctypes.data, NV, org_np.ctypes.data, float(w["dx"]),
+                                                ni, nj, nk, 1, out.ctypes.data, None, None, flags))
+            return out
+
+        for _ in range(2):
+            out = drop_in_call()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = drop_in_call()
+        e2e_dropin_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        phi_dropin = out
+
+        # extras: (a) blocking call on a REUSED plan with pinned buffers; (b) a stream of requests on one plan (the D2H of
+        # step i overlaps step i+1); (c) the same alternating between two plans in flight.  Every step still moves all
+        # its bytes inside the timed region.
         def e2e_step():
             plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=sh)
             plan.run(w["origin"], w["dx"], 1, stream=sh)
@@ -239,14 +274,11 @@ def run_single_gpu(args):
         e2e_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for _ in range(args.steps):
-                e2e_step()
-            ev1.record(stream)
+        for _ in range(args.steps):
+            e2e_step()
         torch.cuda.synchronize()
-        e2e_wall = (time.perf_counter() - t0) / args.steps
-        e2e_blocking_ms = max(ev0.elapsed_time(ev1) / args.steps, 1e3 * e2e_wall)
+        e2e_blocking_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+        assert np.array_equal(phi_dropin.view(np.uint32), phi_pin.numpy().view(np.uint32))
 
         copy_stream = torch.cuda.Stream()
         phi_pin2 = torch.empty(V, dtype=torch.float32).pin_memory()
@@ -267,10 +299,6 @@ def run_single_gpu(args):
         e2e_one_plan_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert torch.equal(phi_pin, phi_pin2)                      # both buffers hold the same field
 
-        # (c) streaming with TWO plans in flight (sdfb_plan_set_concurrency(2): each plan's sweep kernels take half the
-        #     SMs, the plans run on their own streams): the sweeps are latency-bound, so two grids side by side finish
-        #     sooner than one after the other.  Requests alternate between the plans; every request still uploads its mesh
-        #     and downloads its field inside the timed region.  First the same thing device-resident, for reference.
         plan2 = _lib.Plan(ni, nj, nk, flags=flags)
         stream2 = torch.cuda.Stream()
         plans, streams = (plan, plan2), (stream, stream2)
@@ -305,42 +333,49 @@ def run_single_gpu(args):
         e2e_two_plans_ms = 1e3 * (time.perf_counter() - t0) / args.steps
         assert torch.equal(phi_pin, phi_pin2)
         plan2.close()
-        e2e_ms = min(e2e_one_plan_ms, e2e_two_plans_ms)
-        e2e_mode = ("streaming, two plans in flight: requests alternate between two plans on their own streams (each plan's sweep kernels take half "
-                    "the SMs); the D2H copy of a request (copy stream, pinned) overlaps the H2D + kernels of the following ones; host wall clock over the timed steps"
-                    if e2e_two_plans_ms < e2e_one_plan_ms else
-                    "streaming: host wall clock over the timed steps; the D2H copy of step i (copy stream, pinned) overlaps the H2D + kernels of step i+1")
-        e2e = {"value": V / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+        gv = lambda ms: V / (ms * 1e-3) / 1e9
+        e2e = {"value": gv(e2e_dropin_ms), "unit": UNIT, "ms_per_step": e2e_dropin_ms,
                "h2d_bytes_per_step": 12 * T + 12 * NV, "d2h_bytes_per_step": 4 * V,
-               "mode": e2e_mode,
-               "one_plan_streaming_ms": e2e_one_plan_ms, "one_plan_streaming_value": V / (e2e_one_plan_ms * 1e-3) / 1e9,
-               "two_plans_streaming_ms": e2e_two_plans_ms, "two_plans_streaming_value": V / (e2e_two_plans_ms * 1e-3) / 1e9,
-               "blocking_call_ms": e2e_blocking_ms, "blocking_call_value": V / (e2e_blocking_ms * 1e-3) / 1e9}
-        concurrent = {"plans": 2, "ms_per_grid": two_plans_ms, "value": V / (two_plans_ms * 1e-3) / 1e9, "unit": UNIT,
+               "mode": "the blocking drop-in call sdfb_make_level_set3 (slot of sdfgen::gpu::make_level_set3): pageable numpy mesh in, a "
+                       "fresh pageable numpy phi out, plan creation + H2D + kernels + D2H + release inside every timed call; host wall clock",
+               "reused_plan_blocking_ms": e2e_blocking_ms, "reused_plan_blocking_value": gv(e2e_blocking_ms),
+               "one_plan_streaming_ms": e2e_one_plan_ms, "one_plan_streaming_value": gv(e2e_one_plan_ms),
+               "two_plans_streaming_ms": e2e_two_plans_ms, "two_plans_streaming_value": gv(e2e_two_plans_ms)}
+        concurrent = {"plans": 2, "ms_per_grid": two_plans_ms, "value": gv(two_plans_ms), "unit": UNIT,
                       "note": "device-resident, two independent grids in flight on one GPU; `value` above is one grid at a time"}
     clocks = sampler.stop()
     inside = int((phi_pin < 0).sum())
     plan.close()
 
     peak, peak_src = measured_peaks()
-    # dominant kernel: the wavefront sweep of the first pass (8 launches per step; with --schedule columns/strips/levels
-    # the same kernel also runs the second pass)
+    # dominant kernel: the wavefront sweep of the first pass (one fused launch of 8 sweeps per step; with --schedule
+    # columns/levels the same kernel also runs the second pass)
     sweep_launch_ms = pass1_ms / 8
     algo_bytes_sweep = 16.0 * V                               # 8 B read + 8 B write per voxel per sweep
     achieved = algo_bytes_sweep / (sweep_launch_ms * 1e-3) / 1e9
     path_bytes = 280.0 * V + 36.0 * T
     path_achieved = path_bytes / (phase["total"] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic()
+    # the roof that actually binds the sweeps: fp32 instruction issue of the distance evaluations
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    issue_peak = sms * 4 * sm_mhz * 1e6                       # warp instructions per second, 4 schedulers per SM
+    issue_ms = evals_pass1 * INSTR_PER_EVAL / 32.0 / issue_peak * 1e3
+    issue = {"evals_per_voxel_first_pass": evals_pass1 / V, "instr_per_eval": INSTR_PER_EVAL,
+             "peak_warp_instr_per_s": issue_peak, "bound_ms_first_pass": issue_ms, "measured_ms_first_pass": pass1_ms,
+             "frac": issue_ms / pass1_ms,
+             "note": "time the first pass's distance evaluations alone would take at 100 % instruction issue on every SM, over the measured first pass"}
 
     cpu = None
     if not args.no_cpu_baseline:
         import oracle
-        n = min(CPU_SAMPLE_GRID, ni)
-        dt, kind, vox = cpu_reference_run(w, n, 0)
+        dt, kind, vox = cpu_reference_run(w, ni, 0)
         cores = oracle.ref.hardware_concurrency() if kind == "reference" else 1
         cpu = {"value": vox / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"same mesh on a {n}^3 grid, one run ({dt:.1f} s), sdfgen::cpu::make_level_set3 "
-                         f"num_threads=0 (auto) built in place from the reference sources"}
+               "sample": f"the same configuration at full size ({ni}^3, {T} triangles), one run ({dt:.1f} s), "
+                         f"sdfgen::cpu::make_level_set3 num_threads=0 (auto) built in place from the reference sources"}
 
+    fused = args.schedule == "default" and os.environ.get("SDFB_FUSE_PASS") != "0"
     line = {
         "metric": METRIC, "value": V / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -348,12 +383,12 @@ def run_single_gpu(args):
         "config": {"workload": w["name"], "triangles": T, "vertices": NV, "grid": [ni, nj, nk], "exact_band": 1,
                    "sweeps": 16, "schedule": args.schedule, "l2": "grid state (12 B/voxel + 4 B/voxel output) is far larger than the 126 MB L2; no flush needed",
                    "phase_ms": phase, "sweep_pass_ms": {"first_pass_8_sweeps": pass1_ms, "second_pass_8_sweeps": pass2_ms},
-                   "inside_voxels": inside},
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_columns_fused (first pass: the 8 direction sweeps in one launch, consecutive sweeps overlapping; launch_ms and the bytes are per sweep = launch / 8)" if args.schedule == "default" and os.environ.get("SDFB_FUSE_PASS") != "0" else "k_sweep_columns (first pass: one launch per direction, 8 per step)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(), "peak_source": peak_src,
+                   "inside_voxels": inside, "inconsistent_cells": chk["inconsistent"], "checksum_values": f"{chk['checksum_values']:016x}"},
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_columns_fused (first pass: the 8 direction sweeps in one launch, consecutive sweeps overlapping; launch_ms and the bytes are per sweep = launch / 8)" if fused else "k_sweep_columns (first pass: one launch per direction, 8 per step)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes_sweep, "launch_ms": sweep_launch_ms,
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak,
-                     "path_algorithmic_bytes": path_bytes},
+                     "path_algorithmic_bytes": path_bytes, "issue": issue},
         "cpu_baseline": cpu,
         "e2e": e2e,
         "concurrent": concurrent,
@@ -372,14 +407,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--grid", type=int, default=None, help="override the grid edge (debug / down-scaled twin)")
-    ap.add_argument("--schedule", default="default", choices=["default", "columns", "relax", "strips", "levels"])
-    ap.add_argument("--exact", action="store_true",
-                    help="N > 1: also time the exact multi-GPU mode (serial sweep order kept across slabs, dist.run_sharded_exact)")
+    ap.add_argument("--schedule", default="default", choices=["default", "columns", "relax", "levels"])
+    ap.add_argument("--exact", action="store_true", help="accepted for compatibility: N > 1 always runs the exact (linked) mode")
+    ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the 2048^3 configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for the ncu launch list)")
     args = ap.parse_args()
     if args.workload is None:
-        args.workload = "c2_icosphere_512"      # N > 1 uses meshes.stacked_workload(N): one C2 block per GPU
+        args.workload = "c2_icosphere_512"      # N > 1 uses c3_torus_1024 (and c4_mix_2048 on 8 GPUs), see dist.bench_main
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

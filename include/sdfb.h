@@ -53,7 +53,7 @@ extern "C" {
  * fixed-point relaxation for every later sweep (almost nothing changes).  The flags force one schedule for
  * all sweeps (cross-checks and experiments). */
 #define SDFB_SWEEP_LEVELS       0x2u  /* one launch per anti-diagonal level (slow, trivially exact)         */
-#define SDFB_SWEEP_STRIPS       0x8u  /* warp pipelines without CTA-wide barriers (experimental)            */
+#define SDFB_SWEEP_STRIPS       0x8u  /* retired experiment of round 1: plans created with it are refused   */
 #define SDFB_SWEEP_RELAX        0x10u /* fixed-point relaxation for every sweep                             */
 #define SDFB_SWEEP_COLUMNS      0x20u /* pipelined columns for every sweep                                  */
 #define SDFB_NO_SIGN            0x4u  /* stop before the sign pass (phi stays unsigned)              */
@@ -140,7 +140,9 @@ int sdfb_plan_set_mesh_device(sdfb_plan *plan, const uint32_t *d_tri, uint64_t n
 /* Phase A: init + exact band + crossing counts (cpu_lib/makelevelset3.cpp:196-236). Asynchronous. */
 int sdfb_plan_band(sdfb_plan *plan, const float origin[3], float dx, int32_t exact_band, void *stream);
 /* Phase B: sweeps first..first+count-1 of the reference's 16 (index s uses direction s%8 of
- * cpu_lib/makelevelset3.cpp:245-248).  Asynchronous.  Halo planes, if the slab has neighbours, must
+ * cpu_lib/makelevelset3.cpp:245-248).  Asynchronous.  Sweeps must be run in order since the last sdfb_plan_band:
+ * `first` may repeat an index already run but not skip one (SDFB_ERR_STATE) -- the candidate memo relies on every
+ * earlier sweep having examined the cells.  Halo planes, if the slab has neighbours and is not linked, must
  * have been filled by the caller (sdfb_plan_device_ptrs + sdfb_plan_halo_refresh) before each call. */
 int sdfb_plan_sweep(sdfb_plan *plan, int32_t first, int32_t count, void *stream);
 /* Phase C: parity sign + unpack to the float output (cpu_lib/makelevelset3.cpp:295-303). Asynchronous. */
@@ -166,6 +168,17 @@ int sdfb_plan_changed(sdfb_plan *plan, void *stream, uint64_t *changed);
  * out[0] = changed cells.  Both counters are reset. */
 int sdfb_plan_counters(sdfb_plan *plan, void *stream, uint64_t out[2]);
 
+/* Verification on the device (blocking), for grids no CPU reference can check in reasonable time or at all (the
+ * reference's int index overflows at 2^31 voxels, common/array3.h:59-61):
+ *   out[0] = cells of the slab whose distance is NOT bit-identical to point_triangle_distance(voxel, the triangle the
+ *            cell names) (cpu_lib/makelevelset3.cpp:49-70), or whose distance is not the initial one although no triangle
+ *            was assigned -- 0 for any correct state after band or sweeps;
+ *   out[1] = cells without a triangle;
+ *   out[2] = order-independent checksum (sum mod 2^64 of a hash of global voxel index and cell word) of the slab: the
+ *            slabs of a sharded run add up to the checksum of one plan on the whole grid iff all cells are identical;
+ *   out[3] = the same over (distance, triangle) only, without the sweep stamps. */
+int sdfb_plan_verify(sdfb_plan *plan, void *stream, uint64_t out[4]);
+
 /* Blocking copies of the slab results to host memory (any may be NULL).  phi is the output of
  * sdfb_plan_sign (or the unsigned cell phi if the sign pass has not run). */
 int sdfb_plan_download(sdfb_plan *plan, float *phi_out, int32_t *closest_tri_out,
@@ -187,6 +200,48 @@ int sdfb_plan_download_phi_async(sdfb_plan *plan, float *phi_out, void *copy_str
  * inside_count_out may be NULL.  Blocking. */
 int sdfb_plan_write_sdf(sdfb_plan *plan, const char *path, const float min_box[3], float dx,
                         int64_t *inside_count_out, void *stream);
+
+/* ---- several GPUs: k-slabs whose sweeps keep the reference's serial order across the slab faces ------------------
+ *
+ * The reference is single-device; its README lists multi-GPU as future work (README.md:220).  A
+ * sweep reads only k offsets 0 and -dk (cpu_lib/makelevelset3.cpp:143-149), so the grid is cut into contiguous k-slabs,
+ * one plan per GPU, and each slab's last plane is handed to the next slab column by column WHILE the sweep runs (peer
+ * stores over NVLink + system-scope flags inside the sweep kernel; no host synchronisation, no collective).  The result
+ * is bit-identical to one plan on the whole grid.  Phases A and C are slab-local (x-rays run along i).
+ *
+ * One process driving all GPUs: sdfb_make_level_set3_multi.  One process per GPU (torch.distributed / MPI style):
+ * every rank creates its slab's plan, calls sdfb_plan_link_export, sends the SDFB_LINK_HANDLE_BYTES bytes to the ranks
+ * holding the slabs below and above (any transport), imports theirs with sdfb_plan_link_import, and from then on runs
+ *     sdfb_plan_band -> sdfb_plan_sweep(plan, 0, 16) -> sdfb_plan_sign
+ * in lockstep with the other ranks (same number of band calls on every slab; the device-side waits carry a watchdog,
+ * SDFB_LINK_TIMEOUT_S, default 20 s, after which the kernel traps instead of hanging).  Linked plans always use the
+ * column schedule.  Slabs that touch the grid's first or last plane need at least 2 planes.
+ */
+#define SDFB_LINK_HANDLE_BYTES 128
+
+/* Contiguous k range of slab `index` of `slabs` (the first nk % slabs slabs get one extra plane). */
+int sdfb_slab_bounds(int32_t nk, int32_t slabs, int32_t index, int32_t *k_lo, int32_t *k_hi);
+/* Allocates this plan's inbound hand-over buffers (16 planes of cells + flags, cudaMalloc) and writes an opaque handle
+ * (CUDA IPC handle + slab geometry) to handle_out[SDFB_LINK_HANDLE_BYTES]. */
+int sdfb_plan_link_export(sdfb_plan *plan, void *handle_out);
+/* Maps the inbound buffers of the plan that holds the neighbouring slab: side 0 = the slab below (its k_hi == this
+ * k_lo), 1 = the slab above.  Works across processes (cudaIpcOpenMemHandle) and inside one (peer access is enabled
+ * when the devices differ; two slabs may also share a device: then cap their grids with sdfb_plan_set_concurrency). */
+int sdfb_plan_link_import(sdfb_plan *plan, int32_t side, const void *handle);
+/* Drops all links (waits for the plan's device first).  Every rank must have finished its last run before any rank
+ * unlinks or destroys a linked plan: a neighbour's sweep kernel stores into this plan's buffers. */
+int sdfb_plan_unlink(sdfb_plan *plan);
+/* sdfb_plan_download into arrays of the WHOLE grid: the slab is written at its place (either layout). */
+int sdfb_plan_download_global(sdfb_plan *plan, float *phi_grid, int32_t *closest_tri_grid,
+                              int32_t *intersection_count_grid, void *stream);
+/* sdfb_make_level_set3 on num_gpus devices (0 = all usable) of the calling process, devices 0 .. num_gpus-1.  Same
+ * arguments, same results bit for bit; the SURVEY's proposed `num_gpus` parameter of the C entry
+ * (gpu_lib/makelevelset3_gpu.h:40-42 has no such notion).  Falls back to one device for grids with fewer than 2 planes
+ * per device. */
+int sdfb_make_level_set3_multi(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
+                               const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
+                               int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
+                               int32_t *intersection_count_out, int32_t num_gpus, uint32_t flags);
 
 /* Device time of the phases of the last completed run, in ms: out[0]=band (init+records+band+counts),
  * out[1]=sweeps, out[2]=sign/unpack, out[3]=total.  Blocks until the work has finished. */

@@ -35,6 +35,12 @@ inline bool is_gpu_available() { return sdfb_device_count() > 0; }
 
 namespace gpu {
 
+// Not in the reference (it is single-device, README.md:220 lists multi-GPU as future work): number of GPUs of this
+// process the grid is cut over, k-slabs with the sweeps' serial order kept across the faces (sdfb_make_level_set3_multi,
+// bit-identical results).  1 = one device (default), 0 = all usable devices.  The reference's signature has no room for
+// it, so it is a process-wide setting: sdfgen::gpu::num_gpus() = 8;
+inline int& num_gpus() { static int n = 1; return n; }
+
 inline void make_level_set3(const std::vector<Vec3ui>& tri, const std::vector<Vec3f>& x, const Vec3f& origin, float dx,
                             int nx, int ny, int nz, Array3f& phi, const int exact_band = 1)
 {
@@ -42,9 +48,13 @@ inline void make_level_set3(const std::vector<Vec3ui>& tri, const std::vector<Ve
     if (nx <= 0 || ny <= 0 || nz <= 0) throw std::invalid_argument("Grid dimensions must be positive (nx, ny, nz > 0)");
     phi.resize(nx, ny, nz);
     const float o[3] = {origin[0], origin[1], origin[2]};
-    const int rc = sdfb_make_level_set3(reinterpret_cast<const uint32_t*>(tri.data()), tri.size(),
-                                        reinterpret_cast<const float*>(x.data()), x.size(), o, dx, nx, ny, nz, exact_band,
-                                        &phi.a[0], nullptr, nullptr, 0u);
+    const int rc = num_gpus() == 1
+        ? sdfb_make_level_set3(reinterpret_cast<const uint32_t*>(tri.data()), tri.size(),
+                               reinterpret_cast<const float*>(x.data()), x.size(), o, dx, nx, ny, nz, exact_band,
+                               &phi.a[0], nullptr, nullptr, 0u)
+        : sdfb_make_level_set3_multi(reinterpret_cast<const uint32_t*>(tri.data()), tri.size(),
+                                     reinterpret_cast<const float*>(x.data()), x.size(), o, dx, nx, ny, nz, exact_band,
+                                     &phi.a[0], nullptr, nullptr, num_gpus(), 0u);
     if (rc == SDFB_ERR_INVALID) throw std::invalid_argument(sdfb_last_error());
     if (rc != SDFB_OK) throw std::runtime_error(std::string("sdfgen::gpu::make_level_set3: ") + sdfb_last_error());
 }

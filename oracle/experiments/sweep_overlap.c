@@ -229,3 +229,134 @@ int fused_emulation_run(const uint32_t *tri, const float *x, float *phi, int32_t
     if (rc) return rc;
     return (memcmp(phi, ref_phi, sizeof(float) * V) || memcmp(ctri, ref_tri, 4 * V)) ? 1 : 0;
 }
+
+/* ---- emulation of the LINKED multi-GPU launch (k_sweep_columns_fused<.., LINK = true> on every slab) ---------------
+ * nslabs k-slabs [kb[r], kb[r+1]) share the global cell arrays (each writes only its own planes) but read the plane
+ * below their slab (in sweep direction) ONLY from their per-sweep inbound buffer, as the device does (LinkSweep in
+ * sdfgen_b200/csrc/sdfb_kernels.cuh): a column of the last K block pushes its rows of the slab's boundary plane (plus row
+ * rj = 0 when J = 0) to the downstream slab's buffer of that sweep and then raises the per-column flag there; a column
+ * of the first K block waits for the flag of the column below it.  Every slab runs its own fused ticket sequence over
+ * sweeps 0..count-1 with W "CTA" slots and its own double-buffered progress words; a seeded random choice among ALL
+ * ready columns of ALL slabs drives the interleaving.  Checked: no deadlock, never a read of a cell that was not
+ * pushed in this sweep (buffers start poisoned), bit equality with the serial sweeps of the whole grid.
+ * Returns 0 ok, 1 differs, -1 deadlock, -2 buffer-reuse invariant, -3 a slab declines a sweep, -4 poisoned read. */
+#define POISON_TRI (-77)
+typedef struct {
+    G g; SP sp[16]; int begin[17]; uint32_t *flags; int stride; int *completed; int next_ticket, ntaken, *taken, ndone, total;
+    float *in_phi; int32_t *in_tri; uint8_t *in_flag;          /* [16][plane], [16][plane], [16][NJ] */
+} Slab;
+static int g_poison_reads;
+
+static void relax_linked(const Slab *S, int s, int i, int j, int k, int di, int dj, int dk)
+{
+    const G *g = &S->g;
+    const int64_t plane = (int64_t)g->ni * g->nj;
+    const int64_t c0 = (int64_t)i + (int64_t)g->ni * (j + (int64_t)g->nj * k);
+    float gx[3] = { i * g->dx + g->o[0], j * g->dx + g->o[1], k * g->dx + g->o[2] };
+    static const int OFF[7][3] = { {1,0,0}, {0,1,0}, {1,1,0}, {0,0,1}, {1,0,1}, {0,1,1}, {1,1,1} };
+    for (int m = 0; m < 7; ++m) {
+        int i1 = i - di * OFF[m][0], j1 = j - dj * OFF[m][1], k1 = k - dk * OFF[m][2];
+        int32_t t;
+        if (k1 < g->k_lo || k1 >= g->k_hi) {                  /* the plane below the slab: this sweep's inbound buffer */
+            t = S->in_tri[(int64_t)s * plane + i1 + (int64_t)g->ni * j1];
+            if (t == POISON_TRI) { ++g_poison_reads; continue; }
+        } else t = g->ctri[(int64_t)i1 + (int64_t)g->ni * (j1 + (int64_t)g->nj * k1)];
+        if (t >= 0) {
+            const uint32_t *tv = g->tri + 3 * (size_t)t;
+            float d = sdfo_point_triangle_distance(gx, g->x + 3 * (size_t)tv[0], g->x + 3 * (size_t)tv[1], g->x + 3 * (size_t)tv[2]);
+            if (d < g->phi[c0]) { g->phi[c0] = d; g->ctri[c0] = t; }
+        }
+    }
+}
+
+static void ticket_to_JK(const SP *P, int loc, int *J, int *K)
+{
+    int d = 0, rem = loc;
+    for (;;) { int lo = d - (P->NK - 1) > 0 ? d - (P->NK - 1) : 0, hi = d < P->NJ - 1 ? d : P->NJ - 1, cnt = hi - lo + 1; if (rem < cnt) { *J = lo + rem; *K = d - *J; return; } rem -= cnt; ++d; }
+}
+
+int linked_emulation_run(const uint32_t *tri, const float *x, float *phi, int32_t *ctri, float *ref_phi, int32_t *ref_tri,
+                         const float origin[3], float dx, int ni, int nj, int nk, int nslabs, const int32_t *kb,
+                         int EJ, int EK, int count, int W, uint32_t seed, int64_t *overlap_out)
+{
+    const int64_t V = (int64_t)ni * nj * nk, plane = (int64_t)ni * nj;
+    if (count < 1 || count > 16) return -3;
+    G gr = { ni, nj, nk, dx, { origin[0], origin[1], origin[2] }, tri, x, ref_phi, ref_tri, 0, nk };
+    memcpy(ref_phi, phi, sizeof(float) * V); memcpy(ref_tri, ctri, 4 * V);
+    for (int s = 0; s < count; ++s) serial_sweep(&gr, s);
+    Slab *S = calloc(nslabs, sizeof(Slab));
+    int rc = 0, all_total = 0, all_done = 0;
+    for (int r = 0; r < nslabs; ++r) {
+        Slab *a = &S[r];
+        G g = { ni, nj, nk, dx, { origin[0], origin[1], origin[2] }, tri, x, phi, ctri, kb[r], kb[r + 1] };
+        a->g = g; a->begin[0] = 0;
+        for (int q = 0; q < count; ++q) { a->sp[q] = sweep_params(&a->g, q, EJ, EK); if (!a->sp[q].ok) rc = -3; a->begin[q + 1] = a->begin[q] + a->sp[q].NJ * a->sp[q].NK; if (a->sp[q].NJ * a->sp[q].NK > a->stride) a->stride = a->sp[q].NJ * a->sp[q].NK; }
+        a->flags = calloc((size_t)2 * a->stride + 1, 4); a->completed = calloc(count, sizeof(int)); a->taken = malloc(sizeof(int) * W);
+        a->total = a->begin[count]; all_total += a->total;
+        a->in_phi = malloc(sizeof(float) * 16 * plane); a->in_tri = malloc(4 * 16 * plane); a->in_flag = calloc((size_t)16 * (a->sp[0].NJ + 1), 1);
+        for (int64_t c = 0; c < 16 * plane; ++c) { a->in_phi[c] = -1.f; a->in_tri[c] = POISON_TRI; }
+    }
+    g_poison_reads = 0;
+    int64_t overlap = 0;
+    uint32_t rng = seed * 2654435761u + 12345u;
+    while (rc == 0 && all_done < all_total) {
+        /* candidates: (slab, slot) pairs whose column is ready */
+        int nready = 0, pick_r = -1, pick_t = -1;
+        for (int r = 0; r < nslabs; ++r) {
+            Slab *a = &S[r];
+            while (a->ntaken < W && a->next_ticket < a->total) a->taken[a->ntaken++] = a->next_ticket++;
+            for (int t = 0; t < a->ntaken; ++t) {
+                int tk = a->taken[t], q = 0; while (tk >= a->begin[q + 1]) ++q;
+                const SP *P = &a->sp[q]; int J, K; ticket_to_JK(P, tk - a->begin[q], &J, &K);
+                const uint32_t *fl = a->flags + (q & 1) * a->stride, mine = (uint32_t)(q + 1) * 2 + 1;
+                int ok = 1;
+                if (J > 0 && fl[K * P->NJ + J - 1] < mine) ok = 0;
+                if (K > 0 && fl[(K - 1) * P->NJ + J] < mine) ok = 0;
+                if (ok && q > 0) {
+                    const SP *Q = &a->sp[q - 1];
+                    const uint32_t *pf = a->flags + ((q - 1) & 1) * a->stride, need = (uint32_t)q * 2 + 1;
+                    int Ja, Jb, Ka, Kb;
+                    if (prereq_device(&a->g, P, Q, EJ, EK, J, K, &Ja, &Jb, &Ka, &Kb))
+                        for (int Kq = Ka; Kq <= Kb && ok; ++Kq) for (int Jq = Ja; Jq <= Jb; ++Jq) if (pf[Kq * Q->NJ + Jq] < need) { ok = 0; break; }
+                }
+                const int up = P->dk > 0 ? r - 1 : r + 1;                               /* the slab below in sweep direction */
+                if (ok && K == 0 && up >= 0 && up < nslabs && !a->in_flag[q * (P->NJ + 1) + J]) ok = 0;   /* link_down */
+                if (ok) { ++nready; rng = rng * 1664525u + 1013904223u; if ((rng >> 8) % (uint32_t)nready == 0) { pick_r = r; pick_t = t; } }
+            }
+        }
+        if (pick_r < 0) { rc = -1; break; }
+        Slab *a = &S[pick_r];
+        int tk = a->taken[pick_t], q = 0; while (tk >= a->begin[q + 1]) ++q;
+        const SP *P = &a->sp[q]; int J, K; ticket_to_JK(P, tk - a->begin[q], &J, &K);
+        if (q >= 2 && a->completed[q - 2] != a->sp[q - 2].NJ * a->sp[q - 2].NK) { rc = -2; break; }
+        for (int r2 = 0; r2 < nslabs; ++r2) if (r2 != pick_r && S[r2].ndone < S[r2].total) { int q2 = 0, t2 = S[r2].ndone; while (t2 >= S[r2].begin[q2 + 1]) ++q2; if (q2 != q) { ++overlap; break; } }
+        for (int rk = P->rk_first + K * EK; rk < P->rk_first + (K + 1) * EK && rk <= P->rk_last; ++rk)
+            for (int rj = 1 + J * EJ; rj < 1 + (J + 1) * EJ && rj < nj; ++rj)
+                for (int ri = 1; ri < ni; ++ri)
+                    relax_linked(a, q, P->di > 0 ? ri : ni - 1 - ri, P->dj > 0 ? rj : nj - 1 - rj, P->dk > 0 ? rk : nk - 1 - rk, P->di, P->dj, P->dk);
+        /* hand-over: the last K block pushes its rows of the boundary plane (rk_last), row rj = 0 rides with J = 0 */
+        const int down = P->dk > 0 ? pick_r + 1 : pick_r - 1;
+        if (K == P->NK - 1 && down >= 0 && down < nslabs) {
+            Slab *d = &S[down];
+            const int kbnd = P->dk > 0 ? P->rk_last : nk - 1 - P->rk_last;
+            for (int rj = (J == 0 ? 0 : 1 + J * EJ); rj < 1 + (J + 1) * EJ && rj < nj; ++rj) {
+                const int j = P->dj > 0 ? rj : nj - 1 - rj;
+                for (int i = 0; i < ni; ++i) {
+                    const int64_t c = (int64_t)i + (int64_t)ni * (j + (int64_t)nj * kbnd);
+                    d->in_phi[(int64_t)q * plane + i + (int64_t)ni * j] = phi[c];
+                    d->in_tri[(int64_t)q * plane + i + (int64_t)ni * j] = ctri[c];
+                }
+            }
+            d->in_flag[q * (P->NJ + 1) + J] = 1;
+        }
+        a->flags[(q & 1) * a->stride + K * P->NJ + J] = (uint32_t)(q + 1) * 2 + 1;
+        ++a->completed[q]; ++a->ndone; ++all_done;
+        a->taken[pick_t] = a->taken[--a->ntaken];
+    }
+    if (overlap_out) *overlap_out = overlap;
+    for (int r = 0; r < nslabs; ++r) { free(S[r].flags); free(S[r].completed); free(S[r].taken); free(S[r].in_phi); free(S[r].in_tri); free(S[r].in_flag); }
+    free(S);
+    if (rc) return rc;
+    if (g_poison_reads) return -4;
+    return (memcmp(phi, ref_phi, sizeof(float) * V) || memcmp(ctri, ref_tri, 4 * V)) ? 1 : 0;
+}

@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib
 from ._lib import Plan, SdfbError
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 __all__ = ["generate_sdf", "generate_sdf_batch", "generate_sdf_file", "generate_sdf_debug", "generate_from_mesh", "generate_from_file",
            "is_gpu_available", "load_mesh", "save_sdf", "load_sdf", "Plan", "SdfbError", "launch_count", "trim_memory"]
@@ -71,19 +71,26 @@ def _origin3(origin):
 
 
 def generate_sdf(vertices, triangles, origin, dx, nx, ny, nz, exact_band: int = 1,
-                 backend: str = "auto", num_threads: int = 0) -> np.ndarray:
+                 backend: str = "auto", num_threads: int = 0, num_gpus: int = 1) -> np.ndarray:
     """Signed distance field of a triangle mesh on an nx x ny x nz grid.
 
     Same contract as ``sdfgen_ext.generate_sdf``: float32 ``vertices`` (N,3), uint32 ``triangles``
     (M,3), ``origin`` 3-tuple, returns float32 array of shape (nx, ny, nz), C-contiguous.
     ``num_threads`` is accepted and ignored (it only affects the reference's CPU backend).
+    ``num_gpus`` (not in the reference, which is single-device): cut the grid into k-slabs over this many GPUs of the
+    process (0 = all); the result is bit-identical to one GPU (sdfb_make_level_set3_multi).
     """
     v, t = _validate(vertices, triangles, dx, int(nx), int(ny), int(nz), backend)
     o = _origin3(origin)
     phi = np.empty((int(nx), int(ny), int(nz)), dtype=np.float32)
-    rc = _lib.lib().sdfb_make_level_set3(t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data,
-                                         float(dx), int(nx), int(ny), int(nz), int(exact_band),
-                                         phi.ctypes.data, None, None, _lib.OUT_KFASTEST)
+    if int(num_gpus) == 1:
+        rc = _lib.lib().sdfb_make_level_set3(t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data,
+                                             float(dx), int(nx), int(ny), int(nz), int(exact_band),
+                                             phi.ctypes.data, None, None, _lib.OUT_KFASTEST)
+    else:
+        rc = _lib.lib().sdfb_make_level_set3_multi(t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data,
+                                                   float(dx), int(nx), int(ny), int(nz), int(exact_band),
+                                                   phi.ctypes.data, None, None, int(num_gpus), _lib.OUT_KFASTEST)
     _lib.check(rc)
     return phi
 
@@ -125,7 +132,7 @@ def generate_sdf_file(vertices, triangles, origin, dx, nx, ny, nz, filename: str
         plan.close()
 
 
-def generate_sdf_debug(vertices, triangles, origin, dx, nx, ny, nz, exact_band: int = 1, flags: int = 0):
+def generate_sdf_debug(vertices, triangles, origin, dx, nx, ny, nz, exact_band: int = 1, flags: int = 0, num_gpus: int = 1):
     """Like generate_sdf but returns ``(phi, closest_tri, intersection_count)`` as FLAT arrays in the
     reference's internal i-fastest order (index i + nx*(j + ny*k)); used by the parity tests, which
     are graded on closest_tri and intersection_count as well (the reference keeps them as locals)."""
@@ -133,9 +140,12 @@ def generate_sdf_debug(vertices, triangles, origin, dx, nx, ny, nz, exact_band: 
     o = _origin3(origin)
     V = int(nx) * int(ny) * int(nz)
     phi, tri, cnt = np.empty(V, np.float32), np.empty(V, np.int32), np.empty(V, np.int32)
-    rc = _lib.lib().sdfb_make_level_set3(t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data,
-                                         float(dx), int(nx), int(ny), int(nz), int(exact_band),
-                                         phi.ctypes.data, tri.ctypes.data, cnt.ctypes.data, int(flags))
+    a = (t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data, float(dx), int(nx), int(ny), int(nz),
+         int(exact_band), phi.ctypes.data, tri.ctypes.data, cnt.ctypes.data)
+    if int(num_gpus) == 1:
+        rc = _lib.lib().sdfb_make_level_set3(*a, int(flags))
+    else:
+        rc = _lib.lib().sdfb_make_level_set3_multi(*a, int(num_gpus), int(flags))
     _lib.check(rc)
     return phi, tri, cnt
 

@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDFB_LIB_PATH") or os.path.join(_HERE, "libsdfb.so")   # override: development builds only
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_LIMIT, ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
-OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN, SWEEP_STRIPS, SWEEP_RELAX, SWEEP_COLUMNS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+OUT_KFASTEST, SWEEP_LEVELS, NO_SIGN, SWEEP_RELAX, SWEEP_COLUMNS = 0x1, 0x2, 0x4, 0x10, 0x20
+LINK_HANDLE_BYTES = 128
 
 _lib = None
 
@@ -85,6 +86,20 @@ def lib():
     L.sdfb_plan_write_sdf.argtypes = [vp, C.c_char_p, vp, f32, C.POINTER(C.c_int64), vp]
     L.sdfb_plan_phase_ms.restype = C.c_int
     L.sdfb_plan_phase_ms.argtypes = [vp, C.POINTER(f32 * 4)]
+    L.sdfb_plan_verify.restype = C.c_int
+    L.sdfb_plan_verify.argtypes = [vp, vp, C.POINTER(u64 * 4)]
+    L.sdfb_slab_bounds.restype = C.c_int
+    L.sdfb_slab_bounds.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.sdfb_plan_link_export.restype = C.c_int
+    L.sdfb_plan_link_export.argtypes = [vp, vp]
+    L.sdfb_plan_link_import.restype = C.c_int
+    L.sdfb_plan_link_import.argtypes = [vp, i32, vp]
+    L.sdfb_plan_unlink.restype = C.c_int
+    L.sdfb_plan_unlink.argtypes = [vp]
+    L.sdfb_plan_download_global.restype = C.c_int
+    L.sdfb_plan_download_global.argtypes = [vp, vp, vp, vp, vp]
+    L.sdfb_make_level_set3_multi.restype = C.c_int
+    L.sdfb_make_level_set3_multi.argtypes = [vp, u64, vp, u64, vp, f32, i32, i32, i32, i32, vp, vp, vp, i32, u32]
     _lib = L
     return L
 
@@ -210,6 +225,32 @@ class Plan:
         inside = C.c_int64()
         check(lib().sdfb_plan_write_sdf(self._h, os.fsencode(path), self._origin(min_box), float(dx), C.byref(inside), stream or None))
         return int(inside.value)
+
+    # ---- exact multi-GPU mode (include/sdfb.h: linked k-slabs) -------------------------------------------------
+    def link_export(self) -> bytes:
+        """Allocate this slab's inbound hand-over buffers and return the opaque handle the neighbours import."""
+        buf = C.create_string_buffer(LINK_HANDLE_BYTES)
+        check(lib().sdfb_plan_link_export(self._h, buf))
+        return buf.raw
+
+    def link_import(self, side: int, handle: bytes):
+        """Map the inbound buffers of the plan holding the slab below (side 0) or above (side 1)."""
+        buf = C.create_string_buffer(bytes(handle), LINK_HANDLE_BYTES)
+        check(lib().sdfb_plan_link_import(self._h, int(side), buf))
+
+    def unlink(self):
+        check(lib().sdfb_plan_unlink(self._h))
+
+    def download_global(self, phi=None, tri=None, counts=None, stream=0):
+        """Blocking copy of the slab into arrays of the WHOLE grid (flat, the plan's layout), at the slab's place."""
+        check(lib().sdfb_plan_download_global(self._h, _addr(phi), _addr(tri), _addr(counts), stream or None))
+
+    def verify(self, stream=0):
+        """Device-side self-consistency check and checksums (sdfb_plan_verify): dict(inconsistent, without_triangle,
+        checksum_cells, checksum_values)."""
+        out = (C.c_uint64 * 4)()
+        check(lib().sdfb_plan_verify(self._h, stream or None, C.byref(out)))
+        return dict(inconsistent=int(out[0]), without_triangle=int(out[1]), checksum_cells=int(out[2]), checksum_values=int(out[3]))
 
     def phase_ms(self):
         out = (C.c_float * 4)()

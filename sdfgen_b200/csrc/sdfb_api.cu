@@ -12,7 +12,9 @@
 #include <new>
 #include <mutex>
 #include <thread>
+#include <string>
 #include <vector>
+#include <unistd.h>
 #include <cuda_runtime.h>
 #include "../../include/sdfb.h"
 #include "sdfb_kernels.cuh"
@@ -40,6 +42,31 @@ int fail(int code, const char *fmt, ...)
             return fail(e_ == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA,            \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+int env_int(const char *name, int dflt) { const char *v = getenv(name); return v && *v ? atoi(v) : dflt; }
+
+}  // namespace
+
+namespace sdfb {
+// the development knobs of DESIGN.md section 4.4, read once per plan
+Tuning tuning_from_env()
+{
+    Tuning t;
+    t.relax_from = env_int("SDFB_RELAX_FROM", -1);
+    t.fuse_pass = env_int("SDFB_FUSE_PASS", -1);
+    t.minb = env_int("SDFB_MINB", 0);
+    t.max_occ = env_int("SDFB_MAX_OCC", 0);
+    t.cta_queue = env_int("SDFB_CTA_QUEUE", -1);
+    t.relax_list_cap = env_int("SDFB_RELAX_LIST_CAP", 0);
+    if (getenv("SDFB_RELAX_HEAVY_LIMIT")) t.relax_heavy_limit = (long long)strtoull(getenv("SDFB_RELAX_HEAVY_LIMIT"), nullptr, 10);
+    t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);
+    t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
+    t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
+    return t;
+}
+}  // namespace sdfb
+
+namespace {
 
 bool device_is_sm100(int dev)
 {
@@ -86,21 +113,27 @@ bool is_pageable(const void *p)
 // Device -> host through two pinned staging buffers: the D2H copy of chunk i+1 overlaps what the sink does with chunk i
 // (a threaded memcpy into pageable memory, or a write to a file).  sink(data, n, offset) returns false to stop.
 // Returns a CUDA error code; *sink_ok tells whether every sink call succeeded.
-// the staging ring is allocated once per process (pinning 64 MB costs several ms) and shared under a lock
+// a staging ring is allocated once per DEVICE (pinning 64 MB costs several ms) and shared by that device's plans under
+// a lock: its events belong to the device's context (recording an event on another device's stream is
+// cudaErrorInvalidResourceHandle), and slabs on different GPUs download concurrently
 struct StagingRing {
     std::mutex mtx;
     char *ring[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
-} g_staging;
+} g_staging_dev[64];
 
 template <class Sink>
 cudaError_t staged_d2h_sink(const void *src, size_t bytes, cudaStream_t st, Sink sink, bool *sink_ok)
 {
     const size_t CH = (size_t)32 << 20;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);                     // the caller holds a DeviceGuard for the plan's device
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    StagingRing &g_staging = g_staging_dev[dev];
     std::lock_guard<std::mutex> lock(g_staging.mtx);
     char **ring = g_staging.ring;
     cudaEvent_t *ev = g_staging.ev;
-    cudaError_t e = cudaSuccess;
     bool ok = true;
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         if (!ring[b]) e = cudaHostAlloc(reinterpret_cast<void **>(&ring[b]), CH, cudaHostAllocPortable);
@@ -246,6 +279,8 @@ struct sdfb_plan {
     bool own_stream = false;         // the plan is only ever used on `stream` (one-shot and batch calls): quiescing waits for
     cudaStream_t stream = nullptr;   // that stream instead of the whole device
     int max_ctas = 0;                // batch mode: cap on the persistent sweep grids so that several plans share the SMs (0 = no cap)
+    Tuning tun;                      // development knobs, read from the environment when the plan is created
+    LinkState link;                  // exact multi-GPU mode: hand-over buffers shared with the neighbouring slabs' plans
 };
 
 namespace {
@@ -311,11 +346,55 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
     return SDFB_OK;
 }
 
+// exact multi-GPU mode: unmap the neighbours' buffers and free our own (the caller made sure no neighbour still writes)
+void link_release(sdfb_plan *p)
+{
+    for (int side = 0; side < 2; ++side) {
+        if (p->link.peer_base[side]) cudaIpcCloseMemHandle(p->link.peer_base[side]);
+        p->link.peer_base[side] = nullptr; p->link.peer_halo[side] = nullptr; p->link.peer_flags[side] = nullptr;
+    }
+    if (p->link.in_halo) cudaFree(p->link.in_halo);
+    p->link = LinkState{};
+    cudaGetLastError();
+}
+
+// what sdfb_plan_link_export hands to the neighbours (SDFB_LINK_HANDLE_BYTES)
+struct LinkHandle {
+    cudaIpcMemHandle_t mem;          // 64 bytes
+    int32_t ni, nj, nk, k_lo, k_hi, device;
+    uint64_t bytes;
+    uint64_t local_ptr;              // the exporter's own pointer: valid for same-process links only
+    int64_t pid;
+};
+static_assert(sizeof(LinkHandle) <= SDFB_LINK_HANDLE_BYTES, "LinkHandle must fit the public handle size");
+
+int link_ensure_buffers(sdfb_plan *p)
+{
+    if (p->link.in_halo) return SDFB_OK;
+    if (p->g.nkl() < 2 && (p->g.k_lo == 0 || p->g.k_hi == p->g.nk))
+        return fail(SDFB_ERR_INVALID, "a linked slab on a grid face needs at least 2 planes (got [%d,%d))", p->g.k_lo, p->g.k_hi);
+    const size_t plane = (size_t)p->g.plane();
+    p->link.NJ = (int)link_flag_words_per_sweep(p->g);
+    const size_t halo_bytes = (size_t)LINK_SWEEPS * plane * sizeof(uint64_t);
+    const size_t bytes = halo_bytes + (size_t)LINK_SWEEPS * p->link.NJ * sizeof(unsigned long long);
+    void *base = nullptr;
+    // plain cudaMalloc, not the pool: the block is exported with cudaIpcGetMemHandle / opened by peer devices
+    cudaError_t e = cudaMalloc(&base, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SDFB_ERR_OOM, "allocating %zu bytes of link buffers failed: %s", bytes, cudaGetErrorString(e)); }
+    // flags start at 0 (below any run << 32 with run >= 1); zeroed and complete BEFORE any neighbour learns the address
+    CU(cudaMemset(base, 0, bytes));
+    CU(cudaDeviceSynchronize());
+    p->link.in_halo = static_cast<uint64_t *>(base);
+    p->link.in_flags = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + halo_bytes);
+    p->link.bytes = bytes;
+    return SDFB_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char *sdfb_version(void) { return "sdfgen-b200 0.1 (sm_100a)"; }
+const char *sdfb_version(void) { return "sdfgen-b200 0.2 (sm_100a)"; }
 const char *sdfb_last_error(void) { return g_err; }
 uint64_t sdfb_launch_count(void) { return g_launches.load(); }
 
@@ -347,6 +426,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
     if (ni <= 0 || nj <= 0 || nk <= 0) return fail(SDFB_ERR_INVALID, "grid dimensions must be positive (got %d x %d x %d)", ni, nj, nk);
     if (ni > 32767 || nj > 32767 || nk > 32767) return fail(SDFB_ERR_INVALID, "grid dimensions above 32767 are not supported");
     if (k_lo < 0 || k_hi > nk || k_lo >= k_hi) return fail(SDFB_ERR_INVALID, "bad slab [%d,%d) of %d planes", k_lo, k_hi, nk);
+    if (flags & SDFB_SWEEP_STRIPS) return fail(SDFB_ERR_INVALID, "the strips schedule (flag 0x8) was an experiment of round 1 and is no longer built");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SDFB_ERR_NO_DEVICE, "no CUDA device is visible; libsdfb has no CPU fallback"); }
     if (device < 0 || device >= ndev) return fail(SDFB_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
@@ -370,8 +450,8 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
         cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
     }
+    p->tun = tuning_from_env();
     p->progress_words = sweep_columns_progress_words(p->g);
-    if (sweep_strips_progress_words(p->g) > p->progress_words) p->progress_words = sweep_strips_progress_words(p->g);
     if (p->progress_words && (e = dev_alloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
         sdfb_plan_destroy(p);
         cudaGetLastError();
@@ -395,6 +475,7 @@ int sdfb_plan_destroy(sdfb_plan *p)
     free_mesh(p);
     dev_free(p->cells); dev_free(p->counts); dev_free(p->phi); dev_free(p->phi_k); dev_free(p->scratch);
     dev_free(p->changed); dev_free(p->progress); dev_free(p->relax);
+    link_release(p);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
     if (p->ev_copy) cudaEventDestroy(p->ev_copy);
     delete p;
@@ -465,6 +546,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
     p->have_band = true; p->have_sign = false; p->timed = false; p->last_sweep = -1;
+    if (p->link.active) ++p->link.run;       // linked slabs run band() in lockstep: flag words are run << 32 | steps
     return SDFB_OK;
 }
 
@@ -473,31 +555,58 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
     if (!p->have_band) return fail(SDFB_ERR_STATE, "sdfb_plan_sweep called before sdfb_plan_band");
     if (first < 0 || count < 0) return fail(SDFB_ERR_INVALID, "bad sweep range");
+    // the stamp memo assumes that every sweep below `first` has run on these cells since the last band (a neighbour whose
+    // stamp is not newer than the last sweep that looked at it is skipped): sweeps may be repeated, never skipped
+    if (first > p->last_sweep + 1)
+        return fail(SDFB_ERR_STATE, "sweep %d requested but the last sweep run since sdfb_plan_band is %d: sweeps must be run in order", first, p->last_sweep);
+    if (count == 0) return SDFB_OK;
     DeviceGuard dg(p->device);
     cudaStream_t st = (cudaStream_t)stream;
+    const Tuning &tun = p->tun;
+    auto reset_epoch_if_needed = [&](uint32_t more) -> cudaError_t {       // progress words are epoch<<16 | steps: start over before it wraps
+        if (p->epoch + more < 65000u) return cudaSuccess;
+        p->epoch = 0;
+        return cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st);
+    };
+    if (p->link.active) {
+        // exact multi-GPU mode: every sweep runs in the fused column launch, which hands the slab's boundary plane to the
+        // downstream neighbour column by column (LinkSweep, sdfb_kernels.cuh).  No host synchronisation in here: the
+        // neighbour's launch may be enqueued by this very thread right after this one.
+        if (p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_RELAX)) return fail(SDFB_ERR_STATE, "linked plans use the column schedule; SDFB_SWEEP_LEVELS / SDFB_SWEEP_RELAX cannot be combined with links");
+        if (first + count > LINK_SWEEPS) return fail(SDFB_ERR_INVALID, "linked plans run the reference's %d sweeps only (asked for %d..%d)", LINK_SWEEPS, first, first + count - 1);
+        for (int side = 0; side < 2; ++side) {
+            const bool has = side == 0 ? p->g.k_lo > 0 : p->g.k_hi < p->g.nk;
+            if (has && !p->link.peer_halo[side]) return fail(SDFB_ERR_STATE, "linked plan: the slab %s this one has not been linked (sdfb_plan_link_import / _local)", side == 0 ? "below" : "above");
+        }
+        CU(reset_epoch_if_needed((uint32_t)count));
+        const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, count, p->changed, p->progress, p->progress_words,
+                                                 &p->epoch, st, tun, p->max_ctas, &p->link);
+        if (!l) return fail(SDFB_ERR_STATE, "linked plan: the fused column launch declined sweeps %d..%d on slab [%d,%d)", first, first + count - 1, p->g.k_lo, p->g.k_hi);
+        g_launches += l;
+        if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(p->ev[2], st));
+        p->have_sign = false;
+        return SDFB_OK;
+    }
     // first sweep index handled by the relaxation schedule: the reference's second pass and everything after it
-    int relax_from = (p->flags & SDFB_SWEEP_RELAX) ? 0 : ((p->flags & (SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS)) ? 1 << 30 : 8);
-    if (getenv("SDFB_RELAX_FROM") && !(p->flags & (SDFB_SWEEP_RELAX | SDFB_SWEEP_COLUMNS | SDFB_SWEEP_STRIPS))) relax_from = atoi(getenv("SDFB_RELAX_FROM"));
+    int relax_from = (p->flags & SDFB_SWEEP_RELAX) ? 0 : ((p->flags & SDFB_SWEEP_COLUMNS) ? 1 << 30 : 8);
+    if (tun.relax_from >= 0 && !(p->flags & (SDFB_SWEEP_RELAX | SDFB_SWEEP_COLUMNS))) relax_from = tun.relax_from;
     // The column sweeps of the first pass go out as ONE launch in which consecutive sweeps overlap where their directions
     // allow it (sdfb_sweep_columns.cu: k_sweep_columns_fused).  SDFB_FUSE_PASS=0 turns it off (one launch per sweep),
-    // =1 also fuses launches of >= 300 M voxels, which otherwise stay on the per-sweep path (their 4-CTA/SM build of the
-    // fused kernel has not been measured yet).
+    // =1 also fuses launches of >= 300 M voxels, which otherwise stay on the per-sweep path.
     int fused_until = first;
-    const char *fuse_env = getenv("SDFB_FUSE_PASS");
-    const int fuse_mode = fuse_env ? atoi(fuse_env) : -1;                       // -1 default, 0 off, 1 forced
+    const int fuse_mode = tun.fuse_pass;                                        // -1 default, 0 off, 1 forced
     const bool big_launch = (int64_t)p->g.ni * (p->g.nj - 1) * p->g.nkl() >= ((int64_t)300 << 20);
     if (fuse_mode != 0 && (fuse_mode == 1 || !big_launch) &&
-        !(p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_STRIPS | SDFB_SWEEP_RELAX)) && first < 8 && first < relax_from) {
+        !(p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_RELAX)) && first < 8 && first < relax_from) {
         int n = (first + count < 8 ? first + count : 8);
         if (n > relax_from) n = relax_from;
         n -= first;
         if (n >= 2) {
-            if (p->epoch + (uint32_t)n >= 65000u) {
-                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
-                p->epoch = 0;
-            }
+            CU(reset_epoch_if_needed((uint32_t)n));
             const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
-                                                     &p->epoch, st, p->max_ctas);
+                                                     &p->epoch, st, tun, p->max_ctas);
             if (l) { g_launches += l; fused_until = first + n; }
         }
     }
@@ -510,24 +619,15 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                 CU(dev_alloc(&p->relax, bytes));
                 CU(cudaMemsetAsync(p->relax, 0, bytes, st));
             }
-            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st, p->max_ctas);
+            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st, tun, p->max_ctas);
             // a sweep that turns out to change a large part of the grid is handed back (cells restored, flag set):
             // this launch then runs it with the column schedule, and exits at once otherwise
-            if (p->epoch >= 65000u) {
-                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
-                p->epoch = 0;
-            }
-            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st,
+            CU(reset_epoch_if_needed(1));
+            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun,
                                                sweep_relax_fallback_flag(p->relax), p->max_ctas);
         } else {
-            if (p->epoch >= 65000u) {   // progress words are epoch<<16 | steps: start over before it wraps
-                CU(cudaMemsetAsync(p->progress, 0, p->progress_words * sizeof(uint32_t), st));
-                p->epoch = 0;
-            }
-            if (p->flags & SDFB_SWEEP_STRIPS)
-                g_launches += launch_sweep_strips(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st);
-            else
-                g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, nullptr, p->max_ctas);
+            CU(reset_epoch_if_needed(1));
+            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, nullptr, p->max_ctas);
         }
     }
     if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;
@@ -593,6 +693,25 @@ int sdfb_plan_counters(sdfb_plan *p, void *stream, uint64_t out[2])
     return SDFB_OK;
 }
 
+int sdfb_plan_verify(sdfb_plan *p, void *stream, uint64_t out[4])
+{
+    if (!p || !out) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "nothing to verify: run the plan first");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d = nullptr;
+    CU(dev_alloc(&d, 4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st));
+    g_launches += launch_verify_cells(p->cells, p->rec, p->g, p->init_phi, d, st);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(d);
+    CU(e);
+    for (int q = 0; q < 4; ++q) out[q] = h[q];
+    return SDFB_OK;
+}
+
 int sdfb_plan_changed(sdfb_plan *p, void *stream, uint64_t *changed)
 {
     if (!changed) return fail(SDFB_ERR_INVALID, "null argument");
@@ -602,38 +721,45 @@ int sdfb_plan_changed(sdfb_plan *p, void *stream, uint64_t *changed)
     return rc;
 }
 
-int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *count_out, void *stream)
+// Copies the slab's results to host memory.  global == false: the three arrays hold the slab only (slab_voxels values).
+// global == true: they are arrays of the WHOLE ni x nj x nk grid and the slab lands at its place -- a contiguous run of
+// planes in the i-fastest layout, a strided copy (nkl values every nk) in the k-fastest one (python/sdfgen_py.cpp:80-86,
+// common/sdf_io.cpp:49-57).
+static int download_impl(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *count_out, cudaStream_t st, bool global)
 {
-    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
-    if (!p->have_band) return fail(SDFB_ERR_STATE, "nothing to download: run the plan first");
-    DeviceGuard dg(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t V = (size_t)p->g.slab_voxels();
     const bool kf = (p->flags & SDFB_OUT_KFASTEST) != 0;
+    const size_t nkl = (size_t)p->g.nkl(), nk = (size_t)p->g.nk, rows = (size_t)p->g.plane();
+    const bool strided = global && kf && nkl != nk;
+    const size_t off = !global ? 0 : (kf ? (size_t)p->g.k_lo : (size_t)p->g.k_lo * rows);
+    auto copy_out = [&](void *dst, const void *src) -> cudaError_t {     // 4-byte elements
+        char *d = static_cast<char *>(dst) + off * 4;
+        if (strided) return cudaMemcpy2DAsync(d, nk * 4, src, nkl * 4, nkl * 4, rows, cudaMemcpyDeviceToHost, st);
+        if (V * 4 >= ((size_t)64 << 20) && is_pageable(d)) return staged_d2h(d, src, V * 4, st);
+        return cudaMemcpyAsync(d, src, V * 4, cudaMemcpyDeviceToHost, st);
+    };
     if (phi_out) {
         if (!p->have_sign) {   // unsigned phi straight from the cells
             if (p->copy_pending) { CU(cudaStreamWaitEvent(st, p->ev_copy, 0)); p->copy_pending = false; }
             g_launches += launch_sign(p->cells, p->counts, p->g, false, false, p->phi, st);
             if (kf) g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, reinterpret_cast<int32_t *>(p->phi_k), st);
         }
-        const float *src = kf ? p->phi_k : p->phi;
-        if (V * sizeof(float) >= ((size_t)64 << 20) && is_pageable(phi_out)) CU(staged_d2h(phi_out, src, V * sizeof(float), st));
-        else CU(cudaMemcpyAsync(phi_out, src, V * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(copy_out(phi_out, kf ? p->phi_k : p->phi));
     }
     if (tri_out || (count_out && kf)) {
-        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t) * (kf ? 2 : 1)));
+        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t) * 2));
     }
     if (tri_out) {
         g_launches += launch_unpack_tri(p->cells, p->g, false, p->scratch, st);
         if (kf) g_launches += launch_relayout_i32(p->scratch, p->g, p->scratch + V, st);
-        CU(cudaMemcpyAsync(tri_out, kf ? p->scratch + V : p->scratch, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(copy_out(tri_out, kf ? p->scratch + V : p->scratch));
     }
     if (count_out) {
         if (kf) {
             g_launches += launch_relayout_i32(p->counts, p->g, p->scratch, st);
-            CU(cudaMemcpyAsync(count_out, p->scratch, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU(copy_out(count_out, p->scratch));
         } else {
-            CU(cudaMemcpyAsync(count_out, p->counts, V * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU(copy_out(count_out, p->counts));
         }
     }
     CU(cudaGetLastError());
@@ -642,6 +768,22 @@ int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *
     CU(cudaStreamSynchronize(st));
     if (bad != ~0ull) return bad_index_error(p, bad);
     return SDFB_OK;
+}
+
+int sdfb_plan_download(sdfb_plan *p, float *phi_out, int32_t *tri_out, int32_t *count_out, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "nothing to download: run the plan first");
+    DeviceGuard dg(p->device);
+    return download_impl(p, phi_out, tri_out, count_out, (cudaStream_t)stream, false);
+}
+
+int sdfb_plan_download_global(sdfb_plan *p, float *phi_grid, int32_t *tri_grid, int32_t *count_grid, void *stream)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    if (!p->have_band) return fail(SDFB_ERR_STATE, "nothing to download: run the plan first");
+    DeviceGuard dg(p->device);
+    return download_impl(p, phi_grid, tri_grid, count_grid, (cudaStream_t)stream, true);
 }
 
 int sdfb_plan_download_phi_async(sdfb_plan *p, float *phi_out, void *copy_stream)
@@ -669,7 +811,7 @@ int sdfb_plan_write_sdf(sdfb_plan *p, const char *path, const float min_box[3], 
     // the file stores k fastest (common/sdf_io.cpp:49-57): take the plan's own k-fastest copy or make one in the scratch
     const float *src = p->phi_k;
     if (!src) {
-        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t)));
+        if (!p->scratch) CU(dev_alloc(&p->scratch, V * sizeof(int32_t) * 2));      // same size as the download path allocates
         g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), p->g, p->scratch, st);
         src = reinterpret_cast<const float *>(p->scratch);
     }
@@ -796,6 +938,159 @@ int sdfb_make_level_set3_batch(sdfb_batch_item *items, int32_t n, int32_t concur
     }
     for (auto &t : th) t.join();
     if (first_rc) return fail(first_rc, "%s", first_msg);
+    return SDFB_OK;
+}
+
+// ---- exact multi-GPU mode: linked k-slabs ---------------------------------------------------------------------------
+
+int sdfb_plan_link_export(sdfb_plan *p, void *handle_out)
+{
+    if (!p || !handle_out) return fail(SDFB_ERR_INVALID, "null argument");
+    DeviceGuard dg(p->device);
+    int rc = link_ensure_buffers(p);
+    if (rc) return rc;
+    LinkHandle h{};
+    cudaError_t e = cudaIpcGetMemHandle(&h.mem, p->link.in_halo);
+    if (e != cudaSuccess) { cudaGetLastError(); memset(&h.mem, 0, sizeof(h.mem)); }      // same-process links still work
+    h.ni = p->g.ni; h.nj = p->g.nj; h.nk = p->g.nk; h.k_lo = p->g.k_lo; h.k_hi = p->g.k_hi; h.device = p->device;
+    h.bytes = p->link.bytes; h.local_ptr = (uint64_t)(uintptr_t)p->link.in_halo; h.pid = (int64_t)getpid();
+    memset(handle_out, 0, SDFB_LINK_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    p->link.active = true;
+    return SDFB_OK;
+}
+
+int sdfb_plan_link_import(sdfb_plan *p, int32_t side, const void *handle)
+{
+    if (!p || !handle) return fail(SDFB_ERR_INVALID, "null argument");
+    if (side != 0 && side != 1) return fail(SDFB_ERR_INVALID, "side must be 0 (the slab below) or 1 (the slab above)");
+    LinkHandle h;
+    memcpy(&h, handle, sizeof(h));
+    if (h.ni != p->g.ni || h.nj != p->g.nj || h.nk != p->g.nk) return fail(SDFB_ERR_INVALID, "link: the neighbour's grid is %d x %d x %d, this plan's %d x %d x %d", h.ni, h.nj, h.nk, p->g.ni, p->g.nj, p->g.nk);
+    if (side == 0 ? h.k_hi != p->g.k_lo : h.k_lo != p->g.k_hi)
+        return fail(SDFB_ERR_INVALID, "link: slab [%d,%d) is not the slab %s [%d,%d)", h.k_lo, h.k_hi, side == 0 ? "below" : "above", p->g.k_lo, p->g.k_hi);
+    DeviceGuard dg(p->device);
+    int rc = link_ensure_buffers(p);
+    if (rc) return rc;
+    if (p->link.peer_base[side]) { cudaIpcCloseMemHandle(p->link.peer_base[side]); p->link.peer_base[side] = nullptr; }
+    void *base = nullptr;
+    if (h.pid == (int64_t)getpid()) {
+        // same process: the exporter's pointer is valid here (unified addressing); another device needs peer access
+        base = (void *)(uintptr_t)h.local_ptr;
+        if (h.device != p->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, p->device, h.device));
+            if (!can) return fail(SDFB_ERR_NO_DEVICE, "link: device %d cannot access device %d's memory (no P2P)", p->device, h.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SDFB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(SDFB_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s (slabs in different processes need CUDA IPC between their devices)", cudaGetErrorString(e)); }
+        p->link.peer_base[side] = base;
+    }
+    const size_t halo_bytes = (size_t)LINK_SWEEPS * (size_t)p->g.plane() * sizeof(uint64_t);
+    p->link.peer_halo[side] = static_cast<uint64_t *>(base);
+    p->link.peer_flags[side] = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + halo_bytes);
+    p->link.active = true;
+    return SDFB_OK;
+}
+
+int sdfb_plan_unlink(sdfb_plan *p)
+{
+    if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
+    DeviceGuard dg(p->device);
+    plan_quiesce(p);
+    link_release(p);
+    return SDFB_OK;
+}
+
+int sdfb_slab_bounds(int32_t nk, int32_t slabs, int32_t index, int32_t *k_lo, int32_t *k_hi)
+{
+    if (nk <= 0 || slabs <= 0 || slabs > nk || index < 0 || index >= slabs || !k_lo || !k_hi) return fail(SDFB_ERR_INVALID, "cannot cut %d planes into %d slabs (index %d)", nk, slabs, index);
+    const int base = nk / slabs, rem = nk % slabs;
+    *k_lo = index * base + (index < rem ? index : rem);
+    *k_hi = *k_lo + base + (index < rem ? 1 : 0);
+    return SDFB_OK;
+}
+
+// One grid over several GPUs of this process: k-slabs, one plan per device, linked so that the 16 sweeps keep the
+// reference's serial order across the slab faces (bit-identical to the single-GPU result).  Everything is enqueued on
+// every device before the first blocking call: a slab's sweep kernel waits, on the device, for its neighbour's.
+int sdfb_make_level_set3_multi(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
+                               const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
+                               int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
+                               int32_t *intersection_count_out, int32_t num_gpus, uint32_t flags)
+{
+    if (!phi_out || !origin) return fail(SDFB_ERR_INVALID, "null argument");
+    const int avail = sdfb_device_count();
+    if (avail == 0) return fail(SDFB_ERR_NO_DEVICE, "no CUDA device is visible; libsdfb has no CPU fallback");
+    if (num_gpus <= 0) num_gpus = avail;                                   // 0 = all usable devices
+    if (num_gpus > avail) return fail(SDFB_ERR_NO_DEVICE, "%d GPUs requested, %d usable", num_gpus, avail);
+    // a slab needs two planes to be linked on a grid face; small grids simply use fewer devices
+    while (num_gpus > 1 && nk / num_gpus < 2) --num_gpus;
+    if (num_gpus == 1 || (flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_RELAX)))
+        return sdfb_make_level_set3(tri, ntri, xyz, nvert, origin, dx, ni, nj, nk, exact_band, phi_out, closest_tri_out, intersection_count_out, flags);
+    const int N = num_gpus;
+    std::vector<sdfb_plan *> plans(N, nullptr);
+    std::vector<cudaStream_t> streams(N, nullptr);
+    int rc = SDFB_OK;
+    int dev0 = 0;
+    cudaGetDevice(&dev0);
+    auto cleanup = [&]() {
+        for (int r = 0; r < N; ++r) if (plans[r]) { DeviceGuard dg(r); cudaStreamSynchronize(streams[r]); }
+        for (int r = 0; r < N; ++r) {
+            DeviceGuard dg(r);
+            sdfb_plan_destroy(plans[r]);
+            if (streams[r]) cudaStreamDestroy(streams[r]);
+        }
+        cudaSetDevice(dev0);
+    };
+    std::vector<char> handles((size_t)N * SDFB_LINK_HANDLE_BYTES);
+    for (int r = 0; r < N && !rc; ++r) {
+        int32_t lo, hi;
+        sdfb_slab_bounds(nk, N, r, &lo, &hi);
+        DeviceGuard dg(r);
+        if (cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking) != cudaSuccess) { rc = fail(SDFB_ERR_CUDA, "could not create a stream on device %d", r); break; }
+        rc = sdfb_plan_create(&plans[r], r, ni, nj, nk, lo, hi, flags);
+        if (!rc) { plans[r]->own_stream = true; plans[r]->stream = streams[r]; }
+        if (!rc) rc = sdfb_plan_link_export(plans[r], handles.data() + (size_t)r * SDFB_LINK_HANDLE_BYTES);
+    }
+    for (int r = 0; r < N && !rc; ++r) {
+        if (r > 0) rc = sdfb_plan_link_import(plans[r], 0, handles.data() + (size_t)(r - 1) * SDFB_LINK_HANDLE_BYTES);
+        if (!rc && r + 1 < N) rc = sdfb_plan_link_import(plans[r], 1, handles.data() + (size_t)(r + 1) * SDFB_LINK_HANDLE_BYTES);
+    }
+    // uploads and record building first (they may allocate, which synchronises), then the phases on every device
+    for (int r = 0; r < N && !rc; ++r) rc = sdfb_plan_set_mesh_host(plans[r], tri, ntri, xyz, nvert, streams[r]);
+    for (int r = 0; r < N && !rc; ++r) rc = sdfb_plan_band(plans[r], origin, dx, exact_band, streams[r]);
+    int enq = 0;                                                            // sweeps enqueued on devices [0, enq)
+    for (int r = 0; r < N && !rc; ++r) { rc = sdfb_plan_sweep(plans[r], 0, LINK_SWEEPS, streams[r]); if (!rc) enq = r + 1; }
+    if (rc && enq > 0 && enq < N) {
+        // a neighbour's launch failed while ours are already waiting for it: nothing can complete them but the watchdog;
+        // this cannot happen for well-formed arguments (every check precedes the first launch), report it as fatal
+        char keep[sizeof(g_err)]; snprintf(keep, sizeof(keep), "%.400s (after %d of %d slab launches; the device waits will time out)", g_err, enq, N);
+        cleanup();
+        return fail(rc, "%s", keep);
+    }
+    for (int r = 0; r < N && !rc; ++r) rc = sdfb_plan_sign(plans[r], streams[r]);
+    const size_t out_bytes = (size_t)ni * nj * nk * sizeof(float);
+    if (!rc && out_bytes >= ((size_t)64 << 20) && is_pageable(phi_out)) parallel_for_bytes(reinterpret_cast<char *>(phi_out), out_bytes, touch_pages, nullptr);
+    if (!rc) {
+        // each slab downloads into its place of the caller's arrays, one host thread per device
+        std::vector<int> rcs(N, SDFB_OK);
+        std::vector<std::string> msgs(N);
+        std::vector<std::thread> th;
+        for (int r = 0; r < N; ++r) th.emplace_back([&, r]() {
+            rcs[r] = sdfb_plan_download_global(plans[r], phi_out, closest_tri_out, intersection_count_out, streams[r]);
+            if (rcs[r]) msgs[r] = g_err;
+        });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < N && !rc; ++r) if (rcs[r]) { rc = rcs[r]; snprintf(g_err, sizeof(g_err), "%s", msgs[r].c_str()); }
+    }
+    char keep[sizeof(g_err)]; snprintf(keep, sizeof(keep), "%s", g_err);
+    cleanup();
+    if (rc) return fail(rc, "%s", keep);
     return SDFB_OK;
 }
 

@@ -91,6 +91,11 @@ __device__ __forceinline__ void tri_boxes(const TriRec &t, const Grid &g, TriBox
     // clip to the planes this slab owns (clamps above use the GLOBAL nk)
     b.k0 = max(b.k0, g.k_lo);   b.k1 = min(b.k1, g.k_hi - 1);
     b.ck0 = max(b.ck0, g.k_lo); b.ck1 = min(b.ck1, g.k_hi - 1);
+    // An extent can come out inverted along ANY axis: d2i_trunc yields INT_MIN for coordinates outside the int range
+    // (|x - o| / dx >= 2^31, inf, NaN), so e.g. i0 = clamp(INT_MIN - band -> wraps) = ni-1 while i1 = 0.  The reference's
+    // `for (i = i0; i <= i1; ++i)` loops (cpu_lib/makelevelset3.cpp:213-215) then run zero times; canonicalise such a box
+    // to "k1 < k0", the one emptiness test band_voxels() and k_band make.
+    if (b.i1 < b.i0 || b.j1 < b.j0) b.k1 = b.k0 - 1;
 }
 
 __device__ __forceinline__ uint32_t units_of(uint64_t n) { return (uint32_t)((n + UNIT - 1) / UNIT); }

@@ -28,6 +28,48 @@ struct Grid {
 // both inclusive and clipped to the slab's planes.
 struct __align__(16) TriExt { int i0, i1, j0, j1, k0, k1, cj0, cj1, ck0, ck1, pad0, pad1; };
 
+// Development knobs, read from the environment ONCE per plan (sdfb_plan_create) -- none is needed in production.
+struct Tuning {
+    int relax_from = -1;          // SDFB_RELAX_FROM: first sweep index run by the relaxation schedule (-1: default 8)
+    int fuse_pass = -1;           // SDFB_FUSE_PASS: 0 one launch per first-pass sweep, 1 fuse launches of >= 300 M voxels too
+    int minb = 0;                 // SDFB_MINB: 3 / 4 = register bound (CTAs per SM) of the column kernels, 0 = by launch size
+    int max_occ = 0;              // SDFB_MAX_OCC: cap on resident column CTAs per SM (experiments)
+    int cta_queue = -1;           // SDFB_CTA_QUEUE: 0/1 force the warp-private / column-wide evaluation queue
+    int relax_list_cap = 0;       // SDFB_RELAX_LIST_CAP: work-list capacity (tests force the bitmap fallback)
+    long long relax_heavy_limit = -1;   // SDFB_RELAX_HEAVY_LIMIT: work-list entries before a sweep is handed back to the columns
+    int relax_scan_from = 13;     // SDFB_RELAX_SCAN_FROM: first sweep whose round 0 uses the lean scan kernel
+    int relax_debug = 0;          // SDFB_RELAX_DEBUG: per-sweep round statistics on stderr
+    int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
+};
+Tuning tuning_from_env();
+
+// Exact multi-GPU mode (linked k-slabs): per-sweep hand-over of the slab boundary plane between neighbouring plans.
+// A sweep reads only offsets 0 and -dk in k (cpu_lib/makelevelset3.cpp:143-149), so the slab downstream of this one
+// consumes this slab's last plane column by column AS THE COLUMNS COMPLETE: the columns of the last K block store their
+// boundary-plane cells into the neighbour's inbound buffer for this sweep (peer memory over NVLink) and publish their
+// step count there with a system-scope fence; the neighbour's first K block polls those words exactly like it polls a
+// column below it on the same GPU.  One inbound plane and one row of flags PER SWEEP INDEX (16 of each): a buffer is
+// written by exactly one sweep of one run, so a neighbour that runs ahead (the next sweep with the same k direction)
+// can never overwrite cells that are still being read.
+constexpr int LINK_SWEEPS = 16;
+struct LinkSweep {
+    const uint64_t *halo_src = nullptr;             // [nj][ni] cells of the upstream slab's boundary plane (local memory, written by the peer)
+    const unsigned long long *flag_src = nullptr;   // [NJ] run << 32 | steps completed by the upstream column (J, last K block)
+    uint64_t *halo_dst = nullptr;                   // the downstream peer's halo_src of this sweep
+    unsigned long long *flag_dst = nullptr;         // the downstream peer's flag_src of this sweep
+};
+struct LinkState {          // host side, per plan
+    bool active = false;
+    uint64_t *in_halo = nullptr;                    // LINK_SWEEPS planes, cudaMalloc (IPC-exportable)
+    unsigned long long *in_flags = nullptr;         // LINK_SWEEPS x NJ words, same allocation
+    uint64_t *peer_halo[2] = {nullptr, nullptr};    // [0] the slab below (k_lo - 1), [1] the slab above (k_hi)
+    unsigned long long *peer_flags[2] = {nullptr, nullptr};
+    void *peer_base[2] = {nullptr, nullptr};        // what cudaIpcOpenMemHandle returned (nullptr for same-process links)
+    unsigned long long run = 0;                     // band() calls so far: flag words are run << 32 | steps
+    int NJ = 0;
+    size_t bytes = 0;
+};
+
 struct Launches { uint64_t n = 0; };
 
 // all launchers enqueue on `st` and return the number of kernels launched
@@ -40,27 +82,26 @@ int launch_sweep_levels(uint64_t *cells, const TriRec *rec, const Grid &g, int s
                         unsigned long long *changed, cudaStream_t st);
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
-                         const unsigned int *run_if = nullptr, int max_ctas = 0);
+                         const Tuning &tun, const unsigned int *run_if = nullptr, int max_ctas = 0);
+// link: nullptr, or the plan's link state (then the launch hands its boundary plane over / waits for the neighbour's)
 int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
                                unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
-                               cudaStream_t st, int max_ctas);
+                               cudaStream_t st, const Tuning &tun, int max_ctas, const LinkState *link = nullptr);
+size_t link_flag_words_per_sweep(const Grid &g);     // NJ of the column schedule
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st);
 int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st);
 int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st);
+int launch_verify_cells(const uint64_t *cells, const TriRec *rec, const Grid &g, float init_phi, unsigned long long *out, cudaStream_t st);
 int launch_count_negative(const float *v, int64_t n, unsigned long long *out, cudaStream_t st);
 int launch_relayout_i32(const int32_t *src, const Grid &g, int32_t *dst_kfastest, cudaStream_t st);
-
-int launch_sweep_strips(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                        unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st);
 
 bool sweep_relax_supported(const Grid &g);
 size_t sweep_relax_scratch_bytes(const Grid &g);
 const unsigned int *sweep_relax_fallback_flag(const void *scratch);
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas = 0);
+                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas = 0);
 
 size_t sweep_columns_progress_words(const Grid &g);
-size_t sweep_strips_progress_words(const Grid &g);
 
 }  // namespace sdfb

@@ -86,7 +86,56 @@ __global__ void __launch_bounds__(256) k_halo_refresh(uint64_t *__restrict__ cel
     }
 }
 
+// Verification pass (checks for grids the reference cannot run): every cell must hold EXACTLY the
+// reference distance to the triangle it names (phi == point_triangle_distance(gx, tri[closest_tri]), bit for bit), or the
+// initial distance where no triangle was ever assigned.  Also folds the slab into two order-independent 64-bit
+// checksums keyed by the GLOBAL voxel index, so that the checksums of the slabs of a sharded run add up (mod 2^64) to
+// the checksum of one plan on the whole grid: out[2] over whole cell words (distance, stamp, triangle), out[3] over
+// (distance, triangle) only.  out[0] = inconsistent cells, out[1] = cells without a triangle.
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) k_verify_cells(const uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Grid g,
+                                                      uint32_t init_bits, unsigned long long *__restrict__ out)
+{
+    const int64_t n = g.slab_voxels(), stride = (int64_t)gridDim.x * blockDim.x, plane = g.plane();
+    unsigned long long bad = 0, none = 0, sum_cell = 0, sum_val = 0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const uint64_t c = cells[plane + v];
+        const uint32_t lo = cell_lo(c), t = lo_tri(lo), pb = (uint32_t)(c >> 32);
+        const int64_t kk = v / plane, r = v - kk * plane;
+        const int j = (int)(r / g.ni), i = (int)(r - (int64_t)j * g.ni), k = (int)kk + g.k_lo;
+        if (t == TRI_NONE) { ++none; bad += pb != init_bits; }
+        else {
+            const F3 gx{lattice(i, g.dx, g.ox), lattice(j, g.dx, g.oy), lattice(k, g.dx, g.oz)};
+            bad += __float_as_uint(ptd_rec(gx, rec[t])) != pb;
+        }
+        const uint64_t gidx = (uint64_t)v + (uint64_t)g.k_lo * (uint64_t)plane;
+        sum_cell += mix64(mix64(gidx) ^ c);
+        sum_val += mix64(mix64(gidx) ^ (((uint64_t)pb << 32) | t));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_down_sync(0xffffffffu, bad, o); none += __shfl_down_sync(0xffffffffu, none, o);
+        sum_cell += __shfl_down_sync(0xffffffffu, sum_cell, o); sum_val += __shfl_down_sync(0xffffffffu, sum_val, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(out, bad);
+        if (none) atomicAdd(out + 1, none);
+        atomicAdd(out + 2, sum_cell);
+        atomicAdd(out + 3, sum_val);
+    }
+}
+
 }  // namespace
+
+int launch_verify_cells(const uint64_t *cells, const TriRec *rec, const Grid &g, float init_phi, unsigned long long *out, cudaStream_t st)
+{
+    k_verify_cells<<<148 * 8, 256, 0, st>>>(cells, rec, g, __builtin_bit_cast(uint32_t, init_phi), out);
+    return 1;
+}
 
 int launch_halo_refresh(uint64_t *cells, const Grid &g, cudaStream_t st)
 {

@@ -121,6 +121,10 @@ struct ColParams {
     // (rj = nj-1), 4 = last plane (rk = nk-1): such voxels lie on a grid face and are only visited by sweeps
     // whose direction along that axis equals the current one.
     uint8_t last[8][8];
+    // exact multi-GPU mode (k_sweep_columns_fused<.., LINK = true> only; see LinkSweep in sdfb_kernels.cuh)
+    LinkSweep link;
+    unsigned long long run_base;             // run << 32: link flag words are run_base | steps
+    unsigned long long link_timeout_ns;      // watchdog of the waits on a neighbour GPU (0 = none)
 };
 
 // smem exchange array: [2 slots][EK+1][EJ+1] words, index (b+1)*(EJ+1) + (a+1); a fastest
@@ -267,12 +271,29 @@ __device__ __forceinline__ void wait_previous_sweep(const ColParams &P, const Co
     __threadfence();                    // acquire side: the column's loads (all ld.cg in fused launches) come after this
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// LINK (exact multi-GPU mode): `link_down` replaces prog_down for the columns of the FIRST K block when the slab below
+// (in sweep direction) lives on another GPU -- same meaning (steps completed by the column that produces this column's
+// b = -1 halo rows), 64-bit words run << 32 | steps written by that GPU with a system-scope release; `link_mine` is
+// where the columns of the LAST K block publish for the slab above.  The words sit in the CONSUMER's memory, so
+// polling them is a local L2 access.  A neighbour that never shows up (a host that died, mismatched calls) trips the
+// watchdog: the kernel traps instead of spinning forever.
+template <bool LINK>
 __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, int lane, const uint32_t *prog_left,
-                                            const uint32_t *prog_down, uint32_t *prog_mine)
+                                            const uint32_t *prog_down, uint32_t *prog_mine,
+                                            const unsigned long long *link_down = nullptr, unsigned long long *link_mine = nullptr)
 {
     const uint32_t ebase = P.epoch << 16;
     const int nchunks = P.steps / PUBLISH;
     int cleared = 0, published = 0;                        // counts of chunks
+    unsigned idle = 0;
+    unsigned long long t_wait = 0;
     while (published < nchunks) {
         int act = 0, d = 0;                                // 1: clear the next chunk, 2: publish finished chunks
         if (lane == 0) {
@@ -283,7 +304,10 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
                 const uint32_t fd = prog_down ? *reinterpret_cast<const volatile uint32_t *>(prog_down) : 0xffffffffu;
                 // no fence on this side: the halo lanes' loads are issued only after the barrier below (control
                 // dependence) and go to L2 (ld.cg), where the producer's stores landed before its flag
-                if (fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3)) act = 1;
+                bool ok = fl >= ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3) && fd >= ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3);
+                if (LINK && link_down)
+                    ok = ok && *reinterpret_cast<const volatile unsigned long long *>(link_down) >= P.run_base + (unsigned long long)min(P.steps, s1 - 1 + EK + 3);
+                if (ok) act = 1;
             }
             if (!act && d > published) act = 2;
         }
@@ -292,20 +316,43 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
         if (act == 1) {
             bar_go_arrive(cleared);
             ++cleared;
+            idle = 0;
         } else if (act == 2) {
             if (lane == 0) {
-                __threadfence();                           // release: the chunk's stores happen-before the flag
+                if (LINK && link_mine) {
+                    // release at system scope: the boundary-plane cells the compute lanes stored into the neighbour's
+                    // memory (peer stores over NVLink, ordered before sh.done by the CTA barrier) are visible there
+                    // before the word that announces them
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long *>(link_mine) = P.run_base + (unsigned long long)(d * PUBLISH);
+                } else {
+                    __threadfence();                       // release: the chunk's stores happen-before the flag
+                }
                 *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
             }
             published = d;
+            idle = 0;
         } else {
             __nanosleep(SDFB_SYNC_SLEEP);
+            if (LINK && P.link_timeout_ns && (++idle & 1023u) == 0) {            // uniform over the warp
+                const unsigned long long now = global_timer_ns();
+                if (idle == 1024u) t_wait = now;
+                else if (now - t_wait > P.link_timeout_ns) {
+                    if (lane == 0) printf("sdfb: column wait timed out (sweep stamp %u, waiting for %s)\n", P.stamp, link_down ? "the neighbour GPU" : "a local column");
+                    __trap();
+                }
+            }
         }
     }
 }
 
 // ---- halo warps: feed the words of the upstream columns / boundary faces into the exchange array ----
-template <bool CTA_QUEUE>
+// LINK (exact multi-GPU mode): the b = -1 rows of a column of the FIRST K block lie in the slab below; when that slab
+// lives on another GPU they are read from this sweep's inbound plane (P.link.halo_src, filled by the neighbour's last
+// K block while it runs the same sweep) instead of the halo plane of the cell array.  And the one row no column of
+// the neighbour ever computes -- rj = 0, read-only in this sweep -- is forwarded to the slab above by the a = -1 halo
+// lane of the J = 0 column that reads it anyway (b = the slab's last plane).
+template <bool CTA_QUEUE, bool LINK>
 __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
                                             const ColParams &P, ColShared &sh, int h, int rj0, int rk0, unsigned &my_evals)
 {
@@ -319,6 +366,13 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     const int64_t si = (int64_t)P.sd.di;
     const uint64_t *ptr = cells;
     if (row_ok) ptr = cells + g.cidx(P.sd.abs_i(0, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g)) + si * (int64_t)(0 - a - b - SHIFT);
+    uint64_t *fwd = nullptr;                               // LINK: where this lane forwards row rj = 0 of the boundary plane
+    if (LINK && row_ok) {
+        if (P.link.halo_src && b == -1 && rk0 == P.rk_first)
+            ptr = P.link.halo_src + ((int64_t)P.sd.abs_i(0, g) + (int64_t)g.ni * P.sd.abs_j(rj, g)) + si * (int64_t)(0 - a - b - SHIFT);
+        if (P.link.halo_dst && a == -1 && rj == 0 && rk == P.rk_last)
+            fwd = P.link.halo_dst + ((int64_t)P.sd.abs_i(0, g) + (int64_t)g.ni * P.sd.abs_j(0, g)) + si * (int64_t)(0 - a - b - SHIFT);
+    }
     const int widx = row_ok ? ring_idx(a, b) : 0;
     int ri = 0 - a - b - SHIFT;                            // voxel of virtual step 0
     // Raw cells of virtual steps s (even -> wA, odd -> wB), each loaded two steps before it is published.
@@ -336,6 +390,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
             TRACE(P, 8 + (h >> 5), s, 0);
             if (row_ok) {
                 sh.ring[widx] = cell_lo(wA);               // even step -> slot 0
+                if (LINK && fwd && (unsigned)ri < (unsigned)g.ni) *fwd = wA;
                 wA = ~0ull;
                 if ((unsigned)(ri + 2) < (unsigned)g.ni && s + 2 < P.steps) wA = __ldcg(ptr + 2 * si);
             }
@@ -345,6 +400,7 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
             TRACE(P, 8 + (h >> 5), s + 1, 0);
             if (row_ok) {
                 sh.ring[RSTRIDE + widx] = cell_lo(wB);     // odd step -> slot 1
+                if (LINK && fwd) { if ((unsigned)(ri + 1) < (unsigned)g.ni) *(fwd + si) = wB; fwd += 2 * si; }
                 wB = ~0ull;
                 if ((unsigned)(ri + 3) < (unsigned)g.ni && s + 3 < P.steps) wB = __ldcg(ptr + 3 * si);
                 ri += 2; ptr += 2 * si;
@@ -370,6 +426,7 @@ struct LaneState {
     //   R5(s) = lane(a-1,b-1)@s-1 = (ri+1, rj-1, rk-1)   m=5 one step later, m=6 two steps later
     uint32_t r1_old, r3_old, r5_old, r5_old2;
     unsigned changed, evals;
+    uint64_t *push_ptr;                   // LINK: this voxel's cell in the inbound plane of the slab above (nullptr: not a boundary lane)
 };
 
 // The rare part of a step: at least one lane of the warp has a neighbour whose cell changed since the
@@ -462,10 +519,12 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
 __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                                       int ri, int tid, int s, bool update, uint32_t live_in,
                                                       uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
-                                                      uint32_t nb5, uint32_t nb6, uint32_t cur, uint64_t *self_ptr, float phi)
+                                                      uint32_t nb5, uint32_t nb6, uint32_t cur, uint64_t *self_ptr, float phi,
+                                                      float &phi_new)
 {
     const Grid &g = P.g;
     const int lane = tid & 31, warp = tid >> 5;
+    phi_new = phi;                                 // LINK: the caller forwards the voxel's final cell to the slab above
     uint32_t *const q_ent = &sh.q_ent[0][0];       // flat: NCOMPUTE * 7 entries
     float *const q_d = &sh.q_d[0][0];
     const uint32_t nb[7] = {nb0, nb1, nb2, nb3, nb4, nb5, nb6};
@@ -539,6 +598,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
         if (best >= 0) {
             cur = (P.stamp << 27) | q_ent[off + best];
             *self_ptr = pack_cell(phi, cur);
+            phi_new = phi;
             changed = 1;
         }
     }
@@ -547,7 +607,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
 
 // One step of a compute lane.  PAR = step parity: reads exchange slot PAR^1, writes slot PAR.  `own` holds the
 // lane's cell for this step on entry and is reloaded with the cell two steps ahead (see halo_column).
-template <int PAR, bool CTA_QUEUE, bool L2OWN = false>
+template <int PAR, bool CTA_QUEUE, bool L2OWN = false, bool LINK = false>
 __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, const ColParams &P, ColShared &sh,
                                              const uint32_t *ring_r, uint32_t *ring_w, int s, int lane, int warp,
                                              int rj0, int rk0, bool row_ok, const uint32_t (&thr)[7],
@@ -596,9 +656,16 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
                 live |= keep ? (1u << m) : 0u;
             }
         }
+        float phi_new;
         const uint2 r = evaluate_candidates_cta(rec, P, sh, ri, (warp << 5) + lane, s, update, live,
-                                                nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6], cur, self_ptr, cell_phi(self));
+                                                nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6], cur, self_ptr, cell_phi(self), phi_new);
         cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
+        // LINK: a lane on the slab's last plane stores the voxel's final cell (changed or not, ri = 0 included) into the
+        // inbound plane of the slab above; the sync warp publishes the step count there after a system-scope fence
+        if (LINK && st.push_ptr) {
+            if ((unsigned)ri < (unsigned)ni) *st.push_ptr = pack_cell(phi_new, cur);
+            st.push_ptr += si;
+        }
     } else if (__any_sync(0xffffffffu, update && fresh)) {
         const uint2 r = evaluate_candidates(rec, P, sh, ri, lane, warp, update, false,
                                             nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
@@ -614,7 +681,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     bar_step();
 }
 
-template <bool CTA_QUEUE, bool L2OWN = false>
+template <bool CTA_QUEUE, bool L2OWN = false, bool LINK = false>
 __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
                                                const ColParams &P, ColShared &sh, int tid, int rj0, int rk0,
                                                unsigned &my_changed, unsigned &my_evals)
@@ -627,12 +694,15 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     const int64_t si = (int64_t)P.sd.di;
     LaneState st;
     st.own_ptr = cells;
+    st.push_ptr = nullptr;
     st.ri = 0 - a - b - SHIFT;            // voxel of step 0
     if (row_ok) {
         const int j = P.sd.abs_j(rj, g), k = P.sd.abs_k(rk, g);
         st.own_ptr = cells + g.cidx(P.sd.abs_i(0, g), j, k) + si * (int64_t)st.ri;
         sh.gy[tid] = lattice(j, g.dx, g.oy);
         sh.gz[tid] = lattice(k, g.dx, g.oz);
+        if (LINK && P.link.halo_dst && rk == P.rk_last)
+            st.push_ptr = P.link.halo_dst + ((int64_t)P.sd.abs_i(0, g) + (int64_t)g.ni * j) + si * (int64_t)st.ri;
     }
     // memo thresholds: the neighbour word nb at offset m is fresh iff nb >= thr[m] = (last[m]+1) << 27, i.e.
     // stamp(nb) > last[m] (0 = always fresh where the offset was never examined).  Rows on the far j / k
@@ -660,8 +730,8 @@ __device__ __forceinline__ void compute_column(uint64_t *__restrict__ cells, con
     if (row_ok && (unsigned)st.ri < (unsigned)g.ni) ownA = L2OWN ? __ldcg(st.own_ptr) : *st.own_ptr;
     if (row_ok && (unsigned)(st.ri + 1) < (unsigned)g.ni) ownB = L2OWN ? __ldcg(st.own_ptr + si) : *(st.own_ptr + si);
     for (int s = 0; s < P.steps; s += 2) {   // P.steps is even
-        compute_step<0, CTA_QUEUE, L2OWN>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, ownB, st);
-        compute_step<1, CTA_QUEUE, L2OWN>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, ownA, st);
+        compute_step<0, CTA_QUEUE, L2OWN, LINK>(rec, P, sh, ring_r, ring_w, s, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownA, ownB, st);
+        compute_step<1, CTA_QUEUE, L2OWN, LINK>(rec, P, sh, ring_r, ring_w, s + 1, lane, warp, rj0, rk0, row_ok, thr, thr_edge, ownB, ownA, st);
         if (tid == 0 && ((s + 2) % PUBLISH) == 0) {      // every lane's stores of this chunk precede the barrier
             __threadfence_block();
             sh.done = (s + 2) / PUBLISH;
@@ -702,11 +772,11 @@ __device__ __forceinline__ void column_loop(uint64_t *__restrict__ cells, const 
         if (GROUP != 1 && tid < NCOMPUTE) {
             compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (GROUP != 0 && tid >= NCOMPUTE && tid < NSTEPPERS) {
-            halo_column<CTA_QUEUE>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            halo_column<CTA_QUEUE, false>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
         } else if (GROUP != 0 && tid >= NSTEPPERS && tid < NSTEPPERS + 32) {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
-            sync_column(P, sh, lane, prog_left, prog_down, &progress[K * P.NJ + J]);
+            sync_column<false>(P, sh, lane, prog_left, prog_down, &progress[K * P.NJ + J]);
         }
         __syncthreads();        // sh.col is rewritten next; also orders the two roles' exits
     }
@@ -754,7 +824,7 @@ k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, Co
 // sweep it depends on are complete.  Transitions where only some axes flip overlap; opposite
 // directions serialise by themselves.  Every prerequisite holds a lower ticket, so it is running or done: no deadlock.
 // Progress words are double-buffered by launch-relative sweep parity.  Cells are read through L2 only (L2OWN).
-constexpr int FUSE_MAX = 8;
+constexpr int FUSE_MAX = 16;
 struct FusedParams {
     int n;                       // sweeps in this launch
     int col_begin[FUSE_MAX + 1]; // first ticket of each sweep
@@ -762,7 +832,13 @@ struct FusedParams {
     ColParams p[FUSE_MAX];
 };
 
-template <int MINB>
+// LINK = exact multi-GPU mode: the slab's neighbours run the same launch on their GPUs; the first K block of every sweep
+// waits for (and reads) what the upstream neighbour's last K block hands over, the last K block hands its own boundary
+// plane to the downstream neighbour (LinkSweep in sdfb_kernels.cuh).  A column still only ever waits for columns with
+// lower tickets on its own GPU or for columns of the SAME sweep on the upstream GPU, and the k direction orders the GPUs
+// within a sweep, so the dependency graph over (sweep, position in flow order, ticket) stays acyclic: no deadlock as
+// long as every GPU's launch is eventually resident (one launch per GPU, or capped grids when slabs share a GPU).
+template <int MINB, bool LINK>
 __global__ void __launch_bounds__(NTHREADS, MINB)
 k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, const __grid_constant__ FusedParams FP,
                       uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket, unsigned long long *__restrict__ changed)
@@ -793,15 +869,17 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
         uint32_t *flags = progress + (q & 1) * FP.flag_stride;
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
         if (tid < NCOMPUTE) {
-            compute_column<true, true>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+            compute_column<true, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
-            halo_column<true>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
         } else if (tid < NSTEPPERS + 32) {
             if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, lane, J, K);
             bar_start_arrive();
             const uint32_t *prog_left = (J > 0) ? &flags[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &flags[(K - 1) * P.NJ + J] : nullptr;
-            sync_column(P, sh, lane, prog_left, prog_down, &flags[K * P.NJ + J]);
+            const unsigned long long *link_down = (LINK && K == 0 && P.link.flag_src) ? &P.link.flag_src[J] : nullptr;
+            unsigned long long *link_mine = (LINK && K == P.NK - 1 && P.link.flag_dst) ? &P.link.flag_dst[J] : nullptr;
+            sync_column<LINK>(P, sh, lane, prog_left, prog_down, &flags[K * P.NJ + J], link_down, link_mine);
         }
         __syncthreads();
     }
@@ -838,32 +916,52 @@ bool fill_col_params(ColParams &P, const Grid &g, int sweep_index, uint32_t epoc
 
 }  // namespace
 
-// Sweeps first .. first+count-1 (all of the first pass' kind: column-wide queue) in one launch.
+// Sweeps first .. first+count-1 (all with the column-wide evaluation queue) in one launch.
 // Returns the number of launches (1), or 0 if this grid cannot be fused (then the caller launches sweep by sweep);
-// *epoch is advanced by one per sweep.
+// *epoch is advanced by one per sweep.  link != nullptr: exact multi-GPU mode (the caller has made sure every sweep of
+// the range updates at least one plane of this slab and that first + count <= LINK_SWEEPS).
 int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
                                unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
-                               cudaStream_t st, int max_ctas)
+                               cudaStream_t st, const Tuning &tun, int max_ctas, const LinkState *link)
 {
-    if (WG || count < 2 || count > FUSE_MAX) return 0;
+    if (WG || count < (link ? 1 : 2) || count > FUSE_MAX) return 0;
+    if (link && first + count > LINK_SWEEPS) return 0;
     FusedParams FP{};
     FP.n = count;
     FP.flag_stride = (int)((progress_words - 4) / 2);
     FP.col_begin[0] = 0;
     for (int q = 0; q < count; ++q) {
-        if (!fill_col_params(FP.p[q], g, first + q, *epoch + 1 + (uint32_t)q)) return 0;      // a sweep with nothing to update: do not fuse
-        if ((size_t)FP.p[q].NJ * FP.p[q].NK > (size_t)FP.flag_stride) return 0;
-        FP.col_begin[q + 1] = FP.col_begin[q] + FP.p[q].NJ * FP.p[q].NK;
+        ColParams &P = FP.p[q];
+        if (!fill_col_params(P, g, first + q, *epoch + 1 + (uint32_t)q)) return 0;      // a sweep with nothing to update: do not fuse
+        if ((size_t)P.NJ * P.NK > (size_t)FP.flag_stride) return 0;
+        FP.col_begin[q + 1] = FP.col_begin[q] + P.NJ * P.NK;
+        if (link) {
+            // upstream side of this sweep: the slab below for dk > 0, above for dk < 0 (if there is one); downstream: the other
+            const int s = first + q, up = P.sd.dk > 0 ? 0 : 1, down = 1 - up;
+            const bool has_up = up == 0 ? g.k_lo > 0 : g.k_hi < g.nk, has_down = down == 0 ? g.k_lo > 0 : g.k_hi < g.nk;
+            const size_t plane = (size_t)g.plane();
+            if (has_up) { P.link.halo_src = link->in_halo + (size_t)s * plane; P.link.flag_src = link->in_flags + (size_t)s * link->NJ; }
+            if (has_down) {
+                if (!link->peer_halo[down] || !link->peer_flags[down]) return 0;           // neighbour not linked: the caller reports it
+                P.link.halo_dst = link->peer_halo[down] + (size_t)s * plane;
+                P.link.flag_dst = link->peer_flags[down] + (size_t)s * link->NJ;
+            }
+            P.run_base = link->run << 32;
+            P.link_timeout_ns = tun.link_timeout_s > 0 ? (unsigned long long)tun.link_timeout_s * 1000000000ull : 0ull;
+        }
     }
     *epoch += (uint32_t)count;
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int minb = ((int64_t)g.ni * (g.nj - 1) * (FP.p[0].rk_last - FP.p[0].rk_first + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
-    if (getenv("SDFB_MINB")) minb = atoi(getenv("SDFB_MINB")) >= 4 ? 4 : 3;
-    auto kern = minb == 4 ? k_sweep_columns_fused<4> : k_sweep_columns_fused<3>;
+    if (tun.minb) minb = tun.minb >= 4 ? 4 : 3;
+    using kern_t = void (*)(uint64_t *, const TriRec *, const FusedParams, uint32_t *, uint32_t *, unsigned long long *);
+    const kern_t kern = link ? (minb == 4 ? k_sweep_columns_fused<4, true> : k_sweep_columns_fused<3, true>)
+                             : (minb == 4 ? k_sweep_columns_fused<4, false> : k_sweep_columns_fused<3, false>);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, 0);
     if (occ < 1) occ = 1;
+    if (tun.max_occ > 0 && occ > tun.max_occ) occ = tun.max_occ;
     int grid = sms * occ;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     // small grids: a sweep has fewer columns than the device has CTA slots, and CTAs beyond that would only sit on
@@ -876,6 +974,8 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     return 1;
 }
 
+size_t link_flag_words_per_sweep(const Grid &g) { return (size_t)(g.nj - 1 + EJ - 1) / EJ + 1; }
+
 // progress: [2] ticket words + [1] epoch counter slot (host side keeps the epoch) + 2 x NJ*NK flags (the second array is
 // used by fused launches only)
 size_t sweep_columns_progress_words(const Grid &g)
@@ -886,7 +986,7 @@ size_t sweep_columns_progress_words(const Grid &g)
 
 int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
-                         const unsigned int *run_if, int max_ctas)
+                         const Tuning &tun, const unsigned int *run_if, int max_ctas)
 {
     ColParams P{};
     P.g = g;
@@ -917,17 +1017,17 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // evaluation-heavy sweeps (the first pass) balance the distance evaluations over the whole column
-    const bool cta_queue = getenv("SDFB_CTA_QUEUE") ? atoi(getenv("SDFB_CTA_QUEUE")) != 0 : (sweep_index < 8);
+    const bool cta_queue = tun.cta_queue >= 0 ? tun.cta_queue != 0 : (sweep_index < 8);
     int occ = 1;
     // register bound by the amount of work per launch (see k_sweep_columns)
     int minb = ((int64_t)g.ni * (g.nj - 1) * (rk_hi - rk_lo + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
-    if (getenv("SDFB_MINB")) minb = atoi(getenv("SDFB_MINB")) >= 4 ? 4 : 3;
+    if (tun.minb) minb = tun.minb >= 4 ? 4 : 3;
     using kern_t = void (*)(uint64_t *, const TriRec *, ColParams, uint32_t *, uint32_t *, unsigned long long *);
     const kern_t kern = cta_queue ? (minb == 4 ? k_sweep_columns<true, 4> : k_sweep_columns<true, 3>)
                                   : (minb == 4 ? k_sweep_columns<false, 4> : k_sweep_columns<false, 3>);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, 0);
     if (occ < 1) occ = 1;
-    if (getenv("SDFB_MAX_OCC")) occ = min(occ, atoi(getenv("SDFB_MAX_OCC")));   // experiment knob
+    if (tun.max_occ > 0) occ = min(occ, tun.max_occ);   // experiment knob
     int grid = sms * occ;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;            // batch mode: several plans share the device
     int ncols = P.NJ * P.NK;

@@ -563,7 +563,7 @@ const unsigned int *sweep_relax_fallback_flag(const void *scratch) { return stat
 
 // `scratch` must be zero-initialised once after allocation (bitmaps and counters return to zero after every sweep).
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas)
+                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas)
 {
     RelaxParams P{};
     P.g = g;
@@ -575,7 +575,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     P.stamp = (uint32_t)(sweep_index + 1);
     P.cells = cells; P.rec = rec; P.changed = changed;
     P.list_cap = sweep_relax_list_cap(g);
-    if (getenv("SDFB_RELAX_LIST_CAP")) P.list_cap = min(P.list_cap, (uint32_t)max(1, atoi(getenv("SDFB_RELAX_LIST_CAP"))));   // tests: force the bitmap fallback
+    if (tun.relax_list_cap > 0) P.list_cap = min(P.list_cap, (uint32_t)tun.relax_list_cap);   // tests: force the bitmap fallback
     const size_t ncells = (size_t)g.cell_count(), words = (ncells + 31) / 32 + 1;
     char *s = static_cast<char *>(scratch);
     P.count = reinterpret_cast<unsigned int *>(s); s += 64;
@@ -587,7 +587,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     // light sweeps put well under 1 % of the cells on their work lists (C2: 0.004-0.1 % on the first, less after),
     // heavy ones most of them, round after round
     P.heavy_limit = (uint32_t)(ncells / 64);
-    if (getenv("SDFB_RELAX_HEAVY_LIMIT")) P.heavy_limit = (uint32_t)strtoul(getenv("SDFB_RELAX_HEAVY_LIMIT"), nullptr, 10);   // tests: force the fallback
+    if (tun.relax_heavy_limit >= 0) P.heavy_limit = (uint32_t)tun.relax_heavy_limit;   // tests: force the fallback
     memo_last_table(sweep_index, P.sd, P.last);
     cudaMemsetAsync(P.count, 0, 64, st);
     int dev = 0, sms = 148, occ = 1;
@@ -602,14 +602,13 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         if (dev >= 0 && dev < 64) occ_cached[dev] = occ;
     } else occ = occ_cached[dev];
     static unsigned long long *dbg = nullptr;
-    if (getenv("SDFB_RELAX_DEBUG")) {
+    if (tun.relax_debug) {
         if (!dbg) cudaMalloc(&dbg, 512 * sizeof(unsigned long long));
         cudaMemsetAsync(dbg, 0, 512 * sizeof(unsigned long long), st);
         P.debug = dbg;
     }
     // sweeps late in the second pass have almost no candidates: stream over the cells with the lean scan kernel
-    const int scan_from = getenv("SDFB_RELAX_SCAN_FROM") ? atoi(getenv("SDFB_RELAX_SCAN_FROM")) : 13;
-    P.scan_mode = sweep_index >= scan_from ? 1 : 0;
+    P.scan_mode = sweep_index >= tun.relax_scan_from ? 1 : 0;
     int launches = 1;
     if (P.scan_mode) {
         const dim3 sgrid((g.nj - 1 + SCAN_ROWS - 1) / SCAN_ROWS, rk_hi - rk_lo + 1);
@@ -624,7 +623,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         unsigned long long h[512];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        if (atoi(getenv("SDFB_RELAX_DEBUG")) > 1) {
+        if (tun.relax_debug > 1) {
             fprintf(stderr, "[relax] sweep %2d rounds (n @ us):", sweep_index);
             for (int r = 1; r < 250 && h[4 + 2 * r]; ++r) fprintf(stderr, " %llu@%.0f", h[4 + 2 * r], h[5 + 2 * r] * 1e-3);
             fprintf(stderr, "\n");

@@ -216,13 +216,112 @@ def run_slabs_exact_local(engines, origin, dx, exact_band=1, passes=2):
         e.sign()
 
 
+# ---- linked mode: the exact cross-GPU column pipeline (the default multi-GPU mode) ------------------------------------
+
+def link_slabs(engine, rank, world, group=None):
+    """Exchange the slabs' link handles (include/sdfb.h: sdfb_plan_link_export / _import) and map the neighbours'
+    inbound buffers.  After this every rank runs band -> sweep(0, 16) -> sign in lockstep; the sweep kernels hand the
+    slab boundary planes over among themselves (peer stores over NVLink + flags), the host and NCCL are not involved."""
+    import torch.distributed as dist
+    handle = engine.plan.link_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    if rank > 0:
+        engine.plan.link_import(0, handles[rank - 1])
+    if rank < world - 1:
+        engine.plan.link_import(1, handles[rank + 1])
+    dist.barrier(group=group)            # every neighbour has mapped every buffer before the first launch
+
+
+def run_sharded_linked(engine, origin, dx, exact_band=1) -> ShardStats:
+    """Phases A, B, C on one rank's linked slab: bit-identical to one plan on the whole grid (exact)."""
+    engine.band(origin, dx, exact_band)
+    engine.sweep(0, 16)
+    engine.sign()
+    return ShardStats(passes=2)
+
+
+def unlink_slabs(engine, group=None):
+    """Every rank has finished its last run before any rank frees its inbound buffers."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    engine.plan.unlink()
+    dist.barrier(group=group)
+
+
+class ShardedMeshUpload:
+    """End-to-end mesh ingestion for N ranks without N copies crossing PCIe: every rank uploads 1/N of the index and
+    vertex arrays from its pinned host copy and an NCCL all-gather over NVLink completes the replicas (the sweeps
+    need every triangle record on every GPU: a closest triangle may come from any slab)."""
+
+    def __init__(self, triangles, vertices, rank, world, device):
+        import torch
+        self.torch, self.rank, self.world = torch, rank, world
+        t = np.ascontiguousarray(triangles, np.uint32).view(np.int32).reshape(-1)
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1)
+        self.T, self.NV = triangles.shape[0], vertices.shape[0]
+        self.nt = -(-t.size // world)                       # shard lengths (elements), last shard zero-padded
+        self.nv = -(-v.size // world)
+        tp = np.zeros(self.nt * world, np.int32); tp[:t.size] = t
+        vp = np.zeros(self.nv * world, np.float32); vp[:v.size] = v
+        self.t_pin = torch.from_numpy(tp[rank * self.nt:(rank + 1) * self.nt].copy()).pin_memory()
+        self.v_pin = torch.from_numpy(vp[rank * self.nv:(rank + 1) * self.nv].copy()).pin_memory()
+        self.d_t = torch.empty(self.nt * world, dtype=torch.int32, device=device)
+        self.d_v = torch.empty(self.nv * world, dtype=torch.float32, device=device)
+        self.h2d_bytes = 4 * (self.nt + self.nv)            # per rank and step
+
+    def upload(self, plan, stream, group=None):
+        import torch.distributed as dist
+        r = self.rank
+        self.d_t[r * self.nt:(r + 1) * self.nt].copy_(self.t_pin, non_blocking=True)
+        self.d_v[r * self.nv:(r + 1) * self.nv].copy_(self.v_pin, non_blocking=True)
+        dist.all_gather_into_tensor(self.d_t, self.d_t[r * self.nt:(r + 1) * self.nt], group=group)
+        dist.all_gather_into_tensor(self.d_v, self.d_v[r * self.nv:(r + 1) * self.nv], group=group)
+        plan.set_mesh_device(self.d_t.data_ptr(), self.T, self.d_v.data_ptr(), self.NV, stream=stream, keepalive=(self.d_t, self.d_v))
+
+
 # ---- bench.py --gpus N (N > 1) ---------------------------------------------------------------------
 
+def _timed_linked(eng, w, steps, stream, e2e_fn=None):
+    """K steps between barriers; returns (device ms per step as the max over ranks, wall ms per step as the max)."""
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            if e2e_fn:
+                e2e_fn()
+            else:
+                run_sharded_linked(eng, w["origin"], w["dx"], 1)
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps, wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    return float(t[0].item()), float(t[1].item())
+
+
+def _gather_sum_u64(value, world):
+    import torch.distributed as dist
+    vals = [None] * world
+    dist.all_gather_object(vals, int(value))
+    return sum(vals) & ((1 << 64) - 1), vals
+
+
 def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
+    """N > 1: BASELINE configs[3] (5.0 M-triangle torus at 1024^3) cut into N linked k-slabs -- strong scaling, every
+    number from the exact mode -- plus, on 8 GPUs, configs[4] (10 M triangles at 2048^3).  One rank per GPU."""
     import torch
     import torch.distributed as dist
     import sdfgen_b200
-    from . import meshes
+    from . import meshes, _lib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,107 +330,123 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
         raise SystemExit(f"--gpus {args.gpus} needs torch.distributed.run --nproc-per-node {args.gpus} (WORLD_SIZE={world})")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
 
-    n = args.grid or 512
-    w = meshes.stacked_workload(world, n=n)                 # weak scaling: one 512^3 block + one sphere per GPU
-    ni, nj, nk = w["ni"], w["nj"], w["nk"]
-    k_lo, k_hi = slab_bounds(nk, world, rank)
-    stream = torch.cuda.Stream()
-    eng = CudaSlabEngine(ni, nj, nk, k_lo, k_hi, local, stream=stream)
-    T, NV = int(w["triangles"].shape[0]), int(w["vertices"].shape[0])
-    tri_pin = torch.from_numpy(w["triangles"].view(np.int32)).pin_memory()
-    xyz_pin = torch.from_numpy(w["vertices"]).pin_memory()
-    Vloc = ni * nj * (k_hi - k_lo)
-    phi_pins = [torch.empty(Vloc, dtype=torch.float32).pin_memory() for _ in range(2)]
-    copy_stream = torch.cuda.Stream()
-    counter = [0]
+    def run_config(name, grid, steps, warmup, with_e2e, with_one_gpu):
+        w = meshes.workload(name, n=grid)
+        ni, nj, nk = w["ni"], w["nj"], w["nk"]
+        V, T, NV = ni * nj * nk, int(w["triangles"].shape[0]), int(w["vertices"].shape[0])
+        k_lo, k_hi = slab_bounds(nk, world, rank)
+        stream = torch.cuda.Stream()
+        eng = CudaSlabEngine(ni, nj, nk, k_lo, k_hi, local, stream=stream)
+        link_slabs(eng, rank, world)
+        eng.set_mesh(w["vertices"], w["triangles"])
+        for _ in range(warmup):
+            with torch.cuda.stream(stream):
+                run_sharded_linked(eng, w["origin"], w["dx"], 1)
+        n0 = sdfgen_b200.launch_count()
+        dev_ms, _ = _timed_linked(eng, w, steps, stream)
+        launches = (sdfgen_b200.launch_count() - n0) // steps
+        ph = eng.plan.phase_ms()
+        res = {"workload": w["name"], "triangles": T, "vertices": NV, "grid": [ni, nj, nk], "slab_planes": k_hi - k_lo,
+               "ms_per_step": dev_ms, "value": V / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "gpu_launches_per_rank": int(launches),
+               "rank0_phase_ms": ph}
+        # device-side checks (untimed): self-consistency of every cell, checksums that add up over the slabs
+        chk = eng.plan.verify(stream=eng.sh)
+        bad = torch.tensor([chk["inconsistent"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(bad)
+        res["inconsistent_cells"] = int(bad.item())
+        sum_cells, _ = _gather_sum_u64(chk["checksum_cells"], world)
+        sum_vals, _ = _gather_sum_u64(chk["checksum_values"], world)
+        res["checksum_values"] = f"{sum_vals:016x}"
+        if with_e2e:
+            up = ShardedMeshUpload(w["triangles"], w["vertices"], rank, world, dev)
+            Vloc = ni * nj * (k_hi - k_lo)
+            phi_pin = torch.empty(Vloc, dtype=torch.float32).pin_memory()
 
-    def step_exact():
-        with torch.cuda.stream(stream):
-            return run_sharded_exact(eng, rank, world, w["origin"], w["dx"], 1)
+            def e2e_step():
+                up.upload(eng.plan, eng.sh)
+                run_sharded_linked(eng, w["origin"], w["dx"], 1)
+                eng.plan.download(phi=True, stream=eng.sh, phi_out=phi_pin.data_ptr())      # blocking, this rank's slab
 
-    def step(e2e):
-        # e2e: every step uploads the mesh from pinned host memory and downloads this rank's slab of phi; the download
-        # runs on a copy stream and overlaps the next step (sdfb_plan_download_phi_async), as in the single-GPU bench
-        with torch.cuda.stream(stream):
-            if e2e:
-                eng.plan.set_mesh_host_ptr(tri_pin.data_ptr(), T, xyz_pin.data_ptr(), NV, stream=eng.sh)
-            st = run_sharded(eng, rank, world, w["origin"], w["dx"], 1)
-            if e2e:
-                eng.plan.download_phi_async(phi_pins[counter[0] & 1].data_ptr(), copy_stream.cuda_stream)
-                counter[0] += 1
-        return st
+            with torch.cuda.stream(stream):
+                e2e_step()
+            _, e2e_ms = _timed_linked(eng, w, steps, stream, e2e_fn=e2e_step)
+            res["e2e"] = {"value": V / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+                          "h2d_bytes_per_step": up.h2d_bytes * world, "d2h_bytes_per_step": 4 * V,
+                          "mode": "per step and rank: 1/N of the mesh H2D from pinned memory + NCCL all-gather of the replicas over "
+                                  "NVLink, band + 16 linked sweeps + sign, blocking D2H of the rank's slab of phi into pinned "
+                                  "memory; host wall clock, max over ranks"}
+            del up, phi_pin
+        unlink_slabs(eng)
+        eng.close()
+        if with_one_gpu:
+            # the same grid as ONE plan on rank 0's GPU: the 1-GPU figure of the strong-scaling line and the
+            # 1-GPU-vs-N-GPU equality check of SURVEY.md 8(c)(iii), by checksum over every cell
+            one = {}
+            if rank == 0:
+                p1 = _lib.Plan(ni, nj, nk, device=local)
+                p1.set_mesh_host(w["vertices"], w["triangles"], stream=stream.cuda_stream)
+                for _ in range(2):
+                    p1.run(w["origin"], w["dx"], 1, stream=stream.cuda_stream)
+                one = {"ms_per_step": p1.phase_ms()["total"]}
+                c1 = p1.verify(stream=stream.cuda_stream)
+                one["checksum_values"], one["checksum_cells"], one["inconsistent"] = c1["checksum_values"], c1["checksum_cells"], c1["inconsistent"]
+                p1.close()
+                sdfgen_b200.trim_memory()
+            box = [one]
+            dist.broadcast_object_list(box, src=0)
+            one = box[0]
+            res["one_gpu_ms_per_step"] = one["ms_per_step"]
+            res["one_gpu_value"] = V / (one["ms_per_step"] * 1e-3) / 1e9
+            res["speedup_vs_one_gpu"] = one["ms_per_step"] / dev_ms
+            res["parallel_efficiency"] = one["ms_per_step"] / dev_ms / world
+            res["equal_to_one_gpu"] = bool(one["checksum_values"] == sum_vals and one["inconsistent"] == 0)
+            res["equal_to_one_gpu_with_stamps"] = bool(one["checksum_cells"] == sum_cells)
+        torch.cuda.synchronize()
+        sdfgen_b200.trim_memory()
+        return res, (ni, nj, nk, V, T, NV, k_lo, k_hi)
 
-    eng.set_mesh(w["vertices"], w["triangles"])
-    for _ in range(args.warmup):
-        st = step(False)
-    torch.cuda.synchronize()
+    name = args.workload if args.workload and args.workload != "c2_icosphere_512" else "c3_torus_1024"
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-
-    def timed(e2e):
-        n0 = sdfgen_b200.launch_count()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        for _ in range(args.steps):
-            st = step(e2e)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        ms = max(ev0.elapsed_time(ev1), wall if e2e else 0.0) / args.steps
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
-        return float(t.item()), st, (sdfgen_b200.launch_count() - n0) // args.steps
-
-    dev_ms, st, launches = timed(False)
-    e2e_ms, _, _ = timed(True)
-    exact = None
-    if getattr(args, "exact", False):
-        step_exact()                                         # warm-up: first send/recv between neighbours
-        dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_exact()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        exact = {"ms_per_step": float(t.item()), "value": ni * nj * nk / (float(t.item()) * 1e-3) / 1e9, "unit": UNIT,
-                 "note": "run_sharded_exact: 16 sweeps in the serial order across slabs, bit-identical to one grid; "
-                         "device-resident, max over ranks"}
+    c3, (ni, nj, nk, V, T, NV, k_lo, k_hi) = run_config(name, args.grid, args.steps, args.warmup, True, True)
+    c4 = None
+    if world >= 8 and not args.grid and not getattr(args, "no_c4", False):
+        c4, _ = run_config("c4_mix_2048", None, min(args.steps, 2), 1, False, False)
+        # per-GPU work of C4 on 8 GPUs equals C3 on one GPU (2048^3 / 8 = 1024^3 voxels): weak-scaling efficiency
+        c4["one_gpu_reference"] = "c3_torus_1024 on one GPU (same voxels per GPU)"
+        c4["parallel_efficiency_vs_c3_one_gpu"] = c4["value"] / (world * c3["one_gpu_value"])
     clocks = sampler.stop() if sampler else None
-    eng.close()
-    V = ni * nj * nk
     if rank == 0:
         peak, peak_src = measured_peaks()
-        algo = 16.0 * (V / world)                            # per rank, per sweep launch
-        sweep_ms = dev_ms / (8 * st.passes)                  # upper bound: whole step / sweep launches
+        dev_ms = c3["ms_per_step"]
+        algo = 16.0 * (V / world)                            # per rank, per sweep
+        sweep_ms = c3["rank0_phase_ms"]["sweeps"] / 16.0
         line = {
-            "metric": METRIC, "value": V / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": c3["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "triangles": T, "grid": [ni, nj, nk], "slab_planes": k_hi - k_lo, "exact_band": 1,
-                       "sweep_passes": st.passes, "changed_per_pass": st.changed_per_pass,
-                       "sharding": "z-slabs, replicated mesh, halo planes over NCCL send/recv, passes until no cell changes",
+            "config": {"workload": c3["workload"], "triangles": T, "vertices": NV, "grid": [ni, nj, nk], "slab_planes": k_hi - k_lo,
+                       "exact_band": 1, "sweeps": 16,
+                       "sharding": "k-slabs, one rank per GPU, replicated triangle records; the 16 sweeps keep the reference's serial "
+                                   "order across slab faces: boundary planes handed over column by column inside the sweep kernel "
+                                   "(peer stores over NVLink + system-scope flags, CUDA IPC between the ranks), no collective in the "
+                                   "data path; bit-identical to one GPU (equal_to_one_gpu)",
                        "l2": "per-GPU grid state far larger than the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "kernel": "sweep (per rank)", "achieved": algo / (sweep_ms * 1e-3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": algo / (sweep_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "launch_ms here is step time / sweep launches (includes band, sign and halo exchange)"},
+            "strong_c3": c3,
+            "roofline": {"bound": "hbm", "kernel": "k_sweep_columns_fused<LINK> (16 sweeps in one launch per rank; per sweep = launch / 16)",
+                         "achieved": algo / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (sweep_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo, "launch_ms": sweep_ms,
+                         "note": "rank 0's sweep phase (CUDA events around the launch) / 16, against one GPU's HBM peak; includes the time the rank waits for its neighbours"},
             "cpu_baseline": None,
-            "e2e": {"value": V / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": (12 * T + 12 * NV) * world, "d2h_bytes_per_step": 4 * V,
-                    "mode": "streaming: host wall clock; each rank's D2H copy of step i overlaps step i+1"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": c3.get("e2e"),
+            "gpu_launches": int(c3["gpu_launches_per_rank"]) * world, "clocks": clocks,
         }
-        if exact:
-            line["exact_mode"] = exact
+        if c4:
+            line["c4"] = c4
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

@@ -58,6 +58,16 @@ def small_cases():
     out.append(_case("grid_1x1x1", *meshes.unit_cube(), [0.5, 0.5, 0.5], 0.1, 1, 1, 1))
     out.append(_case("grid_2x3x1", *meshes.unit_cube(), [0.4, 0.4, 0.5], 0.2, 2, 3, 1))
     out.append(_case("grid_1x5x4", *meshes.unit_cube(), [0.5, 0.1, 0.1], 0.2, 1, 5, 4))
+    # vertices outside the int range of grid coordinates (|x - o| / dx >= 2^31), infinite and NaN: the reference's
+    # int() yields INT_MIN there (cvttsd2si), its clamped loop bounds come out inverted along i/j/k and the loops at
+    # cpu_lib/makelevelset3.cpp:213-215 run zero times -- next to an ordinary cube so that the grid is not empty
+    v, t = meshes.unit_cube()
+    o, dx, ni, nj, nk = _grid(12, -0.3, 1.3)
+    for nm, bad in (("far_vertex", [1e12, 0.4, 0.6]), ("far_vertex_neg", [0.3, -1e12, 0.5]), ("far_vertex_k", [0.3, 0.5, 3e11]),
+                    ("inf_vertex", [np.inf, 0.4, 0.6]), ("nan_vertex", [0.2, np.nan, 0.6])):
+        v2 = np.concatenate([v, np.array([[0.1, 0.2, 0.3], [0.9, 0.3, 0.2], bad], np.float32)], axis=0)
+        t2 = np.concatenate([t, np.array([[8, 9, 10]], np.uint32)], axis=0)
+        out.append(_case(nm, v2, t2, o, dx, ni, nj, nk))
     return out
 
 
