@@ -574,6 +574,8 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
         // neighbour's launch may be enqueued by this very thread right after this one.
         if (p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_RELAX)) return fail(SDFB_ERR_STATE, "linked plans use the column schedule; SDFB_SWEEP_LEVELS / SDFB_SWEEP_RELAX cannot be combined with links");
         if (first + count > LINK_SWEEPS) return fail(SDFB_ERR_INVALID, "linked plans run the reference's %d sweeps only (asked for %d..%d)", LINK_SWEEPS, first, first + count - 1);
+        // a sweep's hand-over buffers and flags are written once per run: repeating an index would find the flags already raised
+        if (first != p->last_sweep + 1) return fail(SDFB_ERR_STATE, "linked plans run every sweep exactly once per sdfb_plan_band, in order (asked for %d after %d)", first, p->last_sweep);
         for (int side = 0; side < 2; ++side) {
             const bool has = side == 0 ? p->g.k_lo > 0 : p->g.k_hi < p->g.nk;
             if (has && !p->link.peer_halo[side]) return fail(SDFB_ERR_STATE, "linked plan: the slab %s this one has not been linked (sdfb_plan_link_import / _local)", side == 0 ? "below" : "above");

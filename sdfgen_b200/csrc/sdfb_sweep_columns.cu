@@ -125,6 +125,7 @@ struct ColParams {
     LinkSweep link;
     unsigned long long run_base;             // run << 32: link flag words are run_base | steps
     unsigned long long link_timeout_ns;      // watchdog of the waits on a neighbour GPU (0 = none)
+    int cta_queue;                           // fused launches: 1 = column-wide evaluation queue, 0 = warp-private queues
 };
 
 // smem exchange array: [2 slots][EK+1][EJ+1] words, index (b+1)*(EJ+1) + (a+1); a fastest
@@ -439,7 +440,7 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
                                                   uint32_t nb0, uint32_t nb1, uint32_t nb2, uint32_t nb3, uint32_t nb4,
                                                   uint32_t nb5, uint32_t nb6, uint32_t th0, uint32_t th1, uint32_t th2,
                                                   uint32_t th3, uint32_t th4, uint32_t th5, uint32_t th6,
-                                                  uint32_t cur, uint64_t *self_ptr, float phi)
+                                                  uint32_t cur, uint64_t *self_ptr, float phi, float &phi_new)
 {
     const Grid &g = P.g;
     uint32_t *const q_ent = sh.q_ent[warp];
@@ -505,6 +506,7 @@ __device__ __forceinline__ uint2 evaluate_candidates(const TriRec *__restrict__ 
         if (best != TRI_NONE) {
             cur = (P.stamp << 27) | best;
             *self_ptr = pack_cell(phi, cur);
+            phi_new = phi;
             changed = 1;
         }
     }
@@ -645,6 +647,7 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
     bool fresh = false;
     #pragma unroll
     for (int m = 0; m < 7; ++m) { t[m] = edge ? thr_edge[m] : thr[m]; fresh = fresh || (nb[m] >= t[m]); }
+    float phi_new = cell_phi(self);
     if (CTA_QUEUE) {
         // keep m if it names a triangle, not the voxel's own, and (memo) its cell changed since this voxel last looked
         uint32_t live = 0;
@@ -656,22 +659,21 @@ __device__ __forceinline__ void compute_step(const TriRec *__restrict__ rec, con
                 live |= keep ? (1u << m) : 0u;
             }
         }
-        float phi_new;
         const uint2 r = evaluate_candidates_cta(rec, P, sh, ri, (warp << 5) + lane, s, update, live,
                                                 nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6], cur, self_ptr, cell_phi(self), phi_new);
         cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
-        // LINK: a lane on the slab's last plane stores the voxel's final cell (changed or not, ri = 0 included) into the
-        // inbound plane of the slab above; the sync warp publishes the step count there after a system-scope fence
-        if (LINK && st.push_ptr) {
-            if ((unsigned)ri < (unsigned)ni) *st.push_ptr = pack_cell(phi_new, cur);
-            st.push_ptr += si;
-        }
     } else if (__any_sync(0xffffffffu, update && fresh)) {
         const uint2 r = evaluate_candidates(rec, P, sh, ri, lane, warp, update, false,
                                             nb[0], nb[1], nb[2], nb[3], nb[4], nb[5], nb[6],
                                             t[0], t[1], t[2], t[3], t[4], t[5], t[6],
-                                            cur, self_ptr, cell_phi(self));
+                                            cur, self_ptr, cell_phi(self), phi_new);
         cur = r.x; st.changed += r.y & 1u; st.evals += r.y >> 1;
+    }
+    // LINK: a lane on the slab's last plane stores the voxel's final cell (changed or not, ri = 0 included) into the
+    // inbound plane of the slab above; the sync warp publishes the step count there after a system-scope fence
+    if (LINK && st.push_ptr) {
+        if ((unsigned)ri < (unsigned)ni) *st.push_ptr = pack_cell(phi_new, cur);
+        st.push_ptr += si;
     }
     st.r1_old = r1; st.r3_old = r3; st.r5_old2 = st.r5_old; st.r5_old = r5;
     if (row_ok && (unsigned)ri < (unsigned)ni) { ring_w[PAR * RSTRIDE] = cur; st.prev_lo = cur; }
@@ -832,6 +834,8 @@ struct FusedParams {
     ColParams p[FUSE_MAX];
 };
 
+static_assert(sizeof(FusedParams) <= 4096, "FusedParams must stay within the classic 4 KB kernel parameter space");
+
 // LINK = exact multi-GPU mode: the slab's neighbours run the same launch on their GPUs; the first K block of every sweep
 // waits for (and reads) what the upstream neighbour's last K block hands over, the last K block hands its own boundary
 // plane to the downstream neighbour (LinkSweep in sdfb_kernels.cuh).  A column still only ever waits for columns with
@@ -868,10 +872,14 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
         }
         uint32_t *flags = progress + (q & 1) * FP.flag_stride;
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
+        // evaluation-heavy sweeps (the first pass) share one evaluation queue per column; light ones (the second pass, when
+        // it runs in this launch: linked slabs) keep warp-private queues and skip the queue barriers -- uniform per column
         if (tid < NCOMPUTE) {
-            compute_column<true, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+            if (P.cta_queue) compute_column<true, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
+            else compute_column<false, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
-            halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            if (P.cta_queue) halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            else halo_column<false, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
         } else if (tid < NSTEPPERS + 32) {
             if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, lane, J, K);
             bar_start_arrive();
@@ -935,6 +943,7 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
         if (!fill_col_params(P, g, first + q, *epoch + 1 + (uint32_t)q)) return 0;      // a sweep with nothing to update: do not fuse
         if ((size_t)P.NJ * P.NK > (size_t)FP.flag_stride) return 0;
         FP.col_begin[q + 1] = FP.col_begin[q] + P.NJ * P.NK;
+        P.cta_queue = tun.cta_queue >= 0 ? (tun.cta_queue != 0) : (first + q < 8);
         if (link) {
             // upstream side of this sweep: the slab below for dk > 0, above for dk < 0 (if there is one); downstream: the other
             const int s = first + q, up = P.sd.dk > 0 ? 0 : 1, down = 1 - up;

@@ -12,7 +12,7 @@ from sdfgen_b200 import _lib, meshes  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "c2_icosphere_512"
 grid = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("-") else None
 flags = 0
-for opt, f in (("--levels", _lib.SWEEP_LEVELS), ("--strips", _lib.SWEEP_STRIPS), ("--relax", _lib.SWEEP_RELAX), ("--columns", _lib.SWEEP_COLUMNS)):
+for opt, f in (("--levels", _lib.SWEEP_LEVELS), ("--relax", _lib.SWEEP_RELAX), ("--columns", _lib.SWEEP_COLUMNS)):
     if opt in sys.argv:
         flags = f
 w = meshes.workload(name, n=grid)
