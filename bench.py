@@ -375,6 +375,26 @@ def run_single_gpu(args):
                "sample": f"the same configuration at full size ({ni}^3, {T} triangles), one run ({dt:.1f} s), "
                          f"sdfgen::cpu::make_level_set3 num_threads=0 (auto) built in place from the reference sources"}
 
+    # the reference's OWN CUDA file recompiled for sm_100a ("the existing GPU kernel"): a different
+    # far-field algorithm (Jacobi Eikonal, 2*max(n) iterations) whose result differs from the CPU path by cell widths
+    # (its own tests accept 25) -- a labelled timing comparator beside the CPU baseline, one warm-up + one timed call
+    ref_gpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        if oracle.refgpu.available():
+            try:
+                oracle.refgpu.make_level_set3(w["vertices"], w["triangles"], w["origin"], w["dx"], ni, nj, nk, 1, want_phi=False)
+                rphi, rsec = oracle.refgpu.make_level_set3(w["vertices"], w["triangles"], w["origin"], w["dx"], ni, nj, nk, 1)
+                d = np.abs(np.abs(rphi) - np.abs(phi_pin.numpy())) / float(w["dx"])
+                ref_gpu = {"value": V / rsec / 1e9, "unit": UNIT, "ms_per_call": 1e3 * rsec,
+                           "what": "sdfgen::gpu::make_level_set3 of /root/reference/gpu_lib/makelevelset3_gpu.cu:595-777, unmodified, "
+                                   "nvcc -arch=sm_100a --fmad=false, whole call (cudaMalloc x8, H2D, kernels, D2H, cudaFree x8) -- comparable to e2e",
+                           "different_far_field": True, "max_abs_diff_vs_cpu_semantics_in_dx": float(d.max()),
+                           "frac_voxels_off_by_more_than_1e-5_dx": float((d > 1e-5).mean())}
+                del rphi, d
+            except Exception as e:      # a comparator must never take the bench down
+                ref_gpu = {"unavailable": repr(e)[:200]}
+
     fused = args.schedule == "default" and os.environ.get("SDFB_FUSE_PASS") != "0"
     line = {
         "metric": METRIC, "value": V / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -390,6 +410,7 @@ def run_single_gpu(args):
                      "path_achieved": path_achieved, "path_frac": path_achieved / peak,
                      "path_algorithmic_bytes": path_bytes, "issue": issue},
         "cpu_baseline": cpu,
+        "reference_gpu_kernel": ref_gpu,
         "e2e": e2e,
         "concurrent": concurrent,
         "gpu_launches": int(launches),

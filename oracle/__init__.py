@@ -233,8 +233,37 @@ class _Ref:
         return float(self.lib().ref_point_triangle_distance(*a))
 
 
+class _RefGpu:
+    """The reference's OWN CUDA file (gpu_lib/makelevelset3_gpu.cu), unmodified, recompiled in place for sm_100a
+    (oracle/_ref/libsdfgen_refgpu.so).  It computes a different far field (Jacobi Eikonal) -- a TIMING comparator for
+    bench.py ("the existing GPU kernel"), never a parity oracle."""
+    _lib = None
+    _SO = os.path.join(_HERE, "_ref", "libsdfgen_refgpu.so")
+
+    def available(self) -> bool:
+        return os.path.exists(self._SO)
+
+    def make_level_set3(self, vertices, triangles, origin, dx, ni, nj, nk, exact_band=1, want_phi=True):
+        """Returns (phi or None, seconds of the whole call: 8 cudaMalloc, H2D, kernels, D2H, 8 cudaFree)."""
+        if self._lib is None:
+            L = C.CDLL(self._SO)
+            L.sdfref_gpu_make_level_set3.restype = C.c_int
+            L.sdfref_gpu_make_level_set3.argtypes = [_u32p, C.c_uint64, _f32p, C.c_uint64, _f32p, C.c_float, C.c_int, C.c_int,
+                                                     C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+            self._lib = L
+        v, t, o = _prep(vertices, triangles, origin)
+        phi = np.empty(ni * nj * nk, np.float32) if want_phi else None
+        sec = C.c_double()
+        rc = self._lib.sdfref_gpu_make_level_set3(t, t.shape[0], v, v.shape[0], o, dx, ni, nj, nk, exact_band,
+                                                  phi.ctypes.data if want_phi else None, C.byref(sec))
+        if rc != 0:
+            raise RuntimeError(f"reference GPU path failed rc={rc}")
+        return phi, float(sec.value)
+
+
 port = _Port()
 ref = _Ref()
+refgpu = _RefGpu()
 
 
 def have_ref() -> bool:
