@@ -348,9 +348,11 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
         dev_ms, _ = _timed_linked(eng, w, steps, stream)
         launches = (sdfgen_b200.launch_count() - n0) // steps
         ph = eng.plan.phase_ms()
+        all_ph = [None] * world
+        dist.all_gather_object(all_ph, [round(ph["band"], 3), round(ph["sweeps"], 3), round(ph["sign"], 3)])
         res = {"workload": w["name"], "triangles": T, "vertices": NV, "grid": [ni, nj, nk], "slab_planes": k_hi - k_lo,
                "ms_per_step": dev_ms, "value": V / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "gpu_launches_per_rank": int(launches),
-               "rank0_phase_ms": ph}
+               "rank0_phase_ms": ph, "per_rank_band_sweeps_sign_ms": all_ph}
         # device-side checks (untimed): self-consistency of every cell, checksums that add up over the slabs
         chk = eng.plan.verify(stream=eng.sh)
         bad = torch.tensor([chk["inconsistent"]], dtype=torch.int64, device=dev)
@@ -389,15 +391,25 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
                 p1.set_mesh_host(w["vertices"], w["triangles"], stream=stream.cuda_stream)
                 for _ in range(2):
                     p1.run(w["origin"], w["dx"], 1, stream=stream.cuda_stream)
-                one = {"ms_per_step": p1.phase_ms()["total"]}
+                one = {"ms_per_step": p1.phase_ms()["total"], "phase_ms": p1.phase_ms()}
                 c1 = p1.verify(stream=stream.cuda_stream)
                 one["checksum_values"], one["checksum_cells"], one["inconsistent"] = c1["checksum_values"], c1["checksum_cells"], c1["inconsistent"]
                 p1.close()
+                # the same with the column schedule for all 16 sweeps (what the linked slabs run): separates the cost of the
+                # schedule from the cost of the cross-GPU pipeline
+                p2 = _lib.Plan(ni, nj, nk, device=local, flags=_lib.SWEEP_COLUMNS)
+                p2.set_mesh_host(w["vertices"], w["triangles"], stream=stream.cuda_stream)
+                for _ in range(2):
+                    p2.run(w["origin"], w["dx"], 1, stream=stream.cuda_stream)
+                one["all_columns_ms_per_step"] = p2.phase_ms()["total"]
+                p2.close()
                 sdfgen_b200.trim_memory()
             box = [one]
             dist.broadcast_object_list(box, src=0)
             one = box[0]
             res["one_gpu_ms_per_step"] = one["ms_per_step"]
+            res["one_gpu_phase_ms"] = one["phase_ms"]
+            res["one_gpu_all_columns_ms_per_step"] = one["all_columns_ms_per_step"]
             res["one_gpu_value"] = V / (one["ms_per_step"] * 1e-3) / 1e9
             res["speedup_vs_one_gpu"] = one["ms_per_step"] / dev_ms
             res["parallel_efficiency"] = one["ms_per_step"] / dev_ms / world
