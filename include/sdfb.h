@@ -228,6 +228,9 @@ int sdfb_plan_link_export(sdfb_plan *plan, void *handle_out);
  * k_lo), 1 = the slab above.  Works across processes (cudaIpcOpenMemHandle) and inside one (peer access is enabled
  * when the devices differ; two slabs may also share a device: then cap their grids with sdfb_plan_set_concurrency). */
 int sdfb_plan_link_import(sdfb_plan *plan, int32_t side, const void *handle);
+/* Diagnostics (plans created with SDFB_LINK_TRACE=1 in the environment): out[2s] / out[2s+1] = device time (globaltimer,
+ * ns) at which the first column of sweep s started / the last one ended on this slab since the last call; 0 = not run. */
+int sdfb_plan_link_trace(sdfb_plan *plan, void *stream, uint64_t out[32]);
 /* Drops all links (waits for the plan's device first).  Every rank must have finished its last run before any rank
  * unlinks or destroys a linked plan: a neighbour's sweep kernel stores into this plan's buffers. */
 int sdfb_plan_unlink(sdfb_plan *plan);

@@ -94,6 +94,8 @@ def lib():
     L.sdfb_plan_link_export.argtypes = [vp, vp]
     L.sdfb_plan_link_import.restype = C.c_int
     L.sdfb_plan_link_import.argtypes = [vp, i32, vp]
+    L.sdfb_plan_link_trace.restype = C.c_int
+    L.sdfb_plan_link_trace.argtypes = [vp, vp, C.POINTER(u64 * 32)]
     L.sdfb_plan_unlink.restype = C.c_int
     L.sdfb_plan_unlink.argtypes = [vp]
     L.sdfb_plan_download_global.restype = C.c_int
@@ -237,6 +239,12 @@ class Plan:
         """Map the inbound buffers of the plan holding the slab below (side 0) or above (side 1)."""
         buf = C.create_string_buffer(bytes(handle), LINK_HANDLE_BYTES)
         check(lib().sdfb_plan_link_import(self._h, int(side), buf))
+
+    def link_trace(self, stream=0):
+        """[(start_ns, end_ns)] of the 16 sweeps on this slab since the last call (SDFB_LINK_TRACE=1 at plan creation)."""
+        out = (C.c_uint64 * 32)()
+        check(lib().sdfb_plan_link_trace(self._h, stream or None, C.byref(out)))
+        return [(int(out[2 * s]), int(out[2 * s + 1])) for s in range(16)]
 
     def unlink(self):
         check(lib().sdfb_plan_unlink(self._h))

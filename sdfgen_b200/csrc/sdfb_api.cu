@@ -62,6 +62,8 @@ Tuning tuning_from_env()
     t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);
     t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
+    t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
+    t.link_trace = env_int("SDFB_LINK_TRACE", 0);
     return t;
 }
 }  // namespace sdfb
@@ -354,6 +356,7 @@ void link_release(sdfb_plan *p)
         p->link.peer_base[side] = nullptr; p->link.peer_halo[side] = nullptr; p->link.peer_flags[side] = nullptr;
     }
     if (p->link.in_halo) cudaFree(p->link.in_halo);
+    if (p->link.trace) cudaFree(p->link.trace);
     p->link = LinkState{};
     cudaGetLastError();
 }
@@ -384,6 +387,10 @@ int link_ensure_buffers(sdfb_plan *p)
     // flags start at 0 (below any run << 32 with run >= 1); zeroed and complete BEFORE any neighbour learns the address
     CU(cudaMemset(base, 0, bytes));
     CU(cudaDeviceSynchronize());
+    if (p->tun.link_trace) {
+        CU(cudaMalloc(reinterpret_cast<void **>(&p->link.trace), 2 * LINK_SWEEPS * sizeof(unsigned long long)));
+        CU(cudaMemset(p->link.trace, 0, 2 * LINK_SWEEPS * sizeof(unsigned long long)));
+    }
     p->link.in_halo = static_cast<uint64_t *>(base);
     p->link.in_flags = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + halo_bytes);
     p->link.bytes = bytes;
@@ -996,6 +1003,20 @@ int sdfb_plan_link_import(sdfb_plan *p, int32_t side, const void *handle)
     p->link.peer_halo[side] = static_cast<uint64_t *>(base);
     p->link.peer_flags[side] = reinterpret_cast<unsigned long long *>(static_cast<char *>(base) + halo_bytes);
     p->link.active = true;
+    return SDFB_OK;
+}
+
+int sdfb_plan_link_trace(sdfb_plan *p, void *stream, uint64_t out[32])
+{
+    if (!p || !out) return fail(SDFB_ERR_INVALID, "null argument");
+    if (!p->link.trace) return fail(SDFB_ERR_STATE, "no trace: create the plan with SDFB_LINK_TRACE=1 in the environment and link it");
+    DeviceGuard dg(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long h[2 * LINK_SWEEPS];
+    CU(cudaMemcpyAsync(h, p->link.trace, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemsetAsync(p->link.trace, 0, sizeof(h), st));
+    CU(cudaStreamSynchronize(st));
+    for (int s = 0; s < LINK_SWEEPS; ++s) { out[2 * s] = h[2 * s] ? ~h[2 * s] : 0; out[2 * s + 1] = h[2 * s + 1]; }
     return SDFB_OK;
 }
 

@@ -40,6 +40,10 @@ struct Tuning {
     int relax_scan_from = 13;     // SDFB_RELAX_SCAN_FROM: first sweep whose round 0 uses the lean scan kernel
     int relax_debug = 0;          // SDFB_RELAX_DEBUG: per-sweep round statistics on stderr
     int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
+    int link_debug = 0;           // SDFB_LINK_DEBUG: TIMING EXPERIMENTS ONLY, results are wrong -- 1: boundary cells are stored into a
+                                  // local dummy plane instead of the neighbour's memory, 2: device-scope fence before the link flag,
+                                  // 4: do not wait for the upstream neighbour's flags
+    int link_trace = 0;           // SDFB_LINK_TRACE: record first-column-start / last-column-end times of every sweep (sdfb_plan_link_trace)
 };
 Tuning tuning_from_env();
 
@@ -68,6 +72,7 @@ struct LinkState {          // host side, per plan
     unsigned long long run = 0;                     // band() calls so far: flag words are run << 32 | steps
     int NJ = 0;
     size_t bytes = 0;
+    unsigned long long *trace = nullptr;            // SDFB_LINK_TRACE: 2 x LINK_SWEEPS words (~start, end in globaltimer ns), else nullptr
 };
 
 struct Launches { uint64_t n = 0; };

@@ -126,6 +126,7 @@ struct ColParams {
     unsigned long long run_base;             // run << 32: link flag words are run_base | steps
     unsigned long long link_timeout_ns;      // watchdog of the waits on a neighbour GPU (0 = none)
     int cta_queue;                           // fused launches: 1 = column-wide evaluation queue, 0 = warp-private queues
+    int link_gpu_fence;                      // SDFB_LINK_DEBUG & 2 (timing experiment): device-scope fence before the link flag
 };
 
 // smem exchange array: [2 slots][EK+1][EJ+1] words, index (b+1)*(EJ+1) + (a+1); a fastest
@@ -324,7 +325,7 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
                     // release at system scope: the boundary-plane cells the compute lanes stored into the neighbour's
                     // memory (peer stores over NVLink, ordered before sh.done by the CTA barrier) are visible there
                     // before the word that announces them
-                    __threadfence_system();
+                    if (P.link_gpu_fence) __threadfence(); else __threadfence_system();
                     *reinterpret_cast<volatile unsigned long long *>(link_mine) = P.run_base + (unsigned long long)(d * PUBLISH);
                 } else {
                     __threadfence();                       // release: the chunk's stores happen-before the flag
@@ -831,6 +832,7 @@ struct FusedParams {
     int n;                       // sweeps in this launch
     int col_begin[FUSE_MAX + 1]; // first ticket of each sweep
     int flag_stride;             // words between the two progress arrays
+    unsigned long long *trace;   // SDFB_LINK_TRACE: [2q] = max over columns of ~start time, [2q+1] = max of end time (globaltimer ns)
     ColParams p[FUSE_MAX];
 };
 
@@ -872,6 +874,7 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
         }
         uint32_t *flags = progress + (q & 1) * FP.flag_stride;
         const int rj0 = 1 + J * EJ, rk0 = P.rk_first + K * EK;
+        if (LINK && FP.trace && tid == 0) atomicMax(&FP.trace[2 * q], ~global_timer_ns());
         // evaluation-heavy sweeps (the first pass) share one evaluation queue per column; light ones (the second pass, when
         // it runs in this launch: linked slabs) keep warp-private queues and skip the queue barriers -- uniform per column
         if (tid < NCOMPUTE) {
@@ -890,6 +893,7 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
             sync_column<LINK>(P, sh, lane, prog_left, prog_down, &flags[K * P.NJ + J], link_down, link_mine);
         }
         __syncthreads();
+        if (LINK && FP.trace && tid == 0) atomicMax(&FP.trace[2 * q + 1], global_timer_ns());
     }
     unsigned wsum = my_changed, esum = my_evals;
     for (int o = 16; o > 0; o >>= 1) { wsum += __shfl_down_sync(0xffffffffu, wsum, o); esum += __shfl_down_sync(0xffffffffu, esum, o); }
@@ -936,6 +940,7 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     if (link && first + count > LINK_SWEEPS) return 0;
     FusedParams FP{};
     FP.n = count;
+    FP.trace = link && link->trace ? link->trace + 2 * first : nullptr;
     FP.flag_stride = (int)((progress_words - 4) / 2);
     FP.col_begin[0] = 0;
     for (int q = 0; q < count; ++q) {
@@ -955,6 +960,10 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
                 P.link.halo_dst = link->peer_halo[down] + (size_t)s * plane;
                 P.link.flag_dst = link->peer_flags[down] + (size_t)s * link->NJ;
             }
+            // timing experiments (SDFB_LINK_DEBUG, results are wrong): local stores / no upstream wait / device-scope fence
+            if ((tun.link_debug & 1) && has_down) P.link.halo_dst = link->in_halo + (size_t)((s + 8) % LINK_SWEEPS) * plane;
+            if ((tun.link_debug & 4) && has_up) P.link.flag_src = nullptr;
+            P.link_gpu_fence = (tun.link_debug & 2) ? 1 : 0;
             P.run_base = link->run << 32;
             P.link_timeout_ns = tun.link_timeout_s > 0 ? (unsigned long long)tun.link_timeout_s * 1000000000ull : 0ull;
         }
