@@ -28,7 +28,8 @@ def build():
     return L
 
 
-def run_case(L, dims, bounds, EJ, EK, count, W, seed, level=3):
+def run_case(L, dims, bounds, EJ, EK, count, W, seed, level=3, order_w=1):
+    L.linked_emulation_set_order_w(order_w)       # ticket order by w*J + K, as the device's launches (SDFB_ORDER_W)
     ni, nj, nk = dims
     v, f = meshes.icosphere(level, 0.4)
     v, f = np.ascontiguousarray(v, np.float32), np.ascontiguousarray(f, np.uint32)

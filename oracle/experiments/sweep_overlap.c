@@ -269,8 +269,20 @@ static void relax_linked(const Slab *S, int s, int i, int j, int k, int di, int 
     }
 }
 
+static int g_order_w = 1;                   /* tickets ordered by w*J + K: 1 = anti-diagonals, >= NK = row by row (LITERAL PORT of the device decode) */
+void linked_emulation_set_order_w(int v) { g_order_w = v < 1 ? 1 : v; }
 static void ticket_to_JK(const SP *P, int loc, int *J, int *K)
 {
+    if (g_order_w > 1) {
+        const int w = g_order_w;
+        int g = 0, rem = loc;
+        for (;;) {
+            int jlo = g - (P->NK - 1) > 0 ? (g - (P->NK - 1) + w - 1) / w : 0, jhi = g / w < P->NJ - 1 ? g / w : P->NJ - 1;
+            int cnt = jhi - jlo + 1;
+            if (cnt > 0) { if (rem < cnt) { *J = jlo + rem; *K = g - w * *J; return; } rem -= cnt; }
+            ++g;
+        }
+    }
     int d = 0, rem = loc;
     for (;;) { int lo = d - (P->NK - 1) > 0 ? d - (P->NK - 1) : 0, hi = d < P->NJ - 1 ? d : P->NJ - 1, cnt = hi - lo + 1; if (rem < cnt) { *J = lo + rem; *K = d - *J; return; } rem -= cnt; ++d; }
 }

@@ -62,6 +62,7 @@ Tuning tuning_from_env()
     t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);
     t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
+    t.order_w = env_int("SDFB_ORDER_W", -1);
     t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
     t.link_trace = env_int("SDFB_LINK_TRACE", 0);
     return t;

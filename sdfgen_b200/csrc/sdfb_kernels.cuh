@@ -39,6 +39,7 @@ struct Tuning {
     long long relax_heavy_limit = -1;   // SDFB_RELAX_HEAVY_LIMIT: work-list entries before a sweep is handed back to the columns
     int relax_scan_from = 13;     // SDFB_RELAX_SCAN_FROM: first sweep whose round 0 uses the lean scan kernel
     int relax_debug = 0;          // SDFB_RELAX_DEBUG: per-sweep round statistics on stderr
+    int order_w = -1;             // SDFB_ORDER_W: ticket order of fused launches by the key w*J + K (1 = anti-diagonals, >= NK = row by row)
     int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
     int link_debug = 0;           // SDFB_LINK_DEBUG: TIMING EXPERIMENTS ONLY, results are wrong -- 1: boundary cells are stored into a
                                   // local dummy plane instead of the neighbour's memory, 2: device-scope fence before the link flag,

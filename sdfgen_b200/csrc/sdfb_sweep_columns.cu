@@ -832,6 +832,7 @@ struct FusedParams {
     int n;                       // sweeps in this launch
     int col_begin[FUSE_MAX + 1]; // first ticket of each sweep
     int flag_stride;             // words between the two progress arrays
+    int order_w;                 // ticket order inside a sweep: by w*J + K; 1 = anti-diagonals J + K (see the decode in the kernel)
     unsigned long long *trace;   // SDFB_LINK_TRACE: [2q] = max over columns of ~start time, [2q+1] = max of end time (globaltimer ns)
     ColParams p[FUSE_MAX];
 };
@@ -863,7 +864,21 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
         const ColParams &P = FP.p[q];
         const int tk = tk_all - FP.col_begin[q];
         int J, K;
-        {
+        if (FP.order_w > 1) {
+            // Tickets ordered by the key w*J + K (ties: J ascending).  w = 1 is the anti-diagonal order; a larger w brings
+            // the columns of the LAST K block -- the ones a linked slab above waits for -- forward: the neighbour trails
+            // this slab by K_last / w rows of J instead of K_last anti-diagonals, at the price of more columns that hold a
+            // slot before their producers are far enough (w >= NK is row by row).  Both in-sweep prerequisites, (J-1,K) with
+            // key - w and (J,K-1) with key - 1, still hold lower tickets.
+            const int w = FP.order_w;
+            int g = 0, rem = tk;
+            for (;;) {
+                int jlo = g - (P.NK - 1) > 0 ? (g - (P.NK - 1) + w - 1) / w : 0, jhi = min(g / w, P.NJ - 1);
+                int cnt = jhi - jlo + 1;
+                if (cnt > 0) { if (rem < cnt) { J = jlo + rem; K = g - w * J; break; } rem -= cnt; }
+                ++g;
+            }
+        } else {
             int d = 0, rem = tk;
             for (;;) {
                 int lo = max(0, d - (P.NK - 1)), hi = min(d, P.NJ - 1);
@@ -941,6 +956,7 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     FusedParams FP{};
     FP.n = count;
     FP.trace = link && link->trace ? link->trace + 2 * first : nullptr;
+    FP.order_w = tun.order_w >= 1 ? tun.order_w : 1;
     FP.flag_stride = (int)((progress_words - 4) / 2);
     FP.col_begin[0] = 0;
     for (int q = 0; q < count; ++q) {

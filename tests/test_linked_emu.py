@@ -27,7 +27,8 @@ def test_linked_slabs_protocol_is_exact_and_deadlock_free(lib, case):
     assert overlap > 0          # the slabs really were in different sweeps at the same time
 
 
-def test_other_interleavings(lib):
+def test_other_interleavings_and_ticket_orders(lib):
     for seed in range(20, 26):
-        rc, _ = le.run_case(lib, (18, 27, 48), (0, 12, 24, 36, 48), 8, 16, 16, 2, seed)
-        assert rc == 0, (seed, rc)
+        for w in (1, 2, 3, 64):                   # anti-diagonals, J-weighted keys, row by row
+            rc, _ = le.run_case(lib, (18, 27, 48), (0, 12, 24, 36, 48), 8, 4, 16, 2, seed, order_w=w)
+            assert rc == 0, (seed, w, rc)
