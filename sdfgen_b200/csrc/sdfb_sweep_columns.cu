@@ -321,16 +321,19 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
             idle = 0;
         } else if (act == 2) {
             if (lane == 0) {
+                // RELEASE stores, not __threadfence() + store: the chunk's cell stores (made by the compute lanes, ordered
+                // before sh.done by the CTA barrier and observed here through it) happen-before the flag, and that is all a
+                // producer needs.  __threadfence() is fence.sc and ptxas follows it with CCTL.IVALL, which throws away the
+                // SM's whole L1 -- three CTAs per SM doing that every two steps kept the triangle records (the only data
+                // this kernel reads through L1) out of it.  st.release = MEMBAR.ALL + store, no invalidate.
                 if (LINK && link_mine) {
-                    // release at system scope: the boundary-plane cells the compute lanes stored into the neighbour's
-                    // memory (peer stores over NVLink, ordered before sh.done by the CTA barrier) are visible there
-                    // before the word that announces them
-                    if (P.link_gpu_fence) __threadfence(); else __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long *>(link_mine) = P.run_base + (unsigned long long)(d * PUBLISH);
-                } else {
-                    __threadfence();                       // release: the chunk's stores happen-before the flag
+                    // system scope: the boundary-plane cells stored into the neighbour's memory (peer stores over NVLink)
+                    // are visible there before the word that announces them
+                    const unsigned long long v = P.run_base + (unsigned long long)(d * PUBLISH);
+                    if (P.link_gpu_fence) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(link_mine), "l"(v) : "memory");
+                    else asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(link_mine), "l"(v) : "memory");
                 }
-                *reinterpret_cast<volatile uint32_t *>(prog_mine) = ebase + (uint32_t)(d * PUBLISH);
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_mine), "r"(ebase + (uint32_t)(d * PUBLISH)) : "memory");
             }
             published = d;
             idle = 0;
