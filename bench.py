@@ -431,6 +431,7 @@ def main():
     ap.add_argument("--schedule", default="default", choices=["default", "columns", "relax", "levels"])
     ap.add_argument("--exact", action="store_true", help="accepted for compatibility: N > 1 always runs the exact (linked) mode")
     ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the 2048^3 configuration")
+    ap.add_argument("--no-c4-one-gpu", action="store_true", help="N = 8: skip the one-GPU run of the 2048^3 configuration (about 35 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident leg only (for the ncu launch list)")
     args = ap.parse_args()
