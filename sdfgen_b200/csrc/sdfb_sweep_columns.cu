@@ -75,6 +75,7 @@ constexpr int NSTEPPERS = NCOMPUTE + NHALO;  // lanes that take part in the per-
 constexpr bool WG = SDFB_WG != 0;
 constexpr bool HALO_EVAL = !WG || SDFB_WG_HALO_EVAL != 0;   // the halo warp takes a share of the evaluations
 static_assert(!WG || NCOMPUTE == 128, "the warpgroup layout needs exactly four compute warps");
+static_assert(EJ * EK <= 256, "queue entries carry the owner lane in 8 bits");
 constexpr int NTHREADS = WG ? 256 : NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
 constexpr int EVAL_LANES = HALO_EVAL ? NSTEPPERS : NCOMPUTE;   // lanes that share the column-wide evaluation queue
 #ifndef SDFB_SYNC_SLEEP
@@ -101,6 +102,17 @@ constexpr bool QATOMIC = SDFB_QATOMIC != 0;
 #ifndef SDFB_ENQ_PF
 #define SDFB_ENQ_PF 0
 #endif
+// SDFB_STAGE (experiment of round 2, OFF): triangle records of a step's candidates are copied into shared memory with
+// cp.async (LDGSTS) by the lane that owns the voxel as soon as its candidate list is known, so that the record gather
+// overlaps the queue barriers instead of heading every evaluation round (profiles/r2_column_step_phases.txt: one round =
+// ~1000 cycles for ~190 instructions).  Bit-exact and 16-24 % SLOWER at C2 (first pass 67-74 ms with 2-5 slots per lane
+// against 54.9 ms without, profiles/r2_variants.txt): neighbouring voxels share candidates, so the L1-cached gather by
+// the evaluating lanes moves far fewer bytes than one private copy per (voxel, candidate), and the copy instructions sit
+// on the filter's critical path.  -DSDFB_STAGE=<slots per lane> builds it.
+#ifndef SDFB_STAGE
+#define SDFB_STAGE 0
+#endif
+constexpr int STAGE = SDFB_STAGE;            // staged records per compute lane and step (0 = off)
 constexpr int SHIFT = 2;                     // lane (a,b) handles ri = s - a - b - SHIFT, so halo lane (-1,-1) starts at ri = 0
 constexpr int QCAP = 7 * 32;                 // queue entries per warp
 
@@ -174,6 +186,7 @@ struct ColShared {
     int qn;                                           // SDFB_QATOMIC: entries reserved in this step (zeroed by lane 0 after use)
     int col;
     volatile int done;      // chunks whose steps are complete; written by compute lane 0
+    float4 stage[STAGE > 0 ? NCOMPUTE * STAGE * 3 : 1];   // SDFB_STAGE: [owner lane][slot] -> the record's three float4
 };
 
 // Evaluation share of one lane in the column-wide queue: entries first, first+EVAL_LANES, ...
@@ -191,10 +204,17 @@ __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restric
             asm volatile("prefetch.global.L1 [%0];" ::"l"(ra + 32));
         }
 #endif
-        const int ot = __float_as_int(q_d[q]);                         // owner lane, replaced by the distance
+        const int oe = __float_as_int(q_d[q]);                         // owner lane | staged slot << 8, replaced by the distance
+        const int ot = oe & 0xff;
         const F3 gx{sh.gx[ot], sh.gy[ot], sh.gz[ot]};
-        const TriRec *tr = &rec[q_ent[q]];
-        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        float4 p, qq, r;
+        if (STAGE > 0 && (oe >> 8) < STAGE) {                          // the owner staged this record in shared memory
+            const float4 *sr = &sh.stage[(ot * STAGE + (oe >> 8)) * 3];
+            p = sr[0]; qq = sr[1]; r = sr[2];
+        } else {
+            const TriRec *tr = &rec[q_ent[q]];
+            p = __ldg(&tr->p); qq = __ldg(&tr->q); r = __ldg(&tr->r);
+        }
         q_d[q] = ptd_rec(gx, p, qq, r);
         ++evals;
     }
@@ -546,6 +566,21 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
         }
     }
     const int ncand = __popc(live);
+    if (STAGE > 0 && live) {
+        // start the gather of the first STAGE candidates' records into this lane's slots (16-byte cp.async, L1-allocating);
+        // completion is awaited before the second queue barrier, which publishes the slots to the evaluating lanes
+        int slot = 0;
+        #pragma unroll
+        for (int m = 0; m < 7; ++m) if (((live >> m) & 1u) && slot < STAGE) {
+            const char *src = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sh.stage[(tid * STAGE + slot) * 3]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 16) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 32), "l"(src + 32) : "memory");
+            ++slot;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     const uint32_t b0 = __ballot_sync(0xffffffffu, ncand & 1), b1 = __ballot_sync(0xffffffffu, ncand & 2),
                    b2 = __ballot_sync(0xffffffffu, ncand & 4);
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -572,7 +607,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
         #pragma unroll
         for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
             q_ent[w] = nb[m] & TRI_MASK;
-            q_d[w] = __int_as_float(tid);                              // owner, replaced by the distance below
+            q_d[w] = __int_as_float(tid | ((w - off) << 8));           // owner | slot, replaced by the distance below
             ++w;
 #if SDFB_ENQ_PF
             const char *ra = reinterpret_cast<const char *>(&rec[nb[m] & TRI_MASK]);
@@ -581,6 +616,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
 #endif
         }
     }
+    if (STAGE > 0) asm volatile("cp.async.wait_all;" ::: "memory");  // this lane's staged records have landed (no-op without any)
     TRACE(P, warp, s, 3);
     bar_compute();
     TRACE(P, warp, s, 4);
