@@ -47,10 +47,17 @@ ms = timed(lambda: p.run(w["origin"], w["dx"], 1))
 out["independent_slabs_columns_ms"] = ms
 p.close()
 
-variants = [(int(a.split(":")[0]), int(a.split(":")[1])) for a in (os.environ.get("PROBE_VARIANTS") or "1:0,1:4,2:0,4:0,8:0,64:0").split(",")]
-for order_w, dbg in variants:                     # (SDFB_ORDER_W, SDFB_LINK_DEBUG)
+# variants: comma-separated SDFB_ORDER_W:SDFB_LINK_DEBUG[:SDFB_MINB[:SDFB_MAX_OCC]]
+variants = [tuple(int(x) for x in a.split(":")) for a in (os.environ.get("PROBE_VARIANTS") or "1:0,1:4,2:0,4:0,8:0,64:0").split(",")]
+for var in variants:
+    order_w, dbg = var[0], var[1]
     os.environ["SDFB_LINK_DEBUG"] = str(dbg)
     os.environ["SDFB_ORDER_W"] = str(order_w)
+    for name_, idx in (("SDFB_MINB", 2), ("SDFB_MAX_OCC", 3)):
+        if len(var) > idx and var[idx] > 0:
+            os.environ[name_] = str(var[idx])
+        else:
+            os.environ.pop(name_, None)
     os.environ["SDFB_LINK_TRACE"] = "1"
     eng = sdist.CudaSlabEngine(ni, nj, nk, k_lo, k_hi, local)
     sdist.link_slabs(eng, rank, world)
@@ -65,7 +72,7 @@ for order_w, dbg in variants:                     # (SDFB_ORDER_W, SDFB_LINK_DEB
     rel = [[round((a - t0) * 1e-6, 2), round((b - t0) * 1e-6, 2)] for a, b in tr]
     allrel = [None] * world
     dist.all_gather_object(allrel, (t0, rel))
-    out["runs"].append({"order_w": order_w, "link_debug": dbg, "ms_one_step": ms, "ms_per_step_3": ms3,
+    out["runs"].append({"order_w": order_w, "link_debug": dbg, "variant": list(var), "ms_one_step": ms, "ms_per_step_3": ms3,
                         "sweep_windows_ms_rel_to_own_sweep0_start": [r[1] for r in allrel],
                         "sweep0_start_ns": [r[0] for r in allrel]})
     sdist.unlink_slabs(eng)
@@ -73,7 +80,7 @@ for order_w, dbg in variants:                     # (SDFB_ORDER_W, SDFB_LINK_DEB
 if rank == 0:
     print("LINK_PROBE " + json.dumps(out))
     for r in out["runs"]:
-        print(f"\n== SDFB_ORDER_W={r['order_w']} SDFB_LINK_DEBUG={r['link_debug']}: {r['ms_per_step_3']:.1f} ms per step (independent slabs: {out['independent_slabs_columns_ms']:.1f})")
+        print(f"\n== variant {r['variant']} (order_w:link_debug:minb:max_occ): {r['ms_per_step_3']:.1f} ms per step (independent slabs: {out['independent_slabs_columns_ms']:.1f})")
         base = min(r["sweep0_start_ns"])
         if os.environ.get("PROBE_QUIET"):
             continue
