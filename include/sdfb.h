@@ -231,8 +231,10 @@ int sdfb_plan_link_import(sdfb_plan *plan, int32_t side, const void *handle);
 /* Diagnostics (plans created with SDFB_LINK_TRACE=1 in the environment): out[2s] / out[2s+1] = device time (globaltimer,
  * ns) at which the first column of sweep s started / the last one ended on this slab since the last call; 0 = not run. */
 int sdfb_plan_link_trace(sdfb_plan *plan, void *stream, uint64_t out[32]);
-/* Drops all links (waits for the plan's device first).  Every rank must have finished its last run before any rank
- * unlinks or destroys a linked plan: a neighbour's sweep kernel stores into this plan's buffers. */
+/* Drops this plan's mappings of its neighbours' buffers (waits for the plan's device first); its own inbound buffers
+ * stay allocated until sdfb_plan_destroy.  Order for a clean shutdown: every rank finishes its last run -> barrier -> every
+ * rank calls sdfb_plan_unlink -> barrier -> sdfb_plan_destroy (a neighbour's sweep kernel stores into this plan's buffers,
+ * and an exported block should outlive the mappings of it). */
 int sdfb_plan_unlink(sdfb_plan *plan);
 /* sdfb_plan_download into arrays of the WHOLE grid: the slab is written at its place (either layout). */
 int sdfb_plan_download_global(sdfb_plan *plan, float *phi_grid, int32_t *closest_tri_grid,

@@ -350,12 +350,20 @@ int build_records(sdfb_plan *p, const uint32_t *d_tri, const float *d_xyz, uint6
 }
 
 // exact multi-GPU mode: unmap the neighbours' buffers and free our own (the caller made sure no neighbour still writes)
-void link_release(sdfb_plan *p)
+// drop the mappings of the neighbours' buffers (importer side); this plan's own inbound buffers stay allocated
+void link_close_peers(sdfb_plan *p)
 {
     for (int side = 0; side < 2; ++side) {
         if (p->link.peer_base[side]) cudaIpcCloseMemHandle(p->link.peer_base[side]);
         p->link.peer_base[side] = nullptr; p->link.peer_halo[side] = nullptr; p->link.peer_flags[side] = nullptr;
     }
+    p->link.active = false;
+    cudaGetLastError();
+}
+
+void link_release(sdfb_plan *p)
+{
+    link_close_peers(p);
     if (p->link.in_halo) cudaFree(p->link.in_halo);
     if (p->link.trace) cudaFree(p->link.trace);
     p->link = LinkState{};
@@ -1026,7 +1034,9 @@ int sdfb_plan_unlink(sdfb_plan *p)
     if (!p) return fail(SDFB_ERR_INVALID, "plan is null");
     DeviceGuard dg(p->device);
     plan_quiesce(p);
-    link_release(p);
+    // importer side only: the exported block itself is freed by sdfb_plan_destroy (or reused by the next export), i.e. after
+    // every neighbour had the chance to close its mapping of it
+    link_close_peers(p);
     return SDFB_OK;
 }
 

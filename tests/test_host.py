@@ -98,3 +98,22 @@ def test_repository_name_alias_is_the_same_package():
     assert d is dist and sdfgenfast_b200._lib is sdfgen_b200._lib
     for name in ("generate_sdf", "generate_from_file", "generate_from_mesh", "is_gpu_available", "Plan"):
         assert getattr(sdfgenfast_b200, name) is getattr(sdfgen_b200, name)
+
+
+def test_c_slab_bounds_match_the_python_side():
+    """sdfb_slab_bounds (C ABI, used by sdfb_make_level_set3_multi) and dist.slab_bounds cut the k range the same way:
+    contiguous, covering, the first nk % slabs slabs one plane thicker."""
+    import ctypes as C
+    from sdfgen_b200 import _lib, dist
+    L = _lib.lib()
+    for nk, n in [(1024, 8), (2048, 8), (105, 4), (7, 7), (9, 2), (16, 3)]:
+        prev = 0
+        for r in range(n):
+            a, b = C.c_int32(), C.c_int32()
+            assert L.sdfb_slab_bounds(nk, n, r, C.byref(a), C.byref(b)) == 0
+            assert (a.value, b.value) == dist.slab_bounds(nk, n, r)
+            assert a.value == prev and b.value > a.value
+            prev = b.value
+        assert prev == nk
+    a, b = C.c_int32(), C.c_int32()
+    assert L.sdfb_slab_bounds(4, 5, 0, C.byref(a), C.byref(b)) == _lib.ERR_INVALID      # more slabs than planes
