@@ -1,7 +1,9 @@
 // sdfb_sweep_columns.cu -- the production sweep schedule: pipelined columns.
 //
-// One launch per sweep direction (k_sweep_columns), or the whole first pass in one launch with consecutive sweeps
-// overlapping where their directions allow it (k_sweep_columns_fused, near the end of this file).
+// One launch per sweep direction (k_sweep_columns), or several sweeps in one launch with consecutive sweeps overlapping
+// where their directions allow it (k_sweep_columns_fused, near the end of this file): the first pass of a plan on one GPU,
+// all 16 sweeps of a LINKED k-slab -- the exact multi-GPU mode, in which the columns of a slab's last K block hand their
+// boundary-plane cells to the slab above over NVLink (template parameter LINK).
 // In sweep-relative coordinates (ri,rj,rk >= 0, counted from the corner the sweep starts at) the (rj,rk) plane is cut into columns of EJ x EK rows.  A CTA owns one
 // column at a time and marches along i: lane (a,b) of the column handles voxel ri = s - a - b - 2 at step
 // s, so lanes are skewed along the anti-diagonal and every one of the seven upstream neighbours
@@ -23,8 +25,10 @@
 // (J-1), below (K-1) or diagonal, or to the read-only ri/rj/rk = 0 faces (or a slab halo plane).
 // Columns are handed out by an atomic ticket in anti-diagonal order (J+K), so a column's producers
 // always hold lower tickets and are running or finished: the spin on their progress counters cannot
-// deadlock.  A column publishes its step count every PUBLISH steps (__syncthreads, __threadfence,
-// store); a consumer column may run step s once left >= s+EJ+2+... (see need_left/need_down).
+// deadlock.  A column publishes its step count every PUBLISH steps (CTA barrier, then a RELEASE store by the
+// sync warp: st.release.gpu, not __threadfence() + store -- fence.sc drags a CCTL.IVALL behind it that empties
+// the SM's L1, the cache the triangle records live in); a consumer column may run step s once
+// left >= s+EJ+2+... (see sync_column).
 // Every dependency of the serial Gauss-Seidel order is respected, so the result is bit-identical to
 // the reference's single-threaded sweep.
 //
@@ -93,6 +97,16 @@ constexpr int PUBLISH = SDFB_PUBLISH;                   // steps between progres
 #define SDFB_QATOMIC 0
 #endif
 constexpr bool QATOMIC = SDFB_QATOMIC != 0;
+// SDFB_ONEBAR: every warp of a column enqueues into ITS OWN region of the queue (offsets from its own ballots) before the
+// first queue barrier; the evaluating lanes map a global entry number to (warp region, local index) from the four warp
+// totals.  The barrier that only existed to exchange those totals before the enqueue disappears: a working step takes 3
+// CTA barriers instead of 4 and the enqueue no longer waits for the slowest warp's filter.  No atomic (unlike
+// SDFB_QATOMIC): nothing new on any warp's critical path but three compares per evaluated entry.
+#ifndef SDFB_ONEBAR
+#define SDFB_ONEBAR 0
+#endif
+constexpr bool ONEBAR = SDFB_ONEBAR != 0;
+static_assert(!(ONEBAR && QATOMIC), "SDFB_ONEBAR and SDFB_QATOMIC are alternatives");
 // SDFB_EVAL_PF: before a lane evaluates a queue entry it starts the record gather of its NEXT entry (L1 prefetch), so
 // the second evaluation round of a step finds its triangle in L1.  SDFB_ENQ_PF: the enqueuing lane prefetches the
 // records of its own candidates into the SM's L1 (every lane of the column shares it) two barriers before they are read.
@@ -195,9 +209,22 @@ __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restric
     uint32_t *const q_ent = &sh.q_ent[0][0];
     float *const q_d = &sh.q_d[0][0];
     unsigned evals = 0;
-    int q = first;
-    for (; q < total; q += EVAL_LANES) {
-#if SDFB_EVAL_PF
+    int bnd[NCOMPUTE / 32];                       // SDFB_ONEBAR: first global entry number of each warp's region
+    if (ONEBAR) {
+        int acc = 0;
+        #pragma unroll
+        for (int w = 0; w < NCOMPUTE / 32; ++w) { bnd[w] = acc; acc += sh.wtot[w]; }
+    }
+    int qg = first;
+    for (; qg < total; qg += EVAL_LANES) {
+        int q = qg;
+        if (ONEBAR) {                             // global entry number -> slot in the owning warp's region
+            int w = 0, bw = 0;                    // selects, not bnd[w]: a dynamic index would put bnd[] in local memory
+            #pragma unroll
+            for (int u = 1; u < NCOMPUTE / 32; ++u) { const bool ge = qg >= bnd[u]; w += ge ? 1 : 0; bw = ge ? bnd[u] : bw; }
+            q = w * QCAP + (qg - bw);
+        }
+#if SDFB_EVAL_PF && !SDFB_ONEBAR
         if (q + EVAL_LANES < total) {
             const char *ra = reinterpret_cast<const char *>(&rec[q_ent[q + EVAL_LANES]]);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(ra));
@@ -237,7 +264,7 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
     #pragma unroll
     for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
     if (total == 0) return 0u;
-    bar_compute();
+    if (!ONEBAR) bar_compute();                   // SDFB_ONEBAR: the entries were written before the first barrier
     const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, NCOMPUTE + h, total) : 0u;
     bar_compute();
     return e;
@@ -591,6 +618,9 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
             if (lane == 0) base = atomicAdd(&sh.qn, wt);
             base = __shfl_sync(0xffffffffu, base, 0);
         }
+    } else if (ONEBAR) {
+        if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        base = warp * QCAP;                                           // this warp's own region: no other warp's total needed
     } else {
         if (lane == 0) sh.wtot[warp] = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         TRACE(P, warp, s, 1);
@@ -622,6 +652,11 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
     TRACE(P, warp, s, 4);
     if (QATOMIC) {
         total = *reinterpret_cast<volatile int *>(&sh.qn);            // final: every warp reserved before the barrier
+        if (total == 0) return make_uint2(cur, 0u);                   // uniform over the column
+    }
+    if (ONEBAR) {
+        #pragma unroll
+        for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
         if (total == 0) return make_uint2(cur, 0u);                   // uniform over the column
     }
     evals = evaluate_queue_share(rec, sh, tid, total);
