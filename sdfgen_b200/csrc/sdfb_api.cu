@@ -61,6 +61,7 @@ Tuning tuning_from_env()
     if (getenv("SDFB_RELAX_HEAVY_LIMIT")) t.relax_heavy_limit = (long long)strtoull(getenv("SDFB_RELAX_HEAVY_LIMIT"), nullptr, 10);
     t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);
     t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
+    t.lookahead = env_int("SDFB_LOOKAHEAD", 1);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
     t.order_w = env_int("SDFB_ORDER_W", -1);
     t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
@@ -264,6 +265,7 @@ struct sdfb_plan {
     void *relax = nullptr;           // scratch of the relaxation schedule (lazily allocated, zeroed once)
     int last_sweep = -1;             // highest sweep index run since the last band: the relaxation schedule tells the
                                      // cells it changed by this sweep's stamp, so an index must not repeat
+    int look_next = -1, look_hi = -1;   // lookahead window of the relaxation schedule: the next sweep it is valid for, and its end
     // mesh
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
@@ -562,6 +564,7 @@ int sdfb_plan_band(sdfb_plan *p, const float origin[3], float dx, int32_t exact_
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev[1], st));
     p->have_band = true; p->have_sign = false; p->timed = false; p->last_sweep = -1;
+    p->look_next = p->look_hi = -1;
     if (p->link.active) ++p->link.run;       // linked slabs run band() in lockstep: flag words are run << 32 | steps
     return SDFB_OK;
 }
@@ -625,11 +628,12 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
             CU(reset_epoch_if_needed((uint32_t)n));
             const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
                                                      &p->epoch, st, tun, p->max_ctas);
-            if (l) { g_launches += l; fused_until = first + n; }
+            if (l) { g_launches += l; fused_until = first + n; p->look_next = p->look_hi = -1; }
         }
     }
     for (int s = fused_until; s < first + count; ++s) {
         if (p->flags & SDFB_SWEEP_LEVELS) {
+            p->look_next = p->look_hi = -1;
             g_launches += launch_sweep_levels(p->cells, p->rec, p->g, s, p->changed, st);
         } else if (s >= relax_from && s + 1 < 31 && s > p->last_sweep && sweep_relax_supported(p->g)) {
             if (!p->relax) {
@@ -637,13 +641,31 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                 CU(dev_alloc(&p->relax, bytes));
                 CU(cudaMemsetAsync(p->relax, 0, bytes, st));
             }
-            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st, tun, p->max_ctas);
+            // Lookahead (sdfb_sweep_relax.cu: k_look_scan): the sweeps of the second pass and later that this call still has
+            // to run are scanned for in ONE pass over the cells; each then starts from the window's lists.  The window only
+            // holds while its sweeps follow one another through this branch.
+            bool look = false;
+            if (tun.lookahead && s >= 8 && s + 1 < 31) {
+                if (!(p->look_next == s && s < p->look_hi)) {
+                    int hi = first + count < s + 8 ? first + count : s + 8;
+                    if (hi > 30) hi = 30;
+                    p->look_next = p->look_hi = -1;
+                    if (hi - s >= 2) {
+                        const int l = launch_look_scan(p->cells, p->rec, p->g, s, hi, p->changed, p->relax, st, p->max_ctas);
+                        if (l) { g_launches += l; p->look_next = s; p->look_hi = hi; }
+                    }
+                }
+                look = p->look_next == s && s < p->look_hi;
+                if (look) ++p->look_next;
+            }
+            g_launches += launch_sweep_relax(p->cells, p->rec, p->g, s, p->changed, p->relax, st, tun, p->max_ctas, look);
             // a sweep that turns out to change a large part of the grid is handed back (cells restored, flag set):
             // this launch then runs it with the column schedule, and exits at once otherwise
             CU(reset_epoch_if_needed(1));
             g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun,
                                                sweep_relax_fallback_flag(p->relax), p->max_ctas);
         } else {
+            p->look_next = p->look_hi = -1;
             CU(reset_epoch_if_needed(1));
             g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, nullptr, p->max_ctas);
         }

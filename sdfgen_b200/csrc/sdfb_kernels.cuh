@@ -39,6 +39,7 @@ struct Tuning {
     long long relax_heavy_limit = -1;   // SDFB_RELAX_HEAVY_LIMIT: work-list entries before a sweep is handed back to the columns
     int relax_scan_from = 13;     // SDFB_RELAX_SCAN_FROM: first sweep whose round 0 uses the lean scan kernel
     int relax_debug = 0;          // SDFB_RELAX_DEBUG: per-sweep round statistics on stderr
+    int lookahead = 1;            // SDFB_LOOKAHEAD: 0 = every relaxation sweep scans the grid for itself (no lookahead window)
     int order_w = -1;             // SDFB_ORDER_W: ticket order of fused launches by the key w*J + K (1 = anti-diagonals, >= NK = row by row)
     int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
     int link_debug = 0;           // SDFB_LINK_DEBUG: TIMING EXPERIMENTS ONLY, results are wrong -- 1: boundary cells are stored into a
@@ -105,8 +106,14 @@ int launch_relayout_i32(const int32_t *src, const Grid &g, int32_t *dst_kfastest
 bool sweep_relax_supported(const Grid &g);
 size_t sweep_relax_scratch_bytes(const Grid &g);
 const unsigned int *sweep_relax_fallback_flag(const void *scratch);
+// look: the sweep belongs to a lookahead window opened by launch_look_scan (its round 0 starts from the window's lists)
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas = 0);
+                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas = 0,
+                       bool look = false);
+// one pass over the cells that finds, for each of the sweeps s_lo .. s_hi-1 (<= 8), the voxels a candidate can still
+// improve; returns the number of launches (0: not applicable to this grid)
+int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, int s_lo, int s_hi,
+                     unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas = 0);
 
 size_t sweep_columns_progress_words(const Grid &g);
 

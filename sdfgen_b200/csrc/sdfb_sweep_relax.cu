@@ -38,6 +38,26 @@ namespace {
 constexpr int RX_WARPS = 8;                  // warps per CTA; in round 0 warp w handles row j0 + w
 constexpr int RX_THREADS = RX_WARPS * 32;
 
+// ---- lookahead over the sweeps of a pass (second pass and later) ------------------------------------------------------
+// In those sweeps 0.005 .. 0.02 % of the voxels change, yet every sweep's round 0 streams over all cells and evaluates
+// whatever the stamp memo cannot exclude (0.6 .. 0.001 evaluations per voxel) only to find that nearly all of them lose.
+// k_look_scan does that work for up to eight consecutive sweeps in ONE pass over the cells as they are before the first
+// of them: for every voxel and every sweep s of the window it evaluates the candidates sweep s would see IF nothing
+// around the voxel changed in between, and records the voxel in w_list[s % 8] when one of them beats the voxel's
+// distance.  Sweep s then starts from  W_s  u  D_s,  D_s = the cells changed by the window's earlier sweeps (c_list) and
+// their seven downstream neighbours in sweep s's direction: a voxel outside both has exactly the candidates the scan
+// evaluated (same neighbour words, same thresholds -- the memo tables of the window's own sweeps already exclude what
+// an earlier sweep of the window looked at) against the same distance, and they all lost; everything else is the
+// unchanged relaxation (rounds, re-evaluation of downstream neighbours, reverts).  Marking too much is harmless.
+// Any event that makes the lists incomplete (a list overflows, a sweep is handed back to the column schedule) raises
+// dense_off, after which the remaining sweeps of the window do their own dense round 0 as before.
+struct LookState {
+    unsigned int dense_off;                  // lookahead data unusable for the rest of the window
+    unsigned int c_count;                    // entries in c_list (may run past cap_c: then dense_off is set)
+    unsigned int w_count[8];                 // entries in w_list[q]
+    unsigned int pad[6];
+};
+
 struct RelaxParams {
     Grid g;
     SweepDir sd;
@@ -55,6 +75,13 @@ struct RelaxParams {
     unsigned long long *debug;               // SDFB_RELAX_DEBUG: {ns round 0, ns total, round-1 list length, rounds}
     unsigned long long *changed;             // [0] cells whose triangle changed (net), [1] distance evaluations
     uint8_t last[8][8];
+    // lookahead window (k_look_scan below): when set and not switched off on the device, round 0 starts from the bitmap
+    // k_look_mark filled, and every cell this sweep changes is appended to c_list
+    LookState *look;
+    uint32_t *c_list;                        // cells changed by the sweeps of the window so far (duplicates allowed)
+    uint32_t cap_c;
+    uint32_t *w_list;                        // [8][cap_w]: per direction, voxels with a winning candidate in the state before the window
+    uint32_t cap_w;
 };
 
 // Per-warp batch: voxels are filtered as they come (one per lane and call), their candidate triangles are
@@ -215,7 +242,14 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
         }
         const uint64_t new64 = (best != TRI_NONE) ? pack_cell(phi, (P.stamp << 27) | best) : base;
         if (new64 != cur64) {
-            if (!was_changed) P.oldbuf[c] = cur64;                    // == base: the value at the start of the sweep
+            if (!was_changed) {
+                P.oldbuf[c] = cur64;                                  // == base: the value at the start of the sweep
+                if (P.look) {                                         // lookahead window: later sweeps start from what changed
+                    const unsigned idx = atomicAdd(&P.look->c_count, 1u);
+                    if (idx < P.cap_c) P.c_list[idx] = (uint32_t)c;
+                    else P.look->dense_off = 1u;
+                }
+            }
             P.cells[c] = new64;
             net_changed += (best != TRI_NONE ? 1 : 0) - (was_changed ? 1 : 0);
             // schedule the (up to seven) downstream neighbours that this launch updates
@@ -311,6 +345,326 @@ __global__ void __launch_bounds__(SCAN_ROWS * 32) k_relax_scan(RelaxParams P)
     if (any_work && lane == 0) *reinterpret_cast<volatile unsigned int *>(&P.count[0]) = 1u;          // "round 0 has work"
 }
 
+// ---- lookahead: one pass over the cells for up to eight consecutive sweeps (see LookState above) ---------------------
+constexpr int LK_WARPS = 8;
+constexpr int LK_THREADS = LK_WARPS * 32;
+constexpr int LK_QCAP = 512;                 // candidate queue entries per warp
+constexpr int LK_PCAP = 128;                 // pending voxels per warp
+struct LookParams {
+    Grid g;
+    const uint64_t *cells;
+    const TriRec *rec;
+    int sweep_of[8];                         // direction q = s % 8 -> sweep index s of the window, -1 if the window has none
+    uint32_t thr[8][8][8];                   // [q][class][m]: neighbour word >= thr <=> fresh for that sweep (0xffffffff: never)
+    uint32_t tmin;                           // lowest threshold of the window: the cheap "nothing is fresh" test
+    uint32_t othr[26];                       // class-0 threshold of each neighbour offset in the order of kLookOrder (standard windows)
+    int standard;                            // the window starts at a multiple of 8: kLookOrder is its order of first examination
+    LookState *look;
+    uint32_t *w_list;
+    uint32_t cap_w;
+    unsigned long long *changed;             // [1] += distance evaluations
+};
+struct LookPend { uint32_t c; float px, py, pz, phi; };
+struct LookShared {
+    uint32_t q_ent[LK_WARPS][LK_QCAP];       // triangle | q << 27
+    uint16_t q_own[LK_WARPS][LK_QCAP];       // index into pend
+    LookPend pend[LK_WARPS][LK_PCAP];
+};
+
+// directions as compile-time functions of q (SweepDir::of(q), cpu_lib/makelevelset3.cpp:245-248)
+__host__ __device__ constexpr int look_di(int q) { return (q & 1) ? -1 : 1; }
+__host__ __device__ constexpr int look_dj(int q) { return ((q & 1) ? -1 : 1) * ((((q % 8) >> 1) & 2) ? -1 : 1); }
+__host__ __device__ constexpr int look_dk(int q) { return ((q & 1) ? -1 : 1) * ((((q % 8) >> 1) & 1) ? -1 : 1); }
+
+__device__ __forceinline__ void look_mark(const LookParams &P, uint32_t c, int q)
+{
+    const unsigned idx = atomicAdd(&P.look->w_count[q], 1u);
+    if (idx < P.cap_w) P.w_list[(size_t)q * P.cap_w + idx] = c;
+    else P.look->dense_off = 1u;
+}
+
+// The candidates sweep direction Q would evaluate at this voxel: bit m = neighbour m (cpu_lib/makelevelset3.cpp:143-149).
+// w[] = the {stamp|tri} words of the 3 x 3 x 3 neighbourhood, index (dk+1)*9 + (dj+1)*3 + (di+1) in ABSOLUTE offsets.
+// UNIFORM = every lane of the warp is an interior voxel: class 0 thresholds, which are immediate operands then.
+template <int Q, bool UNIFORM>
+__device__ __forceinline__ uint32_t look_live(const LookParams &P, const uint32_t (&w)[27], uint32_t own, bool valid, int cls)
+{
+    constexpr int di = look_di(Q), dj = look_dj(Q), dk = look_dk(Q);
+    uint32_t nb[7];
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const int ci = (m == 0 || m == 2 || m == 4 || m == 6) ? 1 : 0, cj = (m == 1 || m == 2 || m == 5 || m == 6) ? 1 : 0, ck = (m >= 3) ? 1 : 0;
+        nb[m] = w[(1 - dk * ck) * 9 + (1 - dj * cj) * 3 + (1 - di * ci)];
+    }
+    uint32_t live = 0;
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const uint32_t x = nb[m];
+        const uint32_t t = UNIFORM ? P.thr[Q][0][m] : P.thr[Q][cls][m];
+        const bool keep = valid && ((x & TRI_MASK) != TRI_NONE) && (((x ^ own) & TRI_MASK) != 0) && (x >= t);
+        live |= keep ? (1u << m) : 0u;
+    }
+    if (live) {                               // drop repeats of ANY earlier neighbour's triangle, as the sweeps do
+        #pragma unroll
+        for (int m = 1; m < 7; ++m) {
+            bool dup = false;
+            #pragma unroll
+            for (int u = 0; u < m; ++u) dup = dup || (((nb[u] ^ nb[m]) & TRI_MASK) == 0);
+            if (dup) live &= ~(1u << m);
+        }
+    }
+    return live;
+}
+
+// Interior voxels of a window that starts at a multiple of 8: each of the 26 neighbour offsets can be fresh only in the
+// FIRST sweep of the window that examines it (the later ones find it in their memo tables), so the filter walks the
+// offsets once, in the order of that first examination: {di, dj, dk (absolute), q = direction of that sweep, m = the
+// neighbour's number in that sweep}.  launch_look_scan checks the table against SweepDir::of.
+struct LookOfs { int oi, oj, ok, q, m; };
+__device__ constexpr LookOfs kLookOrder[26] = {
+    {-1,0,0,0,0}, {0,-1,0,0,1}, {-1,-1,0,0,2}, {0,0,-1,0,3}, {-1,0,-1,0,4}, {0,-1,-1,0,5}, {-1,-1,-1,0,6},
+    {1,0,0,1,0}, {0,1,0,1,1}, {1,1,0,1,2}, {0,0,1,1,3}, {1,0,1,1,4}, {0,1,1,1,5}, {1,1,1,1,6},
+    {-1,0,1,2,4}, {0,-1,1,2,5}, {-1,-1,1,2,6}, {1,0,-1,3,4}, {0,1,-1,3,5}, {1,1,-1,3,6},
+    {-1,1,0,4,2}, {-1,1,-1,4,6}, {1,-1,0,5,2}, {1,-1,1,5,6}, {-1,1,1,6,6}, {1,-1,-1,7,6}};
+constexpr LookOfs kLookOrderHost[26] = {
+    {-1,0,0,0,0}, {0,-1,0,0,1}, {-1,-1,0,0,2}, {0,0,-1,0,3}, {-1,0,-1,0,4}, {0,-1,-1,0,5}, {-1,-1,-1,0,6},
+    {1,0,0,1,0}, {0,1,0,1,1}, {1,1,0,1,2}, {0,0,1,1,3}, {1,0,1,1,4}, {0,1,1,1,5}, {1,1,1,1,6},
+    {-1,0,1,2,4}, {0,-1,1,2,5}, {-1,-1,1,2,6}, {1,0,-1,3,4}, {0,1,-1,3,5}, {1,1,-1,3,6},
+    {-1,1,0,4,2}, {-1,1,-1,4,6}, {1,-1,0,5,2}, {1,-1,1,5,6}, {-1,1,1,6,6}, {1,-1,-1,7,6}};
+__host__ __device__ constexpr int look_widx(int oi, int oj, int ok) { return (ok + 1) * 9 + (oj + 1) * 3 + (oi + 1); }
+// index into w[] of neighbour u of direction q
+__host__ __device__ constexpr int look_nb_idx(int q, int u)
+{
+    return look_widx(-look_di(q) * ((u == 0 || u == 2 || u == 4 || u == 6) ? 1 : 0),
+                     -look_dj(q) * ((u == 1 || u == 2 || u == 5 || u == 6) ? 1 : 0), -look_dk(q) * ((u >= 3) ? 1 : 0));
+}
+
+template <int N> struct LookStep {
+    // bit N of `live`: the neighbour at offset N is a candidate of its sweep (the sweeps' own rules: it names a triangle, not
+    // the voxel's, its cell is newer than the sweep's memo entry, and no earlier neighbour OF THAT SWEEP holds the same one)
+    static __device__ __forceinline__ void filter(const LookParams &P, const uint32_t (&w)[27], uint32_t own, uint32_t &live)
+    {
+        LookStep<N - 1>::filter(P, w, own, live);
+        constexpr LookOfs o = kLookOrder[N];
+        const uint32_t x = w[look_widx(o.oi, o.oj, o.ok)];
+        bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ own) & TRI_MASK) != 0) && (x >= P.othr[N]);
+        #pragma unroll
+        for (int u = 0; u < o.m; ++u) keep = keep && (((w[look_nb_idx(o.q, u)] ^ x) & TRI_MASK) != 0);
+        live |= keep ? (1u << N) : 0u;
+    }
+    static __device__ __forceinline__ void enqueue(const uint32_t (&w)[27], uint32_t live, uint32_t *q_ent, uint16_t *q_own, int &wq, int pidx)
+    {
+        LookStep<N - 1>::enqueue(w, live, q_ent, q_own, wq, pidx);
+        constexpr LookOfs o = kLookOrder[N];
+        if ((live >> N) & 1u) {
+            q_ent[wq] = (w[look_widx(o.oi, o.oj, o.ok)] & TRI_MASK) | ((uint32_t)o.q << 27);
+            q_own[wq] = (uint16_t)pidx;
+            ++wq;
+        }
+    }
+    static __device__ __forceinline__ void mark_all(const LookParams &P, uint32_t live, uint32_t c)
+    {
+        LookStep<N - 1>::mark_all(P, live, c);
+        constexpr LookOfs o = kLookOrder[N];
+        if ((live >> N) & 1u) look_mark(P, c, o.q);
+    }
+};
+template <> struct LookStep<-1> {
+    static __device__ __forceinline__ void filter(const LookParams &, const uint32_t (&)[27], uint32_t, uint32_t &) {}
+    static __device__ __forceinline__ void enqueue(const uint32_t (&)[27], uint32_t, uint32_t *, uint16_t *, int &, int) {}
+    static __device__ __forceinline__ void mark_all(const LookParams &, uint32_t, uint32_t) {}
+};
+
+template <int Q>
+__device__ __forceinline__ void look_enqueue(const uint32_t (&w)[27], uint32_t live, uint32_t *q_ent, uint16_t *q_own, int &wq, int pidx)
+{
+    constexpr int di = look_di(Q), dj = look_dj(Q), dk = look_dk(Q);
+    if (!live) return;
+    #pragma unroll
+    for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
+        const int ci = (m == 0 || m == 2 || m == 4 || m == 6) ? 1 : 0, cj = (m == 1 || m == 2 || m == 5 || m == 6) ? 1 : 0, ck = (m >= 3) ? 1 : 0;
+        q_ent[wq] = (w[(1 - dk * ck) * 9 + (1 - dj * cj) * 3 + (1 - di * ci)] & TRI_MASK) | ((uint32_t)Q << 27);
+        q_own[wq] = (uint16_t)pidx;
+        ++wq;
+    }
+}
+
+// Evaluate the warp's queue: an entry that beats its voxel's distance puts the voxel on the list of the entry's sweep.
+__device__ __forceinline__ void look_flush(const LookParams &P, LookShared &sh, int warp, int lane, int &nq, int &np, unsigned &evals)
+{
+    __syncwarp();
+    for (int e = lane; e < nq; e += 32) {
+        const uint32_t ent = sh.q_ent[warp][e];
+        const LookPend &pe = sh.pend[warp][sh.q_own[warp][e]];
+        const TriRec *tr = &P.rec[ent & TRI_MASK];
+        const float4 p = __ldg(&tr->p), qq = __ldg(&tr->q), r = __ldg(&tr->r);
+        const float d = ptd_rec(F3{pe.px, pe.py, pe.pz}, p, qq, r);
+        ++evals;
+        if (d < pe.phi) look_mark(P, pe.c, (int)(ent >> 27));
+    }
+    __syncwarp();
+    nq = 0; np = 0;
+}
+
+__global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_constant__ LookParams P)
+{
+    __shared__ LookShared sh;
+    const Grid &g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jblocks = (g.nj + LK_WARPS - 1) / LK_WARPS;
+    const int64_t nitems = (int64_t)jblocks * g.nk;
+    const int64_t plane = g.plane();
+    unsigned evals = 0;
+    int nq = 0, np = 0;
+    // the first toucher of plane k+1 is the item of plane k: ask L2 for that row one item ahead
+    auto prefetch_row = [&](int64_t item) {
+        if (item >= nitems) return;
+        const int pk = (int)(item / jblocks) + 1, pj = (int)(item % jblocks) * LK_WARPS + warp;
+        if (pj > g.nj - 1 || pk > g.nk - 1) return;
+        const uintptr_t beg = reinterpret_cast<uintptr_t>(P.cells + g.cidx(0, pj, pk)) & ~(uintptr_t)15;
+        const uint32_t bytes = ((uint32_t)g.ni * 8u + 16u) & ~15u;
+        for (uint32_t o = (uint32_t)lane * 2048u; o < bytes; o += 32u * 2048u) {
+            const uint32_t len = min(2048u, bytes - o);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(beg + o), "r"(len) : "memory");
+        }
+    };
+    prefetch_row(blockIdx.x);
+    for (int64_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+        prefetch_row(it + gridDim.x);
+        if (__ldcg(&P.look->dense_off)) { nq = np = 0; break; }        // a list overflowed: the sweeps will scan for themselves
+        const int k = (int)(it / jblocks), j = (int)(it % jblocks) * LK_WARPS + warp;
+        if (j > g.nj - 1) continue;                                   // warp-uniform
+        const int64_t row = g.cidx(0, j, k);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(P.cells + row);      // low words: {stamp | tri}
+        const bool row_interior = j >= 1 && j <= g.nj - 2 && k >= 1 && k <= g.nk - 2;
+        const float py = lattice(j, g.dx, g.oy), pz = lattice(k, g.dx, g.oz);
+        // interior voxels of the row (1 <= i <= ni-2) in chunks of 32, then one chunk with the two face voxels i = 0 and
+        // i = ni-1: whole warps of interior voxels of an interior row take the table-driven path
+        const int nint = (g.ni - 2 + 31) / 32;
+        for (int ch = 0; ch <= nint; ++ch) {
+            const bool edge = ch == nint;
+            const int i = edge ? (lane == 0 ? 0 : g.ni - 1) : 1 + ch * 32 + lane;
+            const bool inb = edge ? lane < 2 : i <= g.ni - 2;
+            const bool fast = P.standard && row_interior && !edge;                // warp-uniform
+            uint32_t w[27];
+            #pragma unroll
+            for (int ok = -1; ok <= 1; ++ok) {
+                #pragma unroll
+                for (int oj = -1; oj <= 1; ++oj) {
+                    const bool rok = (unsigned)(j + oj) < (unsigned)g.nj && (unsigned)(k + ok) < (unsigned)g.nk;   // warp-uniform
+                    const uint32_t *rp = base + 2 * ((int64_t)oj * g.ni + (int64_t)ok * plane);
+                    #pragma unroll
+                    for (int oi = -1; oi <= 1; ++oi) {
+                        const int ii = i + oi;
+                        w[(ok + 1) * 9 + (oj + 1) * 3 + (oi + 1)] = (rok && inb && (unsigned)ii < (unsigned)g.ni) ? __ldg(rp + 2 * ii) : TRI_NONE;
+                    }
+                }
+            }
+            const uint32_t own = w[13];
+            uint32_t mx = 0;
+            #pragma unroll
+            for (int t = 0; t < 27; ++t) if (t != 13) mx = max(mx, w[t]);
+            uint32_t live26 = 0, live[8];
+            #pragma unroll
+            for (int q = 0; q < 8; ++q) live[q] = 0;
+            int ncand = 0;
+            if (__any_sync(0xffffffffu, inb && mx >= P.tmin)) {
+                if (fast) {
+                    LookStep<25>::filter(P, w, own, live26);
+                    ncand = __popc(live26);
+                } else {
+                    // a voxel on the face a sweep starts from is not updated by it; one on the opposite face has its own memo class
+                    const bool i_lo = i == 0, i_hi = i == g.ni - 1, j_lo = j == 0, j_hi = j == g.nj - 1, k_lo = k == 0, k_hi = k == g.nk - 1;
+#define SDFB_LOOK_Q(Q) if (P.sweep_of[Q] >= 0) { \
+                        const bool st = (look_di(Q) > 0 ? i_lo : i_hi) || (look_dj(Q) > 0 ? j_lo : j_hi) || (look_dk(Q) > 0 ? k_lo : k_hi); \
+                        const int cls = ((look_di(Q) > 0 ? i_hi : i_lo) ? 1 : 0) | ((look_dj(Q) > 0 ? j_hi : j_lo) ? 2 : 0) | ((look_dk(Q) > 0 ? k_hi : k_lo) ? 4 : 0); \
+                        live[Q] = look_live<Q, false>(P, w, own, inb && !st, cls); }
+                    SDFB_LOOK_Q(0) SDFB_LOOK_Q(1) SDFB_LOOK_Q(2) SDFB_LOOK_Q(3) SDFB_LOOK_Q(4) SDFB_LOOK_Q(5) SDFB_LOOK_Q(6) SDFB_LOOK_Q(7)
+#undef SDFB_LOOK_Q
+                    #pragma unroll
+                    for (int q = 0; q < 8; ++q) ncand += __popc(live[q]);
+                }
+            }
+            const uint32_t bp = __ballot_sync(0xffffffffu, ncand > 0);
+            if (!bp) continue;
+            int incl = ncand;                                         // inclusive warp scan of the candidate counts
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int64_t c = row + i;
+            if (total > LK_QCAP) {
+                // more candidates in one chunk than the queue holds (a voxel can have 7 per sweep): put the voxels on the
+                // lists unevaluated -- the sweeps look at them anyway
+                if (ncand > 0) {
+                    if (fast) LookStep<25>::mark_all(P, live26, (uint32_t)c);
+                    else {
+                        #pragma unroll
+                        for (int q = 0; q < 8; ++q) if (live[q]) look_mark(P, (uint32_t)c, q);
+                    }
+                }
+                continue;
+            }
+            if (nq + total > LK_QCAP || np + 32 > LK_PCAP) look_flush(P, sh, warp, lane, nq, np, evals);
+            const int pidx = np + __popc(bp & ((1u << lane) - 1u));
+            if (ncand > 0) {
+                LookPend &pe = sh.pend[warp][pidx];
+                pe.c = (uint32_t)c;
+                pe.px = lattice(i, g.dx, g.ox); pe.py = py; pe.pz = pz;
+                pe.phi = __uint_as_float(__ldg(base + 2 * i + 1));    // high word: the voxel's distance
+                int wq = nq + incl - ncand;
+                if (fast) LookStep<25>::enqueue(w, live26, sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                else {
+                    look_enqueue<0>(w, live[0], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<1>(w, live[1], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<2>(w, live[2], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<3>(w, live[3], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<4>(w, live[4], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<5>(w, live[5], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<6>(w, live[6], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                    look_enqueue<7>(w, live[7], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                }
+            }
+            nq += total;
+            np += __popc(bp);
+        }
+    }
+    look_flush(P, sh, warp, lane, nq, np, evals);
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_down_sync(0xffffffffu, evals, o);
+    if (lane == 0 && evals) atomicAdd(P.changed + 1, (unsigned long long)evals);
+}
+
+// Round-0 work of sweep P.stamp - 1 from the lookahead lists: W of the sweep's direction, and every cell changed since the
+// scan together with its seven downstream neighbours (those the sweep updates).
+__global__ void __launch_bounds__(256) k_look_mark(RelaxParams P)
+{
+    if (__ldcg(&P.look->dense_off)) return;
+    const Grid &g = P.g;
+    const int q = (int)((P.stamp - 1u) & 7u);
+    const unsigned nW = min(__ldcg(&P.look->w_count[q]), P.cap_w), nC = min(__ldcg(&P.look->c_count), P.cap_c);
+    const uint64_t total = (uint64_t)nW + 8ull * nC;
+    const uint32_t plane32 = (uint32_t)g.plane();
+    bool any = false;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t d;
+        if (t < nW) {
+            d = (int64_t)__ldcg(&P.w_list[(size_t)q * P.cap_w + t]);
+        } else {
+            const uint64_t e = (t - nW) >> 3;
+            const int m = (int)((t - nW) & 7u);
+            const uint32_t c = __ldcg(&P.c_list[e]);
+            const uint32_t p = c / plane32, rem = c - p * plane32;
+            const int j = (int)(rem / (uint32_t)g.ni), i = (int)(rem - (uint32_t)j * (uint32_t)g.ni), k = (int)p - 1 + g.k_lo;
+            const int ri = (P.sd.di > 0 ? i : g.ni - 1 - i) + (m & 1), rj = (P.sd.dj > 0 ? j : g.nj - 1 - j) + ((m >> 1) & 1),
+                      rk = P.sd.rel_k(k, g) + ((m >> 2) & 1);
+            if (ri < 1 || ri > g.ni - 1 || rj < 1 || rj > g.nj - 1 || rk < P.rk_first || rk > P.rk_last) continue;
+            d = g.cidx(P.sd.abs_i(ri, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g));
+        }
+        atomicOr(&P.bitmap[0][d >> 5], 1u << (d & 31));
+        any = true;
+    }
+    if (any) *reinterpret_cast<volatile unsigned int *>(&P.count[0]) = 1u;            // "round 0 has work"
+}
+
 // Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one arrival counter that only grows;
 // `target` is the value it reaches when every CTA has arrived at this barrier.  Several times cheaper than
 // cooperative_groups' grid.sync() here, and the rounds are all latency.
@@ -364,7 +718,9 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     // ---- round 0: every voxel the sweep updates.  CTA = 8 consecutive rows of one plane (warp = row, lanes
     // along the row); the words of the next 32 voxels are loaded while the current ones are filtered. -------
     unsigned int bar_target = 0;
-    if (!P.scan_mode) {
+    // round 0 from a bitmap: the lean scan kernel filled it, or k_look_mark did (lookahead window still valid)
+    const bool scan_mode = P.scan_mode || (P.look && __ldcg(&P.look->dense_off) == 0u);
+    if (!scan_mode) {
         const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
         const int jblocks = (nrows + RX_WARPS - 1) / RX_WARPS;
         const int64_t nitems = (int64_t)jblocks * nplanes;
@@ -433,7 +789,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     // that grows again is still handled correctly, just by that CTA. ------------------------------------------
     const uint32_t plane32 = (uint32_t)g.plane();
     const int64_t nwords = (g.cell_count() + 31) >> 5;
-    int r = P.scan_mode ? 0 : 1;             // with the scan kernel, round 0 runs here from the bitmap it filled
+    int r = scan_mode ? 0 : 1;               // with a scan kernel, round 0 runs here from the bitmap it filled
     bool solo = false;
     unsigned long long work = 0;             // list entries so far (the same number in every CTA)
     for (;; ++r) {
@@ -456,7 +812,10 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
                 if (lo_stamp(cell_lo(x)) == P.stamp) P.cells[c] = ld_cg64(P.oldbuf + c);
             }
             for (int64_t wi = gt; wi < nwords; wi += nt) { P.bitmap[0][wi] = 0; P.bitmap[1][wi] = 0; }
-            if (blockIdx.x == 0 && tid == 0) P.count[5] = 1u;
+            if (blockIdx.x == 0 && tid == 0) {
+                P.count[5] = 1u;
+                if (P.look) P.look->dense_off = 1u;                   // the column schedule will not record what it changes
+            }
             net_changed = 0;
             break;
         }
@@ -545,25 +904,45 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
 
 }  // namespace
 
-// scratch the schedule needs for a slab: oldbuf (8 B per cell), two lists, two bitmaps, three counters
+// scratch the schedule needs for a slab: three counters, oldbuf (8 B per cell), two lists, two bitmaps, and the lookahead
+// window's state and lists
 bool sweep_relax_supported(const Grid &g) { return g.cell_count() < ((int64_t)1 << 32); }
 uint32_t sweep_relax_list_cap(const Grid &g)
 {
     const int64_t cap = g.cell_count() < ((int64_t)16 << 20) ? g.cell_count() : ((int64_t)16 << 20);
     return (uint32_t)cap;
 }
-size_t sweep_relax_scratch_bytes(const Grid &g)
+namespace {
+struct RelaxLayout { size_t count, oldbuf, list0, list1, bitmap0, bitmap1, look, c_list, w_list, total; uint32_t list_cap, cap_c, cap_w; };
+RelaxLayout relax_layout(const Grid &g)
 {
+    RelaxLayout L{};
     const size_t cells = (size_t)g.cell_count(), words = (cells + 31) / 32 + 1;
-    return cells * 8 + 2 * (size_t)sweep_relax_list_cap(g) * 4 + 2 * words * 4 + 64;
+    L.list_cap = sweep_relax_list_cap(g);
+    L.cap_c = (uint32_t)(cells < ((size_t)1 << 20) ? cells : ((size_t)1 << 20));
+    L.cap_w = (uint32_t)(cells < ((size_t)1 << 18) ? cells : ((size_t)1 << 18));
+    size_t o = 0;
+    L.count = o; o += 64;
+    L.oldbuf = o; o += cells * 8;
+    L.list0 = o; o += (size_t)L.list_cap * 4;
+    L.list1 = o; o += (size_t)L.list_cap * 4;
+    L.bitmap0 = o; o += words * 4;
+    L.bitmap1 = o; o += words * 4;
+    L.look = o; o += sizeof(LookState);
+    L.c_list = o; o += (size_t)L.cap_c * 4;
+    L.w_list = o; o += (size_t)L.cap_w * 4 * 8;
+    L.total = o;
+    return L;
 }
+}  // namespace
+size_t sweep_relax_scratch_bytes(const Grid &g) { return relax_layout(g).total; }
 
 // word that is non-zero after a launch that gave its sweep back (launch_sweep_columns' run_if)
 const unsigned int *sweep_relax_fallback_flag(const void *scratch) { return static_cast<const unsigned int *>(scratch) + 5; }
 
 // `scratch` must be zero-initialised once after allocation (bitmaps and counters return to zero after every sweep).
 int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
-                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas)
+                       unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas, bool look)
 {
     RelaxParams P{};
     P.g = g;
@@ -576,14 +955,20 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
     P.cells = cells; P.rec = rec; P.changed = changed;
     P.list_cap = sweep_relax_list_cap(g);
     if (tun.relax_list_cap > 0) P.list_cap = min(P.list_cap, (uint32_t)tun.relax_list_cap);   // tests: force the bitmap fallback
-    const size_t ncells = (size_t)g.cell_count(), words = (ncells + 31) / 32 + 1;
+    const size_t ncells = (size_t)g.cell_count();
+    const RelaxLayout L = relax_layout(g);
     char *s = static_cast<char *>(scratch);
-    P.count = reinterpret_cast<unsigned int *>(s); s += 64;
-    P.oldbuf = reinterpret_cast<uint64_t *>(s); s += ncells * 8;
-    P.list[0] = reinterpret_cast<uint32_t *>(s); s += (size_t)P.list_cap * 4;
-    P.list[1] = reinterpret_cast<uint32_t *>(s); s += (size_t)P.list_cap * 4;
-    P.bitmap[0] = reinterpret_cast<uint32_t *>(s); s += words * 4;
-    P.bitmap[1] = reinterpret_cast<uint32_t *>(s);
+    P.count = reinterpret_cast<unsigned int *>(s + L.count);
+    P.oldbuf = reinterpret_cast<uint64_t *>(s + L.oldbuf);
+    P.list[0] = reinterpret_cast<uint32_t *>(s + L.list0);
+    P.list[1] = reinterpret_cast<uint32_t *>(s + L.list1);
+    P.bitmap[0] = reinterpret_cast<uint32_t *>(s + L.bitmap0);
+    P.bitmap[1] = reinterpret_cast<uint32_t *>(s + L.bitmap1);
+    if (look) {
+        P.look = reinterpret_cast<LookState *>(s + L.look);
+        P.c_list = reinterpret_cast<uint32_t *>(s + L.c_list); P.cap_c = L.cap_c;
+        P.w_list = reinterpret_cast<uint32_t *>(s + L.w_list); P.cap_w = L.cap_w;
+    }
     // light sweeps put well under 1 % of the cells on their work lists (C2: 0.004-0.1 % on the first, less after),
     // heavy ones most of them, round after round
     P.heavy_limit = (uint32_t)(ncells / 64);
@@ -608,8 +993,13 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         P.debug = dbg;
     }
     // sweeps late in the second pass have almost no candidates: stream over the cells with the lean scan kernel
-    P.scan_mode = sweep_index >= tun.relax_scan_from ? 1 : 0;
+    P.scan_mode = (!look && sweep_index >= tun.relax_scan_from) ? 1 : 0;
     int launches = 1;
+    if (look) {
+        // round 0 from the lookahead lists (the kernel does its own dense pass if the window was switched off on the device)
+        k_look_mark<<<sms * 2, 256, 0, st>>>(P);
+        ++launches;
+    }
     if (P.scan_mode) {
         const dim3 sgrid((g.nj - 1 + SCAN_ROWS - 1) / SCAN_ROWS, rk_hi - rk_lo + 1);
         k_relax_scan<<<sgrid, SCAN_ROWS * 32, 0, st>>>(P);
@@ -632,6 +1022,73 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
                 h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], grid, RX_THREADS);
     }
     return launches;
+}
+
+
+// Lookahead over sweeps s_lo .. s_hi-1 (at most eight, so that every direction occurs once): zeroes the window's state and
+// runs k_look_scan on the cells as they are now.  The sweeps of the window must follow in order, each through
+// launch_sweep_relax(..., look = true); anything else invalidates the window (the caller then passes look = false).
+int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, int s_lo, int s_hi,
+                     unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas)
+{
+    if (s_hi - s_lo < 1 || s_hi - s_lo > 8 || g.ni < 2 || g.nj < 2 || g.nk < 2 || g.k_lo != 0 || g.k_hi != g.nk) return 0;
+    const RelaxLayout L = relax_layout(g);
+    char *sc = static_cast<char *>(scratch);
+    LookParams P{};
+    P.g = g; P.cells = cells; P.rec = rec; P.changed = changed;
+    P.look = reinterpret_cast<LookState *>(sc + L.look);
+    P.w_list = reinterpret_cast<uint32_t *>(sc + L.w_list); P.cap_w = L.cap_w;
+    P.tmin = 0xffffffffu;
+    for (int q = 0; q < 8; ++q) {
+        P.sweep_of[q] = -1;
+        for (int c = 0; c < 8; ++c) for (int m = 0; m < 8; ++m) P.thr[q][c][m] = 0xffffffffu;
+    }
+    for (int s = s_lo; s < s_hi; ++s) {
+        const int q = s & 7;
+        const SweepDir sd = SweepDir::of(s);
+        uint8_t last[8][8];
+        memo_last_table(s, sd, last);
+        P.sweep_of[q] = s;
+        for (int c = 0; c < 8; ++c) for (int m = 0; m < 7; ++m) {
+            const uint32_t l = last[c][m];
+            P.thr[q][c][m] = l ? (l + 1u) << 27 : 0u;
+            if (P.thr[q][c][m] < P.tmin) P.tmin = P.thr[q][c][m];
+        }
+    }
+    // interior voxels of a window that starts at a multiple of 8 walk the 26 offsets once (kLookOrder); the table must be
+    // the order in which SweepDir::of's directions first examine each offset
+    P.standard = (s_lo & 7) == 0 ? 1 : 0;
+    {
+        bool seen[27] = {false};
+        int n = 0;
+        for (int q = 0; q < 8 && P.standard; ++q) {
+            const SweepDir sd = SweepDir::of(q);
+            for (int m = 0; m < 7; ++m) {
+                const int oi = -sd.di * ((m == 0 || m == 2 || m == 4 || m == 6) ? 1 : 0), oj = -sd.dj * ((m == 1 || m == 2 || m == 5 || m == 6) ? 1 : 0),
+                          ok = -sd.dk * (m >= 3 ? 1 : 0);
+                if (seen[look_widx(oi, oj, ok)]) continue;
+                seen[look_widx(oi, oj, ok)] = true;
+                if (n >= 26) { P.standard = 0; break; }
+                const LookOfs &o = kLookOrderHost[n];
+                if (o.oi != oi || o.oj != oj || o.ok != ok || o.q != q || o.m != m) { P.standard = 0; break; }
+                P.othr[n] = P.sweep_of[q] >= 0 ? P.thr[q][0][m] : 0xffffffffu;
+                ++n;
+            }
+        }
+        if (n != 26) P.standard = 0;
+    }
+    cudaMemsetAsync(P.look, 0, sizeof(LookState), st);
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_look_scan, LK_THREADS, 0);
+    if (occ < 1) occ = 1;
+    int grid = sms * occ;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    const int64_t nitems = (int64_t)((g.nj + LK_WARPS - 1) / LK_WARPS) * g.nk;
+    if ((int64_t)grid > nitems) grid = (int)nitems;
+    k_look_scan<<<grid, LK_THREADS, 0, st>>>(P);
+    return 1;
 }
 
 }  // namespace sdfb
