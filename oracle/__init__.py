@@ -87,8 +87,61 @@ class _Port:
             L.sdfo_emu_sweep_relax.restype = C.c_long
             L.sdfo_emu_sweep_relax.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
                                                C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_long), C.POINTER(C.c_long)]
+            _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+            L.sdfo_emu_sweep_relax_from.restype = C.c_long
+            L.sdfo_emu_sweep_relax_from.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, C.c_int, C.c_uint64, _u8p, _u8p,
+                                                    C.POINTER(C.c_long), C.POINTER(C.c_long)]
+            L.sdfo_emu_look_scan.restype = C.c_long
+            L.sdfo_emu_look_scan.argtypes = [_u32p, _f32p, _f32p, _u32p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, _u8p]
+            L.sdfo_emu_look_mark.restype = C.c_long
+            L.sdfo_emu_look_mark.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
             self._lib = L
         return self._lib
+
+    def emu_sweep_lookahead(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16,
+                            look_from=8, window=8, dedupe=1, seed=1):
+        """CPU emulation of the production mix WITH the lookahead window of sdfb_sweep_relax.cu: column emulation below
+        `look_from`; from there on windows of `window` sweeps -- one scan of the cells as they are before the window
+        (sdfo_emu_look_scan), then every sweep's relaxation starts from its marks plus the cells the window's earlier
+        sweeps changed and their downstream neighbours (sdfo_emu_look_mark) instead of from every voxel.
+        Returns (phi_swept, tri_final, evals_per_sweep, scan_evals, round0_cells_per_sweep)."""
+        v, t, o = _prep(vertices, triangles, origin)
+        plane = ni * nj
+        ncell = plane * (nk + 2)
+        init = np.float32(np.float32(ni + nj + nk) * np.float32(dx))
+        cphi = np.full(ncell, init, np.float32)
+        clo = np.full(ncell, 0xFFFFFFFF, np.uint32)
+        cphi[plane:plane * (nk + 1)] = phi_band
+        tb = np.asarray(tri_band)
+        clo[plane:plane * (nk + 1)] = np.where(tb < 0, np.uint32(0xFFFFFFFF), tb.astype(np.uint32))
+        evals, scan_evals, r0 = [], [], []
+        L = self.lib()
+        marks = log = None
+        w_lo = w_hi = -1
+        for s in range(nsweeps):
+            ch, rd = C.c_long(), C.c_long()
+            if s < look_from:
+                e = L.sdfo_emu_sweep_columns(t, v, cphi, clo, o, dx, ni, nj, nk, 0, nk, s, C.byref(ch))
+                r0.append(-1)
+            else:
+                if not (w_lo <= s < w_hi):
+                    w_lo, w_hi = s, min(s + window, nsweeps)
+                    marks = np.zeros((w_hi - w_lo) * ncell, np.uint8)
+                    log = np.zeros(ncell, np.uint8)
+                    se = L.sdfo_emu_look_scan(t, v, cphi, clo, o, dx, ni, nj, nk, w_lo, w_hi, dedupe, marks)
+                    assert se >= 0
+                    scan_evals.append(int(se))
+                round0 = np.zeros(ncell, np.uint8)
+                n0 = L.sdfo_emu_look_mark(marks[(s - w_lo) * ncell:(s - w_lo + 1) * ncell], log, ni, nj, nk, s, round0)
+                r0.append(int(n0))
+                e = L.sdfo_emu_sweep_relax_from(t, v, cphi, clo, o, dx, ni, nj, nk, 0, nk, s, seed + s, round0, log,
+                                                C.byref(ch), C.byref(rd))
+            evals.append(int(e))
+        lo = clo[plane:plane * (nk + 1)]
+        tri = np.where((lo & 0x07FFFFFF) == 0x07FFFFFF, -1, (lo & 0x07FFFFFF).astype(np.int64)).astype(np.int32)
+        return cphi[plane:plane * (nk + 1)].copy(), tri, evals, scan_evals, r0
 
     def emu_sweep_columns(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16,
                           k_lo=0, k_hi=None):

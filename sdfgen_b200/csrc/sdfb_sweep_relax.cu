@@ -96,6 +96,9 @@ struct RelaxParams {
 #ifndef SDFB_RELAX_SOLOCAP
 #define SDFB_RELAX_SOLOCAP 2048
 #endif
+#ifndef SDFB_RELAX_PF
+#define SDFB_RELAX_PF 1
+#endif
 constexpr int QCAP_B = SDFB_RELAX_QCAP;                  // queue entries per warp; a call adds at most 7 * 32
 constexpr int PCAP_B = SDFB_RELAX_PCAP;                   // pending voxels per warp; a call adds at most 32
 constexpr int SOLO_CAP = SDFB_RELAX_SOLOCAP;               // entries of the in-CTA work lists of the tail rounds
@@ -252,6 +255,27 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
             }
             P.cells[c] = new64;
             net_changed += (best != TRI_NONE ? 1 : 0) - (was_changed ? 1 : 0);
+            // The rounds are chains of dependent memory round trips.  The next round re-evaluates this voxel's downstream
+            // neighbours: their cells and the cells around them (the 3 x 3 rows around c) and their oldbuf entries are what it
+            // will wait for -- ask L2 for them now (SDFB_RELAX_PF=0 builds without).
+#if SDFB_RELAX_PF
+            {
+                const int64_t ncell = g.cell_count(), rj = (int64_t)g.ni, rk = g.plane();
+                #pragma unroll
+                for (int ok = -1; ok <= 1; ++ok) {
+                    #pragma unroll
+                    for (int oj = -1; oj <= 1; ++oj) {
+                        const int64_t a = c + oj * rj + ok * rk;
+                        if (a >= 0 && a < ncell) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cells + a));
+                    }
+                }
+                #pragma unroll
+                for (int m = 1; m < 4; ++m) {                         // oldbuf rows of the downstream neighbours (the row of c was just written)
+                    const int64_t a = c - ((m & 1) ? sj : 0) - ((m & 2) ? sk : 0);
+                    if (a >= 0 && a < ncell) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.oldbuf + a));
+                }
+            }
+#endif
             // schedule the (up to seven) downstream neighbours that this launch updates
             const bool pi_ok = (info >> 20) & 1u, pj_ok = (info >> 21) & 1u, pk_ok = (info >> 22) & 1u;
             uint32_t fresh = 0;                                       // bit m: neighbour m was not yet scheduled
@@ -369,6 +393,7 @@ struct LookShared {
     uint32_t q_ent[LK_WARPS][LK_QCAP];       // triangle | q << 27
     uint16_t q_own[LK_WARPS][LK_QCAP];       // index into pend
     LookPend pend[LK_WARPS][LK_PCAP];
+    uint32_t priv[LK_WARPS][26 * 32];        // table-driven path: the candidates of each lane's voxel, entry e of lane l at e*32 + l
 };
 
 // directions as compile-time functions of q (SweepDir::of(q), cpu_lib/makelevelset3.cpp:245-248)
@@ -432,47 +457,60 @@ constexpr LookOfs kLookOrderHost[26] = {
     {-1,0,1,2,4}, {0,-1,1,2,5}, {-1,-1,1,2,6}, {1,0,-1,3,4}, {0,1,-1,3,5}, {1,1,-1,3,6},
     {-1,1,0,4,2}, {-1,1,-1,4,6}, {1,-1,0,5,2}, {1,-1,1,5,6}, {-1,1,1,6,6}, {1,-1,-1,7,6}};
 __host__ __device__ constexpr int look_widx(int oi, int oj, int ok) { return (ok + 1) * 9 + (oj + 1) * 3 + (oi + 1); }
-// index into w[] of neighbour u of direction q
-__host__ __device__ constexpr int look_nb_idx(int q, int u)
+// Which earlier offsets (in window order) a candidate is compared with before it is kept: a triangle that an earlier
+// offset already names is either measured there (and if it wins, that earlier sweep changes the voxel, which puts it on
+// c_list, so every later sweep looks at the voxel anyway), or it is the voxel's own, or the memo says it lost before.
+// SDFB_LOOK_DEDUPE = 0: the sweeps' own rule (the earlier neighbours of the same sweep); d > 0: every earlier offset within
+// Manhattan distance d (neighbouring voxels share triangles; 1 = face-adjacent offsets, 48 pairs in all).
+#ifndef SDFB_LOOK_DEDUPE
+#define SDFB_LOOK_DEDUPE 1
+#endif
+__host__ __device__ constexpr int look_abs(int v) { return v < 0 ? -v : v; }
+__device__ constexpr bool look_partner(int n, int u)
 {
-    return look_widx(-look_di(q) * ((u == 0 || u == 2 || u == 4 || u == 6) ? 1 : 0),
-                     -look_dj(q) * ((u == 1 || u == 2 || u == 5 || u == 6) ? 1 : 0), -look_dk(q) * ((u >= 3) ? 1 : 0));
+    if (u >= n) return false;
+    const LookOfs a = kLookOrder[n], b = kLookOrder[u];
+#if SDFB_LOOK_DEDUPE > 0
+    return look_abs(a.oi - b.oi) + look_abs(a.oj - b.oj) + look_abs(a.ok - b.ok) <= SDFB_LOOK_DEDUPE;
+#else
+    // neighbour u' < m of sweep a.q sits at offset -d * c(u')
+    for (int up = 0; up < a.m; ++up) {
+        const int oi = -look_di(a.q) * ((up == 0 || up == 2 || up == 4 || up == 6) ? 1 : 0),
+                  oj = -look_dj(a.q) * ((up == 1 || up == 2 || up == 5 || up == 6) ? 1 : 0), ok = -look_dk(a.q) * ((up >= 3) ? 1 : 0);
+        if (b.oi == oi && b.oj == oj && b.ok == ok) return true;
+    }
+    return false;
+#endif
 }
 
-template <int N> struct LookStep {
-    // bit N of `live`: the neighbour at offset N is a candidate of its sweep (the sweeps' own rules: it names a triangle, not
-    // the voxel's, its cell is newer than the sweep's memo entry, and no earlier neighbour OF THAT SWEEP holds the same one)
-    static __device__ __forceinline__ void filter(const LookParams &P, const uint32_t (&w)[27], uint32_t own, uint32_t &live)
+template <int N, int U> struct LookDup {      // does any partner offset u <= U of offset N hold triangle x?
+    static __device__ __forceinline__ bool any(const uint32_t (&w)[27], uint32_t x)
     {
-        LookStep<N - 1>::filter(P, w, own, live);
+        bool d = LookDup<N, U - 1>::any(w, x);
+        if (look_partner(N, U)) { constexpr LookOfs b = kLookOrder[U]; d = d || (((w[look_widx(b.oi, b.oj, b.ok)] ^ x) & TRI_MASK) == 0); }
+        return d;
+    }
+};
+template <int N> struct LookDup<N, -1> { static __device__ __forceinline__ bool any(const uint32_t (&)[27], uint32_t) { return false; } };
+
+template <int N> struct LookStep {
+    // Offsets 0..N in window order: a neighbour that names another triangle than the voxel's, whose cell is newer than the
+    // memo entry of the sweep that examines it first and whose triangle no partner offset repeats goes to the lane's private
+    // list (entry = triangle | q << 27).  A neighbour without a triangle carries stamp 0 and fails every threshold of a second
+    // pass (launch_look_scan checks that they are all >= 1 << 27).
+    static __device__ __forceinline__ void filter(const LookParams &P, const uint32_t (&w)[27], uint32_t own, uint32_t *priv, int &cnt)
+    {
+        LookStep<N - 1>::filter(P, w, own, priv, cnt);
         constexpr LookOfs o = kLookOrder[N];
         const uint32_t x = w[look_widx(o.oi, o.oj, o.ok)];
-        bool keep = ((x & TRI_MASK) != TRI_NONE) && (((x ^ own) & TRI_MASK) != 0) && (x >= P.othr[N]);
-        #pragma unroll
-        for (int u = 0; u < o.m; ++u) keep = keep && (((w[look_nb_idx(o.q, u)] ^ x) & TRI_MASK) != 0);
-        live |= keep ? (1u << N) : 0u;
-    }
-    static __device__ __forceinline__ void enqueue(const uint32_t (&w)[27], uint32_t live, uint32_t *q_ent, uint16_t *q_own, int &wq, int pidx)
-    {
-        LookStep<N - 1>::enqueue(w, live, q_ent, q_own, wq, pidx);
-        constexpr LookOfs o = kLookOrder[N];
-        if ((live >> N) & 1u) {
-            q_ent[wq] = (w[look_widx(o.oi, o.oj, o.ok)] & TRI_MASK) | ((uint32_t)o.q << 27);
-            q_own[wq] = (uint16_t)pidx;
-            ++wq;
+        if ((((x ^ own) & TRI_MASK) != 0) && (x >= P.othr[N]) && !LookDup<N, N - 1>::any(w, x)) {
+            priv[cnt * 32] = (x & TRI_MASK) | ((uint32_t)o.q << 27);
+            ++cnt;
         }
-    }
-    static __device__ __forceinline__ void mark_all(const LookParams &P, uint32_t live, uint32_t c)
-    {
-        LookStep<N - 1>::mark_all(P, live, c);
-        constexpr LookOfs o = kLookOrder[N];
-        if ((live >> N) & 1u) look_mark(P, c, o.q);
     }
 };
 template <> struct LookStep<-1> {
-    static __device__ __forceinline__ void filter(const LookParams &, const uint32_t (&)[27], uint32_t, uint32_t &) {}
-    static __device__ __forceinline__ void enqueue(const uint32_t (&)[27], uint32_t, uint32_t *, uint16_t *, int &, int) {}
-    static __device__ __forceinline__ void mark_all(const LookParams &, uint32_t, uint32_t) {}
+    static __device__ __forceinline__ void filter(const LookParams &, const uint32_t (&)[27], uint32_t, uint32_t *, int &) {}
 };
 
 template <int Q>
@@ -508,12 +546,14 @@ __device__ __forceinline__ void look_flush(const LookParams &P, LookShared &sh, 
 
 __global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_constant__ LookParams P)
 {
-    __shared__ LookShared sh;
+    extern __shared__ __align__(16) unsigned char look_smem[];
+    LookShared &sh = *reinterpret_cast<LookShared *>(look_smem);
     const Grid &g = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int jblocks = (g.nj + LK_WARPS - 1) / LK_WARPS;
     const int64_t nitems = (int64_t)jblocks * g.nk;
     const int64_t plane = g.plane();
+    uint32_t *const priv = &sh.priv[warp][lane];
     unsigned evals = 0;
     int nq = 0, np = 0;
     // the first toucher of plane k+1 is the item of plane k: ask L2 for that row one item ahead
@@ -546,44 +586,53 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_consta
             const int i = edge ? (lane == 0 ? 0 : g.ni - 1) : 1 + ch * 32 + lane;
             const bool inb = edge ? lane < 2 : i <= g.ni - 2;
             const bool fast = P.standard && row_interior && !edge;                // warp-uniform
-            uint32_t w[27];
-            #pragma unroll
-            for (int ok = -1; ok <= 1; ++ok) {
+            uint32_t w[27], live[8];
+            int ncand = 0;
+            if (fast) {
+                // all 27 cells exist (lanes past the end of the row read the next row's first cells and are masked below)
                 #pragma unroll
-                for (int oj = -1; oj <= 1; ++oj) {
-                    const bool rok = (unsigned)(j + oj) < (unsigned)g.nj && (unsigned)(k + ok) < (unsigned)g.nk;   // warp-uniform
-                    const uint32_t *rp = base + 2 * ((int64_t)oj * g.ni + (int64_t)ok * plane);
+                for (int ok = -1; ok <= 1; ++ok) {
                     #pragma unroll
-                    for (int oi = -1; oi <= 1; ++oi) {
-                        const int ii = i + oi;
-                        w[(ok + 1) * 9 + (oj + 1) * 3 + (oi + 1)] = (rok && inb && (unsigned)ii < (unsigned)g.ni) ? __ldg(rp + 2 * ii) : TRI_NONE;
+                    for (int oj = -1; oj <= 1; ++oj) {
+                        const uint32_t *pp = base + 2 * ((int64_t)oj * g.ni + (int64_t)ok * plane + i);
+                        #pragma unroll
+                        for (int oi = -1; oi <= 1; ++oi) w[(ok + 1) * 9 + (oj + 1) * 3 + (oi + 1)] = __ldg(pp + 2 * oi);
                     }
                 }
-            }
-            const uint32_t own = w[13];
-            uint32_t mx = 0;
-            #pragma unroll
-            for (int t = 0; t < 27; ++t) if (t != 13) mx = max(mx, w[t]);
-            uint32_t live26 = 0, live[8];
-            #pragma unroll
-            for (int q = 0; q < 8; ++q) live[q] = 0;
-            int ncand = 0;
-            if (__any_sync(0xffffffffu, inb && mx >= P.tmin)) {
-                if (fast) {
-                    LookStep<25>::filter(P, w, own, live26);
-                    ncand = __popc(live26);
-                } else {
-                    // a voxel on the face a sweep starts from is not updated by it; one on the opposite face has its own memo class
-                    const bool i_lo = i == 0, i_hi = i == g.ni - 1, j_lo = j == 0, j_hi = j == g.nj - 1, k_lo = k == 0, k_hi = k == g.nk - 1;
-#define SDFB_LOOK_Q(Q) if (P.sweep_of[Q] >= 0) { \
-                        const bool st = (look_di(Q) > 0 ? i_lo : i_hi) || (look_dj(Q) > 0 ? j_lo : j_hi) || (look_dk(Q) > 0 ? k_lo : k_hi); \
-                        const int cls = ((look_di(Q) > 0 ? i_hi : i_lo) ? 1 : 0) | ((look_dj(Q) > 0 ? j_hi : j_lo) ? 2 : 0) | ((look_dk(Q) > 0 ? k_hi : k_lo) ? 4 : 0); \
-                        live[Q] = look_live<Q, false>(P, w, own, inb && !st, cls); }
-                    SDFB_LOOK_Q(0) SDFB_LOOK_Q(1) SDFB_LOOK_Q(2) SDFB_LOOK_Q(3) SDFB_LOOK_Q(4) SDFB_LOOK_Q(5) SDFB_LOOK_Q(6) SDFB_LOOK_Q(7)
-#undef SDFB_LOOK_Q
-                    #pragma unroll
-                    for (int q = 0; q < 8; ++q) ncand += __popc(live[q]);
+                uint32_t mx = 0;
+                #pragma unroll
+                for (int t = 0; t < 27; ++t) if (t != 13) mx = max(mx, w[t]);
+                if (__any_sync(0xffffffffu, inb && mx >= P.tmin)) {
+                    LookStep<25>::filter(P, w, w[13], priv, ncand);
+                    if (!inb) ncand = 0;
                 }
+            } else {
+                #pragma unroll
+                for (int ok = -1; ok <= 1; ++ok) {
+                    #pragma unroll
+                    for (int oj = -1; oj <= 1; ++oj) {
+                        const bool rok = (unsigned)(j + oj) < (unsigned)g.nj && (unsigned)(k + ok) < (unsigned)g.nk;   // warp-uniform
+                        const uint32_t *rp = base + 2 * ((int64_t)oj * g.ni + (int64_t)ok * plane);
+                        #pragma unroll
+                        for (int oi = -1; oi <= 1; ++oi) {
+                            const int ii = i + oi;
+                            w[(ok + 1) * 9 + (oj + 1) * 3 + (oi + 1)] = (rok && inb && (unsigned)ii < (unsigned)g.ni) ? __ldg(rp + 2 * ii) : TRI_NONE;
+                        }
+                    }
+                }
+                const uint32_t own = w[13];
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) live[q] = 0;
+                // a voxel on the face a sweep starts from is not updated by it; one on the opposite face has its own memo class
+                const bool i_lo = i == 0, i_hi = i == g.ni - 1, j_lo = j == 0, j_hi = j == g.nj - 1, k_lo = k == 0, k_hi = k == g.nk - 1;
+#define SDFB_LOOK_Q(Q) if (P.sweep_of[Q] >= 0) { \
+                    const bool st = (look_di(Q) > 0 ? i_lo : i_hi) || (look_dj(Q) > 0 ? j_lo : j_hi) || (look_dk(Q) > 0 ? k_lo : k_hi); \
+                    const int cls = ((look_di(Q) > 0 ? i_hi : i_lo) ? 1 : 0) | ((look_dj(Q) > 0 ? j_hi : j_lo) ? 2 : 0) | ((look_dk(Q) > 0 ? k_hi : k_lo) ? 4 : 0); \
+                    live[Q] = look_live<Q, false>(P, w, own, inb && !st, cls); }
+                SDFB_LOOK_Q(0) SDFB_LOOK_Q(1) SDFB_LOOK_Q(2) SDFB_LOOK_Q(3) SDFB_LOOK_Q(4) SDFB_LOOK_Q(5) SDFB_LOOK_Q(6) SDFB_LOOK_Q(7)
+#undef SDFB_LOOK_Q
+                #pragma unroll
+                for (int q = 0; q < 8; ++q) ncand += __popc(live[q]);
             }
             const uint32_t bp = __ballot_sync(0xffffffffu, ncand > 0);
             if (!bp) continue;
@@ -592,40 +641,42 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_consta
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             const int64_t c = row + i;
-            if (total > LK_QCAP) {
-                // more candidates in one chunk than the queue holds (a voxel can have 7 per sweep): put the voxels on the
-                // lists unevaluated -- the sweeps look at them anyway
-                if (ncand > 0) {
-                    if (fast) LookStep<25>::mark_all(P, live26, (uint32_t)c);
-                    else {
-                        #pragma unroll
-                        for (int q = 0; q < 8; ++q) if (live[q]) look_mark(P, (uint32_t)c, q);
+            if (nq + total > LK_QCAP || np + 32 > LK_PCAP) look_flush(P, sh, warp, lane, nq, np, evals);
+            // Enqueue the chunk, lane range by lane range if its candidates do not fit the (now empty) queue at once: a
+            // voxel has at most 56, so every range makes progress.
+            int start = 0, done = 0;                                  // first lane not yet enqueued, candidates before it
+            for (;;) {
+                const uint32_t fits = __ballot_sync(0xffffffffu, lane >= start && incl - done <= LK_QCAP - nq);
+                const int end = start + __popc(fits);                 // the lanes that fit are a prefix of [start, 32)
+                const bool mine = lane >= start && lane < end;
+                const uint32_t range = (end >= 32 ? 0xffffffffu : (1u << end) - 1u) & ~((1u << start) - 1u);
+                if (mine && ncand > 0) {
+                    const int pidx = np + __popc(bp & range & ((1u << lane) - 1u));
+                    LookPend &pe = sh.pend[warp][pidx];
+                    pe.c = (uint32_t)c;
+                    pe.px = lattice(i, g.dx, g.ox); pe.py = py; pe.pz = pz;
+                    pe.phi = __uint_as_float(__ldg(base + 2 * i + 1));    // high word: the voxel's distance
+                    int wq = nq + incl - ncand - done;
+                    if (fast) {
+                        for (int e = 0; e < ncand; ++e, ++wq) { sh.q_ent[warp][wq] = priv[e * 32]; sh.q_own[warp][wq] = (uint16_t)pidx; }
+                    } else {
+                        look_enqueue<0>(w, live[0], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<1>(w, live[1], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<2>(w, live[2], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<3>(w, live[3], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<4>(w, live[4], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<5>(w, live[5], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<6>(w, live[6], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
+                        look_enqueue<7>(w, live[7], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
                     }
                 }
-                continue;
+                const int upto = __shfl_sync(0xffffffffu, incl, end - 1);   // candidates of lanes [0, end)
+                nq += upto - done;
+                np += __popc(bp & range);
+                if (end >= 32) break;
+                look_flush(P, sh, warp, lane, nq, np, evals);
+                start = end; done = upto;
             }
-            if (nq + total > LK_QCAP || np + 32 > LK_PCAP) look_flush(P, sh, warp, lane, nq, np, evals);
-            const int pidx = np + __popc(bp & ((1u << lane) - 1u));
-            if (ncand > 0) {
-                LookPend &pe = sh.pend[warp][pidx];
-                pe.c = (uint32_t)c;
-                pe.px = lattice(i, g.dx, g.ox); pe.py = py; pe.pz = pz;
-                pe.phi = __uint_as_float(__ldg(base + 2 * i + 1));    // high word: the voxel's distance
-                int wq = nq + incl - ncand;
-                if (fast) LookStep<25>::enqueue(w, live26, sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                else {
-                    look_enqueue<0>(w, live[0], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<1>(w, live[1], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<2>(w, live[2], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<3>(w, live[3], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<4>(w, live[4], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<5>(w, live[5], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<6>(w, live[6], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    look_enqueue<7>(w, live[7], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                }
-            }
-            nq += total;
-            np += __popc(bp);
         }
     }
     look_flush(P, sh, warp, lane, nq, np, evals);
@@ -643,7 +694,6 @@ __global__ void __launch_bounds__(256) k_look_mark(RelaxParams P)
     const unsigned nW = min(__ldcg(&P.look->w_count[q]), P.cap_w), nC = min(__ldcg(&P.look->c_count), P.cap_c);
     const uint64_t total = (uint64_t)nW + 8ull * nC;
     const uint32_t plane32 = (uint32_t)g.plane();
-    bool any = false;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
         int64_t d;
         if (t < nW) {
@@ -659,20 +709,22 @@ __global__ void __launch_bounds__(256) k_look_mark(RelaxParams P)
             if (ri < 1 || ri > g.ni - 1 || rj < 1 || rj > g.nj - 1 || rk < P.rk_first || rk > P.rk_last) continue;
             d = g.cidx(P.sd.abs_i(ri, g), P.sd.abs_j(rj, g), P.sd.abs_k(rk, g));
         }
-        atomicOr(&P.bitmap[0][d >> 5], 1u << (d & 31));
-        any = true;
+        const uint32_t bit = 1u << (d & 31);
+        if (!(atomicOr(&P.bitmap[0][d >> 5], bit) & bit)) {           // not yet on the list of round 0
+            const unsigned idx = atomicAdd(&P.count[0], 1u);
+            if (idx < P.list_cap) P.list[0][idx] = (uint32_t)d;       // (beyond that the round walks the bitmap)
+        }
     }
-    if (any) *reinterpret_cast<volatile unsigned int *>(&P.count[0]) = 1u;            // "round 0 has work"
 }
 
 // Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one arrival counter that only grows;
 // `target` is the value it reaches when every CTA has arrived at this barrier.  Several times cheaper than
 // cooperative_groups' grid.sync() here, and the rounds are all latency.
-__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &target)
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &target, unsigned int nctas)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        target += gridDim.x;
+        target += nctas;
         __threadfence();
         atomicAdd(ctr, 1u);
         while (*reinterpret_cast<volatile unsigned int *>(ctr) < target) { }
@@ -685,6 +737,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &ta
 constexpr int MAX_GRID_ROUNDS = 256;         // more grid-wide rounds than this cost as much as a column sweep
 constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by one CTA (a CTA barrier per round
                                              // instead of a grid barrier)
+// In between, a TEAM of the first few CTAs carries on: a list of a few thousand entries is one batch for their warps, and a
+// barrier among 16 CTAs costs a fraction of one among all 444 (the rounds are pure latency: ~80 of them per sweep).
+#ifndef SDFB_RELAX_TEAM
+#define SDFB_RELAX_TEAM 16
+#endif
+constexpr unsigned TEAM_CTAS = SDFB_RELAX_TEAM;
+constexpr unsigned TEAM_MAX = TEAM_CTAS * RX_WARPS * 32;    // entries the team handles in one batch
 
 #ifndef SDFB_RELAX_MINB
 #define SDFB_RELAX_MINB 3
@@ -719,7 +778,8 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     // along the row); the words of the next 32 voxels are loaded while the current ones are filtered. -------
     unsigned int bar_target = 0;
     // round 0 from a bitmap: the lean scan kernel filled it, or k_look_mark did (lookahead window still valid)
-    const bool scan_mode = P.scan_mode || (P.look && __ldcg(&P.look->dense_off) == 0u);
+    const bool look_on = P.look && __ldcg(&P.look->dense_off) == 0u;
+    const bool scan_mode = P.scan_mode || look_on;
     if (!scan_mode) {
         const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
         const int jblocks = (nrows + RX_WARPS - 1) / RX_WARPS;
@@ -776,7 +836,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             }
         }
         relax_flush(P, sh, warp, lane, nq, np, 1, &P.count[1], false, net_changed, evals);
-        grid_barrier(&P.count[4], bar_target);
+        grid_barrier(&P.count[4], bar_target, gridDim.x);
         if (P.debug && blockIdx.x == 0 && tid == 0) {
             unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             P.debug[0] = t - t_start; P.debug[2] = P.count[1];
@@ -790,7 +850,8 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     const uint32_t plane32 = (uint32_t)g.plane();
     const int64_t nwords = (g.cell_count() + 31) >> 5;
     int r = scan_mode ? 0 : 1;               // with a scan kernel, round 0 runs here from the bitmap it filled
-    bool solo = false;
+    bool solo = false, team = false;
+    unsigned int team_target = 0;
     unsigned long long work = 0;             // list entries so far (the same number in every CTA)
     for (;; ++r) {
         const int par = r & 1;
@@ -798,7 +859,9 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
                           : *reinterpret_cast<volatile unsigned int *>(&P.count[r % 3]);
         if (n == 0) break;
         work += n;
-        if (!solo && r >= 1 && (work > P.heavy_limit || r > MAX_GRID_ROUNDS)) {                         // uniform over the grid
+        // (not once the team or one CTA has taken over: the CTAs that left have already reported their change counts, and a
+        // list of a few thousand entries is no longer the heavy case)
+        if (!solo && !team && r >= 1 && (work > P.heavy_limit || r > MAX_GRID_ROUNDS)) {                // uniform over the grid
             // ---- fallback: this sweep changes too much for relaxation to pay (every changed voxel re-opens its
             // downstream neighbours, and a front that crosses an empty region is re-evaluated again and again:
             // such sweeps take seconds).  Put the cells back as they were before
@@ -823,7 +886,11 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             P.debug[4 + 2 * r] = n; P.debug[5 + 2 * r] = t - t_start;
         }
-        if (!solo && r > 0 && n <= SOLO_MAX) {                        // uniform over the grid
+        if (!solo && !team && r > 0 && n <= TEAM_MAX && gridDim.x > TEAM_CTAS) {     // uniform over the grid
+            team = true;
+            if (blockIdx.x >= TEAM_CTAS) break;
+        }
+        if (!solo && r > 0 && n <= SOLO_MAX) {                        // uniform over the grid / the team
             solo = true;
             if (blockIdx.x != 0) break;
             for (unsigned t = tid; t < n; t += RX_THREADS) sh.slist[par][t] = __ldcg(&P.list[par][t]);     // import the list
@@ -834,8 +901,9 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         else if (blockIdx.x == 0 && tid == 0) P.count[(r + 2) % 3] = 0;
         unsigned int *const push_count = solo ? &sh.scount[(r + 1) % 3] : &P.count[(r + 1) % 3];
         // the bitmap is the work list when a list overflowed
-        const bool use_bitmap = r == 0 || n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
-        const int64_t w = solo ? warp : gwarp, nw = solo ? RX_WARPS : nwarps;
+        // (round 0 after the lean scan kernel walks the bitmap it filled; k_look_mark leaves a list like any other round's)
+        const bool use_bitmap = (r == 0 && !look_on) || n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
+        const int64_t w = solo ? warp : gwarp, nw = solo ? RX_WARPS : (team ? (int64_t)TEAM_CTAS * RX_WARPS : nwarps);
         const int64_t limit = use_bitmap ? nwords : (int64_t)n;
         for (int64_t pos = w * 32; pos < limit; pos += nw * 32) {
             uint32_t mine = 0, nz = 1;
@@ -885,7 +953,8 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         }
         relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
         if (solo) __syncthreads();                                    // orders the CTA's writes (global and shared) and reads
-        else grid_barrier(&P.count[4], bar_target);
+        else if (team) grid_barrier(&P.count[6], team_target, TEAM_CTAS);
+        else grid_barrier(&P.count[4], bar_target, gridDim.x);
         if (r == 0 && P.debug && blockIdx.x == 0 && tid == 0) {
             unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
             P.debug[0] = t - t_start; P.debug[2] = P.count[1];
@@ -1076,18 +1145,22 @@ int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, in
             }
         }
         if (n != 26) P.standard = 0;
+        // the table-driven filter leaves out the "names a triangle" test: a cell without one has stamp 0
+        for (int t = 0; t < 26 && P.standard; ++t) if (P.othr[t] < (1u << 27)) P.standard = 0;
     }
     cudaMemsetAsync(P.look, 0, sizeof(LookState), st);
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_look_scan, LK_THREADS, 0);
+    const size_t smem = sizeof(LookShared);
+    cudaFuncSetAttribute(k_look_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_look_scan, LK_THREADS, smem);
     if (occ < 1) occ = 1;
     int grid = sms * occ;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     const int64_t nitems = (int64_t)((g.nj + LK_WARPS - 1) / LK_WARPS) * g.nk;
     if ((int64_t)grid > nitems) grid = (int)nitems;
-    k_look_scan<<<grid, LK_THREADS, 0, st>>>(P);
+    k_look_scan<<<grid, LK_THREADS, smem, st>>>(P);
     return 1;
 }
 
