@@ -462,10 +462,13 @@ __host__ __device__ constexpr int look_widx(int oi, int oj, int ok) { return (ok
 // c_list, so every later sweep looks at the voxel anyway), or it is the voxel's own, or the memo says it lost before.
 // SDFB_LOOK_DEDUPE = 0: the sweeps' own rule (the earlier neighbours of the same sweep); d > 0: every earlier offset within
 // Manhattan distance d (neighbouring voxels share triangles; 1 = face-adjacent offsets, 48 pairs in all).
+// Measured at C2 (profiles/r2_lookahead.txt): 0 -> 1.71 evaluations per voxel in the second pass, 1 -> 1.97, 2 -> 1.68 (more compares).
 #ifndef SDFB_LOOK_DEDUPE
-#define SDFB_LOOK_DEDUPE 1
+#define SDFB_LOOK_DEDUPE 0
 #endif
+#if SDFB_LOOK_DEDUPE > 0
 __host__ __device__ constexpr int look_abs(int v) { return v < 0 ? -v : v; }
+#endif
 __device__ constexpr bool look_partner(int n, int u)
 {
     if (u >= n) return false;
