@@ -70,7 +70,8 @@ struct RelaxParams {
     const TriRec *rec;
     uint32_t *list[2];                       // cell indices to re-evaluate, by round parity
     uint32_t *bitmap[2];                     // one bit per cell: "is in the list of that parity"
-    unsigned int *count;                     // [0..2] list lengths, rotating by round % 3; [4] grid barrier arrivals
+    unsigned int *count;                     // [0..2] list lengths, rotating by round % 3; [4] grid barrier arrivals; [5] "handed back to the
+                                             // columns"; [6] team barrier arrivals; [7] "round 0 starts from the lookahead lists" (k_look_mark)
     uint32_t heavy_limit;                    // more work-list entries than this in all: give the sweep back to the column schedule
     unsigned long long *debug;               // SDFB_RELAX_DEBUG: {ns round 0, ns total, round-1 list length, rounds}
     unsigned long long *changed;             // [0] cells whose triangle changed (net), [1] distance evaluations
@@ -691,7 +692,11 @@ __global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_consta
 // scan together with its seven downstream neighbours (those the sweep updates).
 __global__ void __launch_bounds__(256) k_look_mark(RelaxParams P)
 {
-    if (__ldcg(&P.look->dense_off)) return;
+    // the decision "this sweep starts from the window's lists" is taken HERE, once, and handed to the rounds kernel in
+    // count[7]: dense_off itself may be raised while that kernel runs (c_list overflow), and its CTAs must all agree
+    const bool off = __ldcg(&P.look->dense_off) != 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.count[7] = off ? 0u : 1u;
+    if (off) return;
     const Grid &g = P.g;
     const int q = (int)((P.stamp - 1u) & 7u);
     const unsigned nW = min(__ldcg(&P.look->w_count[q]), P.cap_w), nC = min(__ldcg(&P.look->c_count), P.cap_c);
@@ -781,7 +786,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
     // along the row); the words of the next 32 voxels are loaded while the current ones are filtered. -------
     unsigned int bar_target = 0;
     // round 0 from a bitmap: the lean scan kernel filled it, or k_look_mark did (lookahead window still valid)
-    const bool look_on = P.look && __ldcg(&P.look->dense_off) == 0u;
+    const bool look_on = P.look && __ldcg(&P.count[7]) != 0u;        // set by k_look_mark, constant during this launch
     const bool scan_mode = P.scan_mode || look_on;
     if (!scan_mode) {
         const int nrows = g.nj - 1, nplanes = P.rk_last - P.rk_first + 1;
@@ -1156,9 +1161,13 @@ int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = sizeof(LookShared);
-    cudaFuncSetAttribute(k_look_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_look_scan, LK_THREADS, smem);
-    if (occ < 1) occ = 1;
+    static int occ_cached[64] = {0};          // per device, as in launch_sweep_relax
+    if (dev < 0 || dev >= 64 || !occ_cached[dev]) {
+        cudaFuncSetAttribute(k_look_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_look_scan, LK_THREADS, smem);
+        if (occ < 1) occ = 1;
+        if (dev >= 0 && dev < 64) occ_cached[dev] = occ;
+    } else occ = occ_cached[dev];
     int grid = sms * occ;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     const int64_t nitems = (int64_t)((g.nj + LK_WARPS - 1) / LK_WARPS) * g.nk;
