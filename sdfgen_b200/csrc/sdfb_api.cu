@@ -10,11 +10,15 @@
 #include <cstdarg>
 #include <atomic>
 #include <new>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
 #include <unistd.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 #include <cuda_runtime.h>
 #include "../../include/sdfb.h"
 #include "sdfb_kernels.cuh"
@@ -62,6 +66,7 @@ Tuning tuning_from_env()
     t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);
     t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
     t.lookahead = env_int("SDFB_LOOKAHEAD", 1);
+    t.look_cap = env_int("SDFB_LOOK_CAP", 0);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
     t.order_w = env_int("SDFB_ORDER_W", -1);
     t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
@@ -87,25 +92,92 @@ bool device_is_sm100(int dev)
 int host_threads()
 {
     unsigned n = std::thread::hardware_concurrency();
-    return (int)(n == 0 ? 4 : (n > 8 ? 8 : n));
+    return (int)(n == 0 ? 4 : (n > 12 ? 12 : n));
 }
+
+// A few persistent host threads for the two memory-bound jobs around a large download (touching the destination pages,
+// copying from the pinned ring into pageable memory).  Spawning and joining a set of std::threads per 32 MB chunk cost
+// 0.1-0.2 ms each time, a sixth of the chunk's copy.  The pool is created on first use and never destroyed (its threads
+// sleep on a condition variable; joining them from a static destructor of a shared library at exit is asking for trouble).
+// One job at a time: callers on several host threads (batch workers, the slabs of a multi-GPU call) take turns chunk by chunk.
+class HostPool {
+public:
+    static HostPool &get() { static HostPool *p = new HostPool(); return *p; }
+    void run(char *dst, size_t bytes, void (*fn)(char *, size_t, const char *), const char *src)
+    {
+        if (bytes == 0) return;
+        std::lock_guard<std::mutex> job(job_mtx_);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            dst_ = dst; bytes_ = bytes; fn_ = fn; src_ = src;
+            per_ = ((bytes + nt_ - 1) / nt_ + 4095) & ~(size_t)4095;
+            remaining_ = nt_;
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return remaining_ == 0; });
+    }
+private:
+    HostPool() : nt_(host_threads())
+    {
+        for (int t = 0; t < nt_; ++t) std::thread([this, t] { worker(t); }).detach();
+    }
+    void worker(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            char *dst; size_t bytes, per; void (*fn)(char *, size_t, const char *); const char *src;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                dst = dst_; bytes = bytes_; per = per_; fn = fn_; src = src_;
+            }
+            const size_t lo = (size_t)t * per;
+            if (lo < bytes) fn(dst + lo, bytes - lo < per ? bytes - lo : per, src ? src + lo : nullptr);
+            bool last;
+            { std::lock_guard<std::mutex> lk(m_); last = --remaining_ == 0; }
+            if (last) cv_done_.notify_all();
+        }
+    }
+    const int nt_;
+    std::mutex job_mtx_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    unsigned long long gen_ = 0;
+    int remaining_ = 0;
+    char *dst_ = nullptr; size_t bytes_ = 0, per_ = 0; void (*fn_)(char *, size_t, const char *) = nullptr; const char *src_ = nullptr;
+};
 
 void parallel_for_bytes(char *dst, size_t bytes, void (*fn)(char *, size_t, const char *), const char *src)
 {
-    const int nt = host_threads();
-    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; ++t) {
-        const size_t lo = (size_t)t * per;
-        if (lo >= bytes) break;
-        const size_t n = bytes - lo < per ? bytes - lo : per;
-        th.emplace_back(fn, dst + lo, n, src ? src + lo : nullptr);
-    }
-    for (auto &x : th) x.join();
+    HostPool::get().run(dst, bytes, fn, src);
 }
 
 void touch_pages(char *dst, size_t n, const char *) { for (size_t o = 0; o < n; o += 4096) reinterpret_cast<volatile char *>(dst)[o] = 0; }
-void copy_bytes(char *dst, size_t n, const char *src) { memcpy(dst, src, n); }
+// pinned ring -> the caller's pageable array.  The destination is written once and not read here: streaming stores skip the
+// read-for-ownership of every destination line (a third of the DRAM traffic of this copy, which is what bounds it).
+void copy_bytes(char *dst, size_t n, const char *src)
+{
+#if defined(__x86_64__) || defined(_M_X64)
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    if (n >= 4096 && ((reinterpret_cast<uintptr_t>(src) + head) & 15) == 0) {
+        memcpy(dst, src, head);
+        dst += head; src += head; n -= head;
+        const size_t blocks = n / 64;
+        const __m128i *s = reinterpret_cast<const __m128i *>(src);
+        __m128i *d = reinterpret_cast<__m128i *>(dst);
+        for (size_t b = 0; b < blocks; ++b, s += 4, d += 4) {
+            const __m128i x0 = _mm_load_si128(s), x1 = _mm_load_si128(s + 1), x2 = _mm_load_si128(s + 2), x3 = _mm_load_si128(s + 3);
+            _mm_stream_si128(d, x0); _mm_stream_si128(d + 1, x1); _mm_stream_si128(d + 2, x2); _mm_stream_si128(d + 3, x3);
+        }
+        _mm_sfence();
+        memcpy(dst + blocks * 64, src + blocks * 64, n - blocks * 64);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
 
 bool is_pageable(const void *p)
 {
@@ -120,16 +192,18 @@ bool is_pageable(const void *p)
 // a staging ring is allocated once per DEVICE (pinning 64 MB costs several ms) and shared by that device's plans under
 // a lock: its events belong to the device's context (recording an event on another device's stream is
 // cudaErrorInvalidResourceHandle), and slabs on different GPUs download concurrently
+constexpr int STAGE_BUFS = 4;                               // pinned buffers in the ring: up to three copies in flight while one is drained
+constexpr size_t STAGE_CHUNK = (size_t)16 << 20;
 struct StagingRing {
     std::mutex mtx;
-    char *ring[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    char *ring[STAGE_BUFS] = {nullptr};
+    cudaEvent_t ev[STAGE_BUFS] = {nullptr};
 } g_staging_dev[64];
 
 template <class Sink>
 cudaError_t staged_d2h_sink(const void *src, size_t bytes, cudaStream_t st, Sink sink, bool *sink_ok)
 {
-    const size_t CH = (size_t)32 << 20;
+    const size_t CH = STAGE_CHUNK;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);                     // the caller holds a DeviceGuard for the plan's device
     if (e != cudaSuccess) return e;
@@ -139,23 +213,23 @@ cudaError_t staged_d2h_sink(const void *src, size_t bytes, cudaStream_t st, Sink
     char **ring = g_staging.ring;
     cudaEvent_t *ev = g_staging.ev;
     bool ok = true;
-    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    for (int b = 0; b < STAGE_BUFS && e == cudaSuccess; ++b) {
         if (!ring[b]) e = cudaHostAlloc(reinterpret_cast<void **>(&ring[b]), CH, cudaHostAllocPortable);
         if (e == cudaSuccess && !ev[b]) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
     }
     const size_t nch = (bytes + CH - 1) / CH;
     auto chunk = [&](size_t i) { return bytes - i * CH < CH ? bytes - i * CH : CH; };
-    if (e == cudaSuccess && nch) {
-        e = cudaMemcpyAsync(ring[0], static_cast<const char *>(src), chunk(0), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaEventRecord(ev[0], st);
-    }
+    auto issue = [&](size_t i) {                            // device -> ring[i % STAGE_BUFS], then the event that says so
+        cudaError_t r = cudaMemcpyAsync(ring[i % STAGE_BUFS], static_cast<const char *>(src) + i * CH, chunk(i), cudaMemcpyDeviceToHost, st);
+        if (r == cudaSuccess) r = cudaEventRecord(ev[i % STAGE_BUFS], st);
+        return r;
+    };
+    for (size_t i = 0; i + 1 < (size_t)STAGE_BUFS && i < nch && e == cudaSuccess; ++i) e = issue(i);
     for (size_t i = 0; i < nch && e == cudaSuccess && ok; ++i) {
-        if (i + 1 < nch) {                                  // ring[(i+1)&1] was drained in iteration i-1
-            e = cudaMemcpyAsync(ring[(i + 1) & 1], static_cast<const char *>(src) + (i + 1) * CH, chunk(i + 1), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaEventRecord(ev[(i + 1) & 1], st);
-        }
-        if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
-        if (e == cudaSuccess) ok = sink(ring[i & 1], chunk(i), i * CH);
+        // the buffer of chunk i + STAGE_BUFS - 1 held chunk i - 1, which the previous iteration drained
+        if (i + STAGE_BUFS - 1 < nch) e = issue(i + STAGE_BUFS - 1);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[i % STAGE_BUFS]);
+        if (e == cudaSuccess) ok = sink(ring[i % STAGE_BUFS], chunk(i), i * CH);
     }
     if (e != cudaSuccess || !ok) cudaStreamSynchronize(st); // nothing may still be writing into the ring when the lock goes
     if (sink_ok) *sink_ok = ok;
@@ -651,7 +725,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                     if (hi > 30) hi = 30;
                     p->look_next = p->look_hi = -1;
                     if (hi - s >= 2) {
-                        const int l = launch_look_scan(p->cells, p->rec, p->g, s, hi, p->changed, p->relax, st, p->max_ctas);
+                        const int l = launch_look_scan(p->cells, p->rec, p->g, s, hi, p->changed, p->relax, st, tun, p->max_ctas);
                         if (l) { g_launches += l; p->look_next = s; p->look_hi = hi; }
                     }
                 }

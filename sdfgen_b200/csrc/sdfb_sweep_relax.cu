@@ -996,8 +996,11 @@ RelaxLayout relax_layout(const Grid &g)
     RelaxLayout L{};
     const size_t cells = (size_t)g.cell_count(), words = (cells + 31) / 32 + 1;
     L.list_cap = sweep_relax_list_cap(g);
-    L.cap_c = (uint32_t)(cells < ((size_t)1 << 20) ? cells : ((size_t)1 << 20));
-    L.cap_w = (uint32_t)(cells < ((size_t)1 << 18) ? cells : ((size_t)1 << 18));
+    // lookahead lists: a light second pass changes ~0.1 % of the cells in all and marks ~0.02 .. 0.1 % of them per sweep;
+    // anything that does not fit a sixteenth (changed cells) / a sixty-fourth (marks of one sweep) is the heavy case
+    auto clamp = [](size_t v, size_t lo, size_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    L.cap_c = (uint32_t)clamp(cells / 16, cells < 4096 ? cells : 4096, (size_t)16 << 20);
+    L.cap_w = (uint32_t)clamp(cells / 64, cells < 4096 ? cells : 4096, (size_t)4 << 20);
     size_t o = 0;
     L.count = o; o += 64;
     L.oldbuf = o; o += cells * 8;
@@ -1045,6 +1048,10 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
         P.look = reinterpret_cast<LookState *>(s + L.look);
         P.c_list = reinterpret_cast<uint32_t *>(s + L.c_list); P.cap_c = L.cap_c;
         P.w_list = reinterpret_cast<uint32_t *>(s + L.w_list); P.cap_w = L.cap_w;
+        if (tun.look_cap > 0) {                                       // tests: force the overflow paths (same caps as launch_look_scan:
+            P.cap_c = min(P.cap_c, (uint32_t)tun.look_cap);           // cap_w is also the row stride of w_list)
+            P.cap_w = min(P.cap_w, (uint32_t)tun.look_cap);
+        }
     }
     // light sweeps put well under 1 % of the cells on their work lists (C2: 0.004-0.1 % on the first, less after),
     // heavy ones most of them, round after round
@@ -1106,7 +1113,7 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
 // runs k_look_scan on the cells as they are now.  The sweeps of the window must follow in order, each through
 // launch_sweep_relax(..., look = true); anything else invalidates the window (the caller then passes look = false).
 int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, int s_lo, int s_hi,
-                     unsigned long long *changed, void *scratch, cudaStream_t st, int max_ctas)
+                     unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas)
 {
     if (s_hi - s_lo < 1 || s_hi - s_lo > 8 || g.ni < 2 || g.nj < 2 || g.nk < 2 || g.k_lo != 0 || g.k_hi != g.nk) return 0;
     const RelaxLayout L = relax_layout(g);
@@ -1115,6 +1122,7 @@ int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, in
     P.g = g; P.cells = cells; P.rec = rec; P.changed = changed;
     P.look = reinterpret_cast<LookState *>(sc + L.look);
     P.w_list = reinterpret_cast<uint32_t *>(sc + L.w_list); P.cap_w = L.cap_w;
+    if (tun.look_cap > 0) P.cap_w = min(P.cap_w, (uint32_t)tun.look_cap);
     P.tmin = 0xffffffffu;
     for (int q = 0; q < 8; ++q) {
         P.sweep_of[q] = -1;

@@ -236,6 +236,36 @@ def test_relaxation_work_list_overflow_falls_back_to_bitmap(monkeypatch):
                 assert _same(g[f], getattr(r, f)), (name, flags, f)
 
 
+def test_lookahead_lists_overflow_falls_back_to_dense_round0(monkeypatch):
+    """The lookahead window of the second pass (k_look_scan / k_look_mark): when a list of marked voxels or the list of
+    changed cells overflows, the remaining sweeps of the window do their own dense round 0.  Force both overflows with tiny
+    capacities (the mark lists overflow inside the scan, the change list inside a sweep) and compare with the live oracle;
+    also without the window, and with windows that do not start at a multiple of 8 (sweeps asked for in odd batches)."""
+    for name, n in [("c1_blob_256", 40), ("c2_icosphere_512", 33)]:
+        w = meshes.workload(name, n=n, shuffle=True)
+        r = oracle.port.staged(w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+        for cap, look in ((None, None), ("3", None), ("40", None), ("400", None), (None, "0")):
+            for var, val in (("SDFB_LOOK_CAP", cap), ("SDFB_LOOKAHEAD", look)):
+                if val is None:
+                    monkeypatch.delenv(var, raising=False)
+                else:
+                    monkeypatch.setenv(var, val)
+            g = _staged_gpu(dict(w, band=1), 0)
+            for f in FIELDS:
+                assert _same(g[f], getattr(r, f)), (name, cap, look, f)
+        monkeypatch.delenv("SDFB_LOOK_CAP", raising=False)
+        monkeypatch.delenv("SDFB_LOOKAHEAD", raising=False)
+        for batches in ([(0, 8), (8, 3), (11, 5)], [(0, 9), (9, 7)], [(0, 8), (8, 2), (10, 1), (11, 2), (13, 3)]):
+            p = _lib.Plan(n, n, n)
+            p.set_mesh_host(w["vertices"], w["triangles"])
+            p.band(w["origin"], w["dx"], 1)
+            for first, count in batches:
+                p.sweep(first, count)
+            phi, tri, _ = p.download(phi=True, tri=True)
+            p.close()
+            assert _same(phi, r.phi_swept) and _same(tri, r.tri_final), (name, batches)
+
+
 def test_relaxation_hands_heavy_sweeps_back_to_columns(monkeypatch):
     """A relaxation sweep that meets more work than its limit restores the cells and lets the conditional column launch
     behind it do the sweep.  Limits 0 (every sweep falls back at once), 300 and 5000 entries (fall back in round 0 or after
