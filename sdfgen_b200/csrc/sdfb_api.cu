@@ -67,6 +67,7 @@ Tuning tuning_from_env()
     t.relax_debug = env_int("SDFB_RELAX_DEBUG", 0);
     t.lookahead = env_int("SDFB_LOOKAHEAD", 1);
     t.look_cap = env_int("SDFB_LOOK_CAP", 0);
+    t.early_copy = env_int("SDFB_EARLY_COPY", 1);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
     t.order_w = env_int("SDFB_ORDER_W", -1);
     t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
@@ -340,6 +341,7 @@ struct sdfb_plan {
     int last_sweep = -1;             // highest sweep index run since the last band: the relaxation schedule tells the
                                      // cells it changed by this sweep's stamp, so an index must not repeat
     int look_next = -1, look_hi = -1;   // lookahead window of the relaxation schedule: the next sweep it is valid for, and its end
+    int look_lo = -1;                   // ... and its first sweep
     // mesh
     uint64_t ntri = 0, nvert = 0;
     uint32_t *tri_own = nullptr;     // owned copies when the mesh came from the host
@@ -726,7 +728,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
                     p->look_next = p->look_hi = -1;
                     if (hi - s >= 2) {
                         const int l = launch_look_scan(p->cells, p->rec, p->g, s, hi, p->changed, p->relax, st, tun, p->max_ctas);
-                        if (l) { g_launches += l; p->look_next = s; p->look_hi = hi; }
+                        if (l) { g_launches += l; p->look_next = s; p->look_hi = hi; p->look_lo = s; }
                     }
                 }
                 look = p->look_next == s && s < p->look_hi;
@@ -971,6 +973,96 @@ int sdfb_plan_phase_ms(sdfb_plan *p, float out[4])
     return SDFB_OK;
 }
 
+// One-shot call, large grid, phi only: the download is as long as the second pass (C2: 13.7 ms for 537 MB into pageable
+// memory against 14.3 ms of kernels), and the second pass changes a few ten thousand of the 134 M values.  So the output
+// is produced EARLY -- sign and layout from the cells as they are after the first pass -- and copied to the host on a second
+// stream while the second pass runs; what the second pass changes is exactly the lookahead window's c_list
+// (sdfb_sweep_relax.cu), which comes back as {index, value} patches that the host applies.  Exact whenever it is used: if
+// the window was not complete (a list overflowed, a sweep was handed back, no window at all), the plain path below runs
+// instead.  Returns SDFB_OK with *done = true when phi_out holds the result; *done = false (and SDFB_OK) = not applicable or
+// not usable this time, nothing was written that the plain path will not overwrite.  SDFB_EARLY_COPY=0 turns it off.
+namespace {
+constexpr uint32_t PATCH_CAP = 1u << 20;      // patches per call; more changed cells than that -> plain path
+cudaStream_t g_copy_stream[64] = {nullptr};
+std::mutex g_copy_stream_mtx;
+
+int oneshot_early_copy(sdfb_plan *p, const float origin[3], float dx, int32_t exact_band, float *phi_out, bool *done, bool *ran)
+{
+    *done = false; *ran = false;
+    const Grid &g = p->g;
+    const size_t V = (size_t)g.slab_voxels(), out_bytes = V * sizeof(float);
+    if (!p->tun.early_copy || !p->tun.lookahead || (p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_COLUMNS)) || p->link.active ||
+        g.k_lo != 0 || g.k_hi != g.nk || out_bytes < ((size_t)64 << 20) || !sweep_relax_supported(g) || V >= ((size_t)1 << 32))
+        return SDFB_OK;
+    if (p->tun.relax_from >= 0 && p->tun.relax_from != 8) return SDFB_OK;
+    const int dev = p->device;
+    cudaStream_t cs = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_copy_stream_mtx);
+        if (dev < 0 || dev >= 64) return SDFB_OK;
+        if (!g_copy_stream[dev]) { CU(cudaStreamCreateWithFlags(&g_copy_stream[dev], cudaStreamNonBlocking)); }
+        cs = g_copy_stream[dev];
+    }
+    cudaStream_t st = nullptr;                                   // the one-shot call's work runs on the default stream
+    const bool kf = (p->flags & SDFB_OUT_KFASTEST) != 0;
+    *ran = true;
+    int rc = sdfb_plan_band(p, origin, dx, exact_band, st);
+    if (!rc) rc = sdfb_plan_sweep(p, 0, 8, st);
+    if (rc) return rc;
+    // the early output, and the event after which it may be copied
+    g_launches += launch_sign(p->cells, p->counts, g, !(p->flags & SDFB_NO_SIGN), false, p->phi, st);
+    if (kf) g_launches += launch_relayout_i32(reinterpret_cast<const int32_t *>(p->phi), g, reinterpret_cast<int32_t *>(p->phi_k), st);
+    CU(cudaGetLastError());
+    cudaEvent_t early = nullptr;
+    CU(cudaEventCreateWithFlags(&early, cudaEventDisableTiming));
+    struct EventGuard { cudaEvent_t e; ~EventGuard() { if (e) cudaEventDestroy(e); } } eg{early};
+    CU(cudaEventRecord(early, st));
+    rc = sdfb_plan_sweep(p, 8, 8, st);
+    if (rc) return rc;
+    const bool window = p->look_lo == 8 && p->look_hi == 16 && p->look_next == 16;
+    uint32_t *d_patch = nullptr;
+    unsigned int *d_head = nullptr;
+    struct DevGuard { void *a, *b; ~DevGuard() { if (a) dev_free(a); if (b) dev_free(b); } } dg{nullptr, nullptr};
+    if (window) {
+        CU(dev_alloc(&d_patch, (size_t)PATCH_CAP * 8));
+        dg.a = d_patch;
+        CU(dev_alloc(&d_head, 16));
+        dg.b = d_head;
+        if (!launch_look_patches(p->cells, p->phi, g, kf, p->relax, p->tun, d_patch, reinterpret_cast<float *>(d_patch + PATCH_CAP), PATCH_CAP, d_head, st))
+            return SDFB_OK;                                      // (cannot happen for a grid that had a window)
+        ++g_launches;
+        CU(cudaGetLastError());
+    }
+    // all of the above is asynchronous: touch the (usually fresh, pageable) output pages while the first pass runs
+    const bool pageable = is_pageable(phi_out);
+    if (pageable) parallel_for_bytes(reinterpret_cast<char *>(phi_out), out_bytes, touch_pages, nullptr);
+    if (window) {
+        CU(cudaStreamWaitEvent(cs, early, 0));
+        const float *src = kf ? p->phi_k : p->phi;
+        if (pageable) CU(staged_d2h(phi_out, src, out_bytes, cs));
+        else CU(cudaMemcpyAsync(phi_out, src, out_bytes, cudaMemcpyDeviceToHost, cs));
+        CU(cudaStreamSynchronize(cs));
+    }
+    unsigned int head[4] = {0, 0, 1, 0};
+    unsigned long long bad = ~0ull;
+    if (window) CU(cudaMemcpyAsync(head, d_head, 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&bad, p->changed + 3, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (bad != ~0ull) return bad_index_error(p, bad);
+    if (!window || head[2] != 0u || head[1] > PATCH_CAP || head[0] != head[1]) return SDFB_OK;     // plain path (sweeps are done)
+    const unsigned n = head[0];
+    if (n) {
+        std::vector<uint32_t> idx(n);
+        std::vector<float> val(n);
+        CU(cudaMemcpy(idx.data(), d_patch, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(val.data(), d_patch + PATCH_CAP, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        for (unsigned e = 0; e < n; ++e) phi_out[idx[e]] = val[e];
+    }
+    *done = true;
+    return SDFB_OK;
+}
+}  // namespace
+
 int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
                          const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
                          int32_t exact_band, float *phi_out, int32_t *closest_tri_out,
@@ -984,11 +1076,21 @@ int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, u
     if (rc) return rc;
     p->own_stream = true; p->stream = nullptr;                   // everything below runs on the default stream
     rc = sdfb_plan_set_mesh_host(p, tri, ntri, xyz, nvert, nullptr);
-    if (!rc) rc = sdfb_plan_run(p, origin, dx, exact_band, nullptr);
-    // everything above is asynchronous: touch the (usually fresh, pageable) output pages while the GPU computes
-    const size_t out_bytes = (size_t)ni * nj * nk * sizeof(float);
-    if (!rc && out_bytes >= ((size_t)64 << 20) && is_pageable(phi_out)) parallel_for_bytes(reinterpret_cast<char *>(phi_out), out_bytes, touch_pages, nullptr);
-    if (!rc) rc = sdfb_plan_download(p, phi_out, closest_tri_out, intersection_count_out, nullptr);
+    bool done = false, ran = false;
+    if (!rc && !closest_tri_out && !intersection_count_out) {
+        DeviceGuard dg(p->device);
+        rc = oneshot_early_copy(p, origin, dx, exact_band, phi_out, &done, &ran);
+    }
+    if (!rc && !done) {
+        // plain path: run (unless the early-copy attempt already ran band and sweeps and only its patches were unusable),
+        // sign, blocking download
+        if (!ran) rc = sdfb_plan_run(p, origin, dx, exact_band, nullptr);
+        else rc = sdfb_plan_sign(p, nullptr);
+        // everything above is asynchronous: touch the (usually fresh, pageable) output pages while the GPU computes
+        const size_t out_bytes = (size_t)ni * nj * nk * sizeof(float);
+        if (!rc && !ran && out_bytes >= ((size_t)64 << 20) && is_pageable(phi_out)) parallel_for_bytes(reinterpret_cast<char *>(phi_out), out_bytes, touch_pages, nullptr);
+        if (!rc) rc = sdfb_plan_download(p, phi_out, closest_tri_out, intersection_count_out, nullptr);
+    }
     sdfb_plan_destroy(p);
     return rc;
 }

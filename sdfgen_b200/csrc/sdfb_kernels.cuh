@@ -41,6 +41,7 @@ struct Tuning {
     int relax_debug = 0;          // SDFB_RELAX_DEBUG: per-sweep round statistics on stderr
     int lookahead = 1;            // SDFB_LOOKAHEAD: 0 = every relaxation sweep scans the grid for itself (no lookahead window)
     int look_cap = 0;             // SDFB_LOOK_CAP: capacity of the window's lists (tests force the overflow -> dense round 0 path)
+    int early_copy = 1;           // SDFB_EARLY_COPY: 0 = the one-shot call downloads phi after the last sweep, not during the second pass
     int order_w = -1;             // SDFB_ORDER_W: ticket order of fused launches by the key w*J + K (1 = anti-diagonals, >= NK = row by row)
     int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
     int link_debug = 0;           // SDFB_LINK_DEBUG: TIMING EXPERIMENTS ONLY, results are wrong -- 1: boundary cells are stored into a
@@ -115,6 +116,10 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
 // improve; returns the number of launches (0: not applicable to this grid)
 int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, int s_lo, int s_hi,
                      unsigned long long *changed, void *scratch, cudaStream_t st, const Tuning &tun, int max_ctas = 0);
+
+// what the window changed, as {output index, value} patches for an output made from the cells before the window
+int launch_look_patches(const uint64_t *cells, const float *phi_early, const Grid &g, bool kfastest, void *scratch, const Tuning &tun,
+                        uint32_t *patch_idx, float *patch_val, uint32_t cap, unsigned int *head, cudaStream_t st);
 
 size_t sweep_columns_progress_words(const Grid &g);
 

@@ -725,6 +725,33 @@ __global__ void __launch_bounds__(256) k_look_mark(RelaxParams P)
     }
 }
 
+// What a lookahead window changed, as patches for a signed-distance output that was produced (and is being copied to the
+// host) from the cells as they were BEFORE the window: every entry of c_list -> {index in the output layout, final value}.
+// The sign of a voxel depends on the crossing counts only, so it is taken from the early output; the magnitude is the
+// cell's.  head[0] = entries written (0 if they do not fit `cap`), head[1] = c_count, head[2] = dense_off: the caller
+// may only use the patches when head[2] == 0 and head[1] <= cap.
+__global__ void __launch_bounds__(256) k_look_patches(const uint64_t *__restrict__ cells, const float *__restrict__ phi_early, Grid g,
+                                                      int kfastest, const LookState *__restrict__ look, const uint32_t *__restrict__ c_list,
+                                                      uint32_t cap_c, uint32_t *__restrict__ patch_idx, float *__restrict__ patch_val,
+                                                      uint32_t cap, unsigned int *__restrict__ head)
+{
+    const unsigned n_all = look->c_count, off = look->dense_off;
+    const bool usable = off == 0u && n_all <= cap && n_all <= cap_c;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { head[0] = usable ? n_all : 0u; head[1] = n_all; head[2] = off; }
+    if (!usable) return;
+    const uint32_t plane32 = (uint32_t)g.plane();
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n_all; e += gridDim.x * blockDim.x) {
+        const uint32_t c = c_list[e];
+        const uint32_t p = c / plane32, rem = c - p * plane32;
+        const uint32_t j = rem / (uint32_t)g.ni, i = rem - j * (uint32_t)g.ni, k = p - 1u;       // whole-grid plans: k_lo = 0
+        const int64_t v = (int64_t)c - g.plane();
+        const float mag = cell_phi(cells[c]);
+        const bool inside = (__float_as_uint(phi_early[v]) >> 31) != 0u;
+        patch_idx[e] = kfastest ? (uint32_t)(((int64_t)i * g.nj + j) * (int64_t)g.nk + k) : (uint32_t)v;
+        patch_val[e] = inside ? -mag : mag;
+    }
+}
+
 // Grid-wide barrier for the co-resident (cooperatively launched) CTAs: one arrival counter that only grows;
 // `target` is the value it reaches when every CTA has arrived at this barrier.  Several times cheaper than
 // cooperative_groups' grid.sync() here, and the rounds are all latency.
@@ -1181,6 +1208,22 @@ int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, in
     const int64_t nitems = (int64_t)((g.nj + LK_WARPS - 1) / LK_WARPS) * g.nk;
     if ((int64_t)grid > nitems) grid = (int)nitems;
     k_look_scan<<<grid, LK_THREADS, smem, st>>>(P);
+    return 1;
+}
+
+
+// Patches for an output produced before the lookahead window (see k_look_patches); phi_early = that output, i fastest.
+// patch_idx / patch_val / head are device buffers; returns the number of launches (0: this grid has no window).
+int launch_look_patches(const uint64_t *cells, const float *phi_early, const Grid &g, bool kfastest, void *scratch, const Tuning &tun,
+                        uint32_t *patch_idx, float *patch_val, uint32_t cap, unsigned int *head, cudaStream_t st)
+{
+    if (g.k_lo != 0 || g.k_hi != g.nk || g.slab_voxels() >= ((int64_t)1 << 32)) return 0;
+    const RelaxLayout L = relax_layout(g);
+    char *sc = static_cast<char *>(scratch);
+    uint32_t cap_c = L.cap_c;
+    if (tun.look_cap > 0) cap_c = min(cap_c, (uint32_t)tun.look_cap);
+    k_look_patches<<<148, 256, 0, st>>>(cells, phi_early, g, kfastest ? 1 : 0, reinterpret_cast<const LookState *>(sc + L.look),
+                                        reinterpret_cast<const uint32_t *>(sc + L.c_list), cap_c, patch_idx, patch_val, cap, head);
     return 1;
 }
 

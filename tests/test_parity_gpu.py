@@ -493,6 +493,47 @@ def test_full_size_equals_the_reference_by_hash(golden_dir, case):
         del phi, tri, cnt
 
 
+@pytest.mark.parametrize("case", ["c1_blob_256", "c2_icosphere_512"])
+def test_one_shot_call_at_full_size_equals_the_reference_by_hash(golden_dir, case, monkeypatch):
+    """The drop-in call on a large grid copies phi to the host WHILE the second pass runs (the output is produced from the
+    cells after the first pass; what the second pass changes comes back as patches, sdfb_api.cu: oneshot_early_copy).
+    The result must hash to the unmodified reference's -- in the k-fastest layout of the Python API and in the
+    i-fastest one of the C entry, on a fresh pageable array and on a reused one, with the patches forced unusable (tiny
+    list capacity -> plain path after the sweeps) and with the early copy switched off."""
+    import json
+    ref = json.load(open(os.path.join(golden_dir, "big_hashes.json")))[case]
+    ni, nj, nk = ref["dims"]
+    w = meshes.workload(ref["workload"], n=ni)
+    v = np.ascontiguousarray(w["vertices"], np.float32)
+    t = np.ascontiguousarray(w["triangles"], np.uint32)
+    o = np.asarray(w["origin"], np.float32)
+
+    def c_entry(flags):
+        phi = np.empty(ni * nj * nk, np.float32)
+        for _ in range(2):                                        # second call: the same (now resident) pages
+            _lib.check(_lib.lib().sdfb_make_level_set3(t.ctypes.data, t.shape[0], v.ctypes.data, v.shape[0], o.ctypes.data,
+                                                       float(w["dx"]), ni, nj, nk, 1, phi.ctypes.data, None, None, flags))
+            yield phi
+
+    variants = [({}, "early copy"), ({"SDFB_LOOK_CAP": "50"}, "patches unusable"), ({"SDFB_EARLY_COPY": "0"}, "early copy off")]
+    if case != "c1_blob_256":
+        variants = variants[:1]                                   # the 512^3 case once: it is the configuration the bench times
+    for env, what in variants:
+        for var in ("SDFB_LOOK_CAP", "SDFB_EARLY_COPY"):
+            monkeypatch.delenv(var, raising=False)
+        for var, val in env.items():
+            monkeypatch.setenv(var, val)
+        sdf = sdfgen_b200.generate_sdf(v, t, tuple(o), float(w["dx"]), ni, nj, nk)
+        assert _sha(sdf.transpose(2, 1, 0)) == ref["phi"]["all"], (case, what, "k-fastest")
+        del sdf
+        signed = None
+        for phi in c_entry(0):
+            assert _sha(phi) == ref["phi"]["all"], (case, what, "i-fastest")
+            signed = phi
+        for phi in c_entry(_lib.NO_SIGN):                         # SDFB_NO_SIGN: the magnitudes, patched the same way
+            assert _same(phi, np.abs(signed)), (case, what, "unsigned")
+
+
 def test_out_of_range_vertex_index_is_an_error_not_a_dead_context():
     """The reference indexes x[] unchecked (cpu_lib/makelevelset3.cpp:205: undefined behaviour; its own test,
     python/tests/test_sdfgen.py:826-847, accepts a crash or any exception).  On a GPU an illegal address would kill the
