@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdarg>
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <condition_variable>
@@ -68,6 +69,7 @@ Tuning tuning_from_env()
     t.lookahead = env_int("SDFB_LOOKAHEAD", 1);
     t.look_cap = env_int("SDFB_LOOK_CAP", 0);
     t.early_copy = env_int("SDFB_EARLY_COPY", 1);
+    t.col_shape = env_int("SDFB_COL_SHAPE", 0);
     t.link_timeout_s = env_int("SDFB_LINK_TIMEOUT_S", 20);
     t.order_w = env_int("SDFB_ORDER_W", -1);
     t.link_debug = env_int("SDFB_LINK_DEBUG", 0);
@@ -545,7 +547,7 @@ int sdfb_plan_create(sdfb_plan **out, int device, int32_t ni, int32_t nj, int32_
         return fail(e == cudaErrorMemoryAllocation ? SDFB_ERR_OOM : SDFB_ERR_CUDA, "device allocation of %zu voxels failed: %s", V, cudaGetErrorString(e));
     }
     p->tun = tuning_from_env();
-    p->progress_words = sweep_columns_progress_words(p->g);
+    p->progress_words = std::max(sweep_columns_progress_words(p->g), sweep_columns_progress_words_ek12(p->g));   // either build may run
     if (p->progress_words && (e = dev_alloc(&p->progress, p->progress_words * sizeof(uint32_t))) != cudaSuccess) {
         sdfb_plan_destroy(p);
         cudaGetLastError();
@@ -695,6 +697,13 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     int fused_until = first;
     const int fuse_mode = tun.fuse_pass;                                        // -1 default, 0 off, 1 forced
     const bool big_launch = (int64_t)p->g.ni * (p->g.nj - 1) * p->g.nkl() >= ((int64_t)300 << 20);
+    // which build of the column schedule: 8 x 12 columns (160-thread CTAs, four per SM) below 300 M voxels, 8 x 16 above
+    // (sdfb_sweep_columns.cu); linked plans always run 8 x 16 (their hand-over buffers are laid out for it)
+    const bool ek12 = tun.col_shape ? tun.col_shape == 12 : !big_launch;
+    auto columns = [&](int s, const unsigned int *run_if) {
+        return ek12 ? launch_sweep_columns_ek12(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, run_if, p->max_ctas)
+                    : launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, run_if, p->max_ctas);
+    };
     if (fuse_mode != 0 && (fuse_mode == 1 || !big_launch) &&
         !(p->flags & (SDFB_SWEEP_LEVELS | SDFB_SWEEP_RELAX)) && first < 8 && first < relax_from) {
         int n = (first + count < 8 ? first + count : 8);
@@ -702,8 +711,10 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
         n -= first;
         if (n >= 2) {
             CU(reset_epoch_if_needed((uint32_t)n));
-            const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
-                                                     &p->epoch, st, tun, p->max_ctas);
+            const int l = ek12 ? launch_sweep_columns_fused_ek12(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
+                                                                  &p->epoch, st, tun, p->max_ctas)
+                               : launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
+                                                            &p->epoch, st, tun, p->max_ctas);
             if (l) { g_launches += l; fused_until = first + n; p->look_next = p->look_hi = -1; }
         }
     }
@@ -738,12 +749,11 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
             // a sweep that turns out to change a large part of the grid is handed back (cells restored, flag set):
             // this launch then runs it with the column schedule, and exits at once otherwise
             CU(reset_epoch_if_needed(1));
-            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun,
-                                               sweep_relax_fallback_flag(p->relax), p->max_ctas);
+            g_launches += columns(s, sweep_relax_fallback_flag(p->relax));
         } else {
             p->look_next = p->look_hi = -1;
             CU(reset_epoch_if_needed(1));
-            g_launches += launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, nullptr, p->max_ctas);
+            g_launches += columns(s, nullptr);
         }
     }
     if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;

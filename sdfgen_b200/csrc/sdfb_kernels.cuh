@@ -42,6 +42,7 @@ struct Tuning {
     int lookahead = 1;            // SDFB_LOOKAHEAD: 0 = every relaxation sweep scans the grid for itself (no lookahead window)
     int look_cap = 0;             // SDFB_LOOK_CAP: capacity of the window's lists (tests force the overflow -> dense round 0 path)
     int early_copy = 1;           // SDFB_EARLY_COPY: 0 = the one-shot call downloads phi after the last sweep, not during the second pass
+    int col_shape = 0;            // SDFB_COL_SHAPE: 12 / 16 = force the 8 x 12 / 8 x 16 build of the column schedule (0: by launch size)
     int order_w = -1;             // SDFB_ORDER_W: ticket order of fused launches by the key w*J + K (1 = anti-diagonals, >= NK = row by row)
     int link_timeout_s = 20;      // SDFB_LINK_TIMEOUT_S: watchdog of the cross-GPU waits (the kernel traps instead of hanging)
     int link_debug = 0;           // SDFB_LINK_DEBUG: TIMING EXPERIMENTS ONLY, results are wrong -- 1: boundary cells are stored into a
@@ -97,6 +98,15 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
                                unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
                                cudaStream_t st, const Tuning &tun, int max_ctas, const LinkState *link = nullptr);
 size_t link_flag_words_per_sweep(const Grid &g);     // NJ of the column schedule
+// the same schedule built with 8 x 12 columns (sdfb_sweep_columns_ek12.cu): four 160-thread CTAs per SM, for launches below
+// 300 M voxels on unlinked plans
+int launch_sweep_columns_ek12(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
+                              unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
+                              const Tuning &tun, const unsigned int *run_if = nullptr, int max_ctas = 0);
+int launch_sweep_columns_fused_ek12(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
+                                    unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
+                                    cudaStream_t st, const Tuning &tun, int max_ctas, const LinkState *link = nullptr);
+size_t sweep_columns_progress_words_ek12(const Grid &g);
 int launch_sign(const uint64_t *cells, const int32_t *counts, const Grid &g, bool apply_sign,
                 bool kfastest, float *phi_out, cudaStream_t st);
 int launch_unpack_tri(const uint64_t *cells, const Grid &g, bool kfastest, int32_t *tri_out, cudaStream_t st);

@@ -44,6 +44,18 @@
 #include "sdfb_kernels.cuh"
 #include "sdfb_sweep_common.cuh"
 
+// This file is compiled TWICE into the library: as it stands (8 x 16 columns: CTAs of 192 threads, three or four per SM), and
+// through sdfb_sweep_columns_ek12.cu with 8 x 12 columns (CTAs of 160 threads, FOUR per SM at the full 93 registers), whose
+// entry points carry the suffix _ek12.  Small launches are bound by the length of the wavefront's dependency chain and by
+// how many columns are resident, and run 5-6 % faster with the smaller CTAs (C2 first pass 54.6 -> 51.5 ms); large ones
+// (>= 300 M voxels) are throughput-bound and keep 8 x 16 (C3: 232 ms against 256).  sdfb_api.cu chooses by launch size.
+#ifndef SDFB_COLS_SUFFIX
+#define SDFB_COLS_SUFFIX
+#endif
+#define SDFB_COLS_CAT2(a, b) a##b
+#define SDFB_COLS_CAT(a, b) SDFB_COLS_CAT2(a, b)
+#define COLS_FN(name) SDFB_COLS_CAT(name, SDFB_COLS_SUFFIX)
+
 namespace sdfb {
 
 namespace {
@@ -89,6 +101,17 @@ constexpr int EVAL_LANES = HALO_EVAL ? NSTEPPERS : NCOMPUTE;   // lanes that sha
 #define SDFB_PUBLISH 2
 #endif
 constexpr int PUBLISH = SDFB_PUBLISH;                   // steps between progress publications
+// The kernels are built for two register bounds, template parameter MINB = 3 and 4 CTAs per SM; SDFB_MINB_HI replaces the
+// "4" (smaller column cross-sections make smaller CTAs, of which more fit an SM).
+#ifndef SDFB_MINB_HI
+#define SDFB_MINB_HI 4
+#endif
+constexpr int minb_bound(int m) { return m >= 4 ? SDFB_MINB_HI : m; }
+// register bound for launches below 300 M voxels (the 160-thread CTAs of the 8 x 12 build fit four to an SM without spills)
+#ifndef SDFB_MINB_SMALL
+#define SDFB_MINB_SMALL 3
+#endif
+constexpr int MINB_SMALL = SDFB_MINB_SMALL;
 // SDFB_QATOMIC: the warps of a column reserve their slice of the column-wide queue with one shared-memory atomicAdd
 // instead of exchanging their totals through a barrier: a step with candidates takes 3 CTA barriers instead of 4.
 // The order of the slices in the queue then depends on arrival order, which only changes WHICH lane evaluates an
@@ -860,7 +883,7 @@ __device__ __forceinline__ void column_loop(uint64_t *__restrict__ cells, const 
 }
 
 template <bool CTA_QUEUE, int MINB>
-__global__ void __launch_bounds__(NTHREADS, WG ? 4 : MINB)
+__global__ void __launch_bounds__(NTHREADS, WG ? 4 : minb_bound(MINB))
 k_sweep_columns(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, ColParams P,
                 uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket,
                 unsigned long long *__restrict__ changed)
@@ -920,7 +943,7 @@ static_assert(sizeof(FusedParams) <= 4096, "FusedParams must stay within the cla
 // within a sweep, so the dependency graph over (sweep, position in flow order, ticket) stays acyclic: no deadlock as
 // long as every GPU's launch is eventually resident (one launch per GPU, or capped grids when slabs share a GPU).
 template <int MINB, bool LINK>
-__global__ void __launch_bounds__(NTHREADS, MINB)
+__global__ void __launch_bounds__(NTHREADS, minb_bound(MINB))
 k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ rec, const __grid_constant__ FusedParams FP,
                       uint32_t *__restrict__ progress, uint32_t *__restrict__ ticket, unsigned long long *__restrict__ changed)
 {
@@ -1021,7 +1044,7 @@ bool fill_col_params(ColParams &P, const Grid &g, int sweep_index, uint32_t epoc
 // Returns the number of launches (1), or 0 if this grid cannot be fused (then the caller launches sweep by sweep);
 // *epoch is advanced by one per sweep.  link != nullptr: exact multi-GPU mode (the caller has made sure every sweep of
 // the range updates at least one plane of this slab and that first + count <= LINK_SWEEPS).
-int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
+int COLS_FN(launch_sweep_columns_fused)(uint64_t *cells, const TriRec *rec, const Grid &g, int first, int count,
                                unsigned long long *changed, uint32_t *progress, size_t progress_words, uint32_t *epoch,
                                cudaStream_t st, const Tuning &tun, int max_ctas, const LinkState *link)
 {
@@ -1062,7 +1085,7 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int minb = ((int64_t)g.ni * (g.nj - 1) * (FP.p[0].rk_last - FP.p[0].rk_first + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
+    int minb = ((int64_t)g.ni * (g.nj - 1) * (FP.p[0].rk_last - FP.p[0].rk_first + 1) >= ((int64_t)300 << 20)) ? 4 : MINB_SMALL;
     if (tun.minb) minb = tun.minb >= 4 ? 4 : 3;
     using kern_t = void (*)(uint64_t *, const TriRec *, const FusedParams, uint32_t *, uint32_t *, unsigned long long *);
     const kern_t kern = link ? (minb == 4 ? k_sweep_columns_fused<4, true> : k_sweep_columns_fused<3, true>)
@@ -1082,17 +1105,17 @@ int launch_sweep_columns_fused(uint64_t *cells, const TriRec *rec, const Grid &g
     return 1;
 }
 
-size_t link_flag_words_per_sweep(const Grid &g) { return (size_t)(g.nj - 1 + EJ - 1) / EJ + 1; }
+size_t COLS_FN(link_flag_words_per_sweep)(const Grid &g) { return (size_t)(g.nj - 1 + EJ - 1) / EJ + 1; }
 
 // progress: [2] ticket words + [1] epoch counter slot (host side keeps the epoch) + 2 x NJ*NK flags (the second array is
 // used by fused launches only)
-size_t sweep_columns_progress_words(const Grid &g)
+size_t COLS_FN(sweep_columns_progress_words)(const Grid &g)
 {
     size_t NJ = (size_t)(g.nj + EJ - 1) / EJ + 1, NK = (size_t)(g.nkl() + EK - 1) / EK + 1;
     return 4 + 2 * NJ * NK;
 }
 
-int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
+int COLS_FN(launch_sweep_columns)(uint64_t *cells, const TriRec *rec, const Grid &g, int sweep_index,
                          unsigned long long *changed, uint32_t *progress, uint32_t epoch, cudaStream_t st,
                          const Tuning &tun, const unsigned int *run_if, int max_ctas)
 {
@@ -1128,7 +1151,7 @@ int launch_sweep_columns(uint64_t *cells, const TriRec *rec, const Grid &g, int 
     const bool cta_queue = tun.cta_queue >= 0 ? tun.cta_queue != 0 : (sweep_index < 8);
     int occ = 1;
     // register bound by the amount of work per launch (see k_sweep_columns)
-    int minb = ((int64_t)g.ni * (g.nj - 1) * (rk_hi - rk_lo + 1) >= ((int64_t)300 << 20)) ? 4 : 3;
+    int minb = ((int64_t)g.ni * (g.nj - 1) * (rk_hi - rk_lo + 1) >= ((int64_t)300 << 20)) ? 4 : MINB_SMALL;
     if (tun.minb) minb = tun.minb >= 4 ? 4 : 3;
     using kern_t = void (*)(uint64_t *, const TriRec *, ColParams, uint32_t *, uint32_t *, unsigned long long *);
     const kern_t kern = cta_queue ? (minb == 4 ? k_sweep_columns<true, 4> : k_sweep_columns<true, 3>)

@@ -59,6 +59,24 @@ def test_golden_small_cases_bit_exact(golden_dir, sched, flags):
             assert _same(g[f], c["ref"][f]), (sched, c["name"], f, int((_bits(g[f]) != _bits(c["ref"][f])).sum()))
 
 
+@pytest.mark.parametrize("shape", ["12", "16"])
+def test_both_builds_of_the_column_schedule(golden_dir, shape, monkeypatch):
+    """The column schedule is compiled twice (8 x 12 columns for launches below 300 M voxels, 8 x 16 above and for linked
+    slabs); force each build onto the small cases, for the default mix and for columns on all 16 sweeps."""
+    monkeypatch.setenv("SDFB_COL_SHAPE", shape)
+    for c in load_golden(golden_dir):
+        for flags in (0, _lib.SWEEP_COLUMNS):
+            g = _staged_gpu(c, flags)
+            for f in FIELDS:
+                assert _same(g[f], c["ref"][f]), (shape, flags, c["name"], f)
+    w = meshes.workload("c2_icosphere_512", n=72, shuffle=True)
+    r = oracle.best().staged(w["vertices"], w["triangles"], w["origin"], w["dx"], 72, 72, 72)
+    for flags in (0, _lib.SWEEP_COLUMNS):
+        g = _staged_gpu(dict(w, band=1), flags)
+        for f in FIELDS:
+            assert _same(g[f], getattr(r, f)), (shape, flags, f)
+
+
 def test_one_shot_abi_matches_golden(golden_dir):
     for c in load_golden(golden_dir):
         phi, tri, cnt = sdfgen_b200.generate_sdf_debug(c["vertices"], c["triangles"], c["origin"], c["dx"],
