@@ -144,10 +144,12 @@ class _Port:
         return cphi[plane:plane * (nk + 1)].copy(), tri, evals, scan_evals, r0
 
     def emu_sweep_columns(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16,
-                          k_lo=0, k_hi=None):
-        """CPU emulation of the CUDA column schedule (oracle/columns_emu.c) starting from band results.
+                          k_lo=0, k_hi=None, shape=(8, 16)):
+        """CPU emulation of the CUDA column schedule (oracle/columns_emu.c) starting from band results; shape = the
+        column cross-section (the library builds 8 x 16 and 8 x 12).
         Returns (phi_swept, tri_final, evals_per_sweep, changed_per_sweep, flag_violations)."""
         v, t, o = _prep(vertices, triangles, origin)
+        self.lib().sdfo_emu_set_column_shape(int(shape[0]), int(shape[1]))
         k_hi = nk if k_hi is None else k_hi
         plane = ni * nj
         nkl = k_hi - k_lo
@@ -164,6 +166,7 @@ class _Port:
             evals.append(int(e)); changed.append(int(ch.value))
         lo = clo[plane:plane * (nkl + 1)]
         tri = np.where((lo & 0x07FFFFFF) == 0x07FFFFFF, -1, (lo & 0x07FFFFFF).astype(np.int64)).astype(np.int32)
+        self.lib().sdfo_emu_set_column_shape(8, 16)
         return cphi[plane:plane * (nkl + 1)].copy(), tri, evals, changed, int(self.lib().sdfo_emu_flag_violations())
 
     def emu_sweep_mixed(self, vertices, triangles, origin, dx, ni, nj, nk, phi_band, tri_band, nsweeps=16, relax_from=8, seed=1):

@@ -17,8 +17,9 @@
 
 float sdfo_point_triangle_distance(const float *x0, const float *x1, const float *x2, const float *x3);
 
-#define EJ 8
-#define EK 16
+/* column cross-section: the library builds the schedule twice, 8 x 16 (default here) and 8 x 12 (sdfb_sweep_columns_ek12.cu) */
+static int EJ = 8, EK = 16;
+void sdfo_emu_set_column_shape(int ej, int ek) { if (ej >= 1 && ek >= 1 && ej * ek <= 256 && (ej * ek) % 32 == 0) { EJ = ej; EK = ek; } }
 #define NCOMPUTE (EJ*EK)
 #define NLANES (NCOMPUTE + 64)
 #define PUBLISH 2
@@ -81,8 +82,8 @@ long sdfo_emu_sweep_columns(const uint32_t *tri, const float *x, float *cells_ph
     long evals = 0, changed = 0;
 
     uint32_t ring[RING * (EK + 1) * (EJ + 1)];
-    static uint32_t q_ent[NCOMPUTE / 32][7 * 32];
-    static float q_d[NCOMPUTE / 32][7 * 32];
+    static uint32_t q_ent[8][7 * 32];
+    static float q_d[8][7 * 32];
 
     const int ncols = NJ * NK;
     for (int tk = 0; tk < ncols; ++tk) {

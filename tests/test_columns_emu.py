@@ -18,12 +18,13 @@ def _same(a, b):
     ("c1_blob_256", (9, 17, 33), False),        # ni shorter than the column skew
     ("c3_torus_1024", (33, 2, 5), False),       # single row of updated voxels in j
 ])
-def test_emulated_columns_equal_serial_oracle(name, dims, shuffle):
+@pytest.mark.parametrize("shape", [(8, 16), (8, 12)])   # the two builds of the schedule in libsdfb.so
+def test_emulated_columns_equal_serial_oracle(name, dims, shuffle, shape):
     ni, nj, nk = dims
     w = meshes.workload(name, n=max(dims), shuffle=shuffle)
     a = (w["vertices"], w["triangles"], w["origin"], w["dx"], ni, nj, nk)
     r = oracle.port.staged(*a, stats=True)
-    phi, tri, evals, changed, viol = oracle.port.emu_sweep_columns(*a, r.phi_band, r.tri_band)
+    phi, tri, evals, changed, viol = oracle.port.emu_sweep_columns(*a, r.phi_band, r.tri_band, shape=shape)
     assert viol == 0
     assert _same(phi, r.phi_swept) and _same(tri, r.tri_final)
     # evaluations: far below the reference's 7 per voxel per sweep and below plain de-duplication
