@@ -700,8 +700,10 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
     // which build of the column schedule: 8 x 12 columns (160-thread CTAs, four per SM) below 300 M voxels, 8 x 16 above
     // (sdfb_sweep_columns.cu); linked plans always run 8 x 16 (their hand-over buffers are laid out for it)
     const bool ek12 = tun.col_shape ? tun.col_shape == 12 : !big_launch;
+    // max_ctas (several plans share the device) is this plan's share of THREE CTAs per SM; the 8 x 12 build fits four
+    const int max_ctas12 = p->max_ctas > 0 ? (p->max_ctas * 4 + 2) / 3 : 0;
     auto columns = [&](int s, const unsigned int *run_if) {
-        return ek12 ? launch_sweep_columns_ek12(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, run_if, p->max_ctas)
+        return ek12 ? launch_sweep_columns_ek12(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, run_if, max_ctas12)
                     : launch_sweep_columns(p->cells, p->rec, p->g, s, p->changed, p->progress, ++p->epoch, st, tun, run_if, p->max_ctas);
     };
     if (fuse_mode != 0 && (fuse_mode == 1 || !big_launch) &&
@@ -712,7 +714,7 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
         if (n >= 2) {
             CU(reset_epoch_if_needed((uint32_t)n));
             const int l = ek12 ? launch_sweep_columns_fused_ek12(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
-                                                                  &p->epoch, st, tun, p->max_ctas)
+                                                                  &p->epoch, st, tun, max_ctas12)
                                : launch_sweep_columns_fused(p->cells, p->rec, p->g, first, n, p->changed, p->progress, p->progress_words,
                                                             &p->epoch, st, tun, p->max_ctas);
             if (l) { g_launches += l; fused_until = first + n; p->look_next = p->look_hi = -1; }

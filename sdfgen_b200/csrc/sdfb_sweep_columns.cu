@@ -226,6 +226,15 @@ struct ColShared {
     float4 stage[STAGE > 0 ? NCOMPUTE * STAGE * 3 : 1];   // SDFB_STAGE: [owner lane][slot] -> the record's three float4
 };
 
+// Which entry an evaluating lane starts with.  The entries beyond a multiple of EVAL_LANES make a partial extra round for the
+// lanes with the lowest start numbers.  SDFB_EVAL_REV=1 numbers the lanes backwards, so that this extra round falls on the
+// halo warp (which has little else to do) and the LAST compute warps instead of on compute warp 0 -- the warp that shares
+// its scheduler with the sync warp's polling loop when warps go to schedulers by warp number.
+#ifndef SDFB_EVAL_REV
+#define SDFB_EVAL_REV 0
+#endif
+__device__ __forceinline__ int eval_first(int lane_number) { return SDFB_EVAL_REV ? EVAL_LANES - 1 - lane_number : lane_number; }
+
 // Evaluation share of one lane in the column-wide queue: entries first, first+EVAL_LANES, ...
 __device__ __forceinline__ unsigned evaluate_queue_share(const TriRec *__restrict__ rec, ColShared &sh, int first, int total)
 {
@@ -280,7 +289,7 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
     if (QATOMIC) {
         total = *reinterpret_cast<volatile int *>(&sh.qn);            // final: every warp reserved before the barrier
         if (total == 0) return 0u;
-        const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, NCOMPUTE + h, total) : 0u;
+        const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, eval_first(NCOMPUTE + h), total) : 0u;
         bar_compute();
         return e;
     }
@@ -288,7 +297,7 @@ __device__ __forceinline__ unsigned halo_evaluate_share(const TriRec *__restrict
     for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
     if (total == 0) return 0u;
     if (!ONEBAR) bar_compute();                   // SDFB_ONEBAR: the entries were written before the first barrier
-    const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, NCOMPUTE + h, total) : 0u;
+    const unsigned e = HALO_EVAL ? evaluate_queue_share(rec, sh, eval_first(NCOMPUTE + h), total) : 0u;
     bar_compute();
     return e;
 }
@@ -682,7 +691,7 @@ __device__ __forceinline__ uint2 evaluate_candidates_cta(const TriRec *__restric
         for (int w = 0; w < NCOMPUTE / 32; ++w) total += sh.wtot[w];
         if (total == 0) return make_uint2(cur, 0u);                   // uniform over the column
     }
-    evals = evaluate_queue_share(rec, sh, tid, total);
+    evals = evaluate_queue_share(rec, sh, eval_first(tid), total);
     TRACE(P, warp, s, 5);
     bar_compute();
     TRACE(P, warp, s, 6);

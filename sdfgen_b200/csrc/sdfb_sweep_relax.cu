@@ -548,7 +548,10 @@ __device__ __forceinline__ void look_flush(const LookParams &P, LookShared &sh, 
     nq = 0; np = 0;
 }
 
-__global__ void __launch_bounds__(LK_THREADS, 3) k_look_scan(const __grid_constant__ LookParams P)
+#ifndef SDFB_LOOK_MINB
+#define SDFB_LOOK_MINB 3
+#endif
+__global__ void __launch_bounds__(LK_THREADS, SDFB_LOOK_MINB) k_look_scan(const __grid_constant__ LookParams P)
 {
     extern __shared__ __align__(16) unsigned char look_smem[];
     LookShared &sh = *reinterpret_cast<LookShared *>(look_smem);
