@@ -92,7 +92,15 @@ constexpr bool WG = SDFB_WG != 0;
 constexpr bool HALO_EVAL = !WG || SDFB_WG_HALO_EVAL != 0;   // the halo warp takes a share of the evaluations
 static_assert(!WG || NCOMPUTE == 128, "the warpgroup layout needs exactly four compute warps");
 static_assert(EJ * EK <= 256, "queue entries carry the owner lane in 8 bits");
-constexpr int NTHREADS = WG ? 256 : NSTEPPERS + 32;     // + 1 sync warp (flag polling and progress publication)
+// SDFB_MERGE_SYNC: no separate sync warp -- the halo warp polls its producers' progress words itself (only when the values
+// it last saw do not cover the next chunk) and publishes the column's progress right after the chunk's last step barrier.
+// A CTA is 32 threads smaller, so one more fits an SM at the full register count (8 x 12: five of 128 threads, 8 x 16: four of
+// 160 without spills), and the polling loops (a third of the executed instructions) disappear.
+#ifndef SDFB_MERGE_SYNC
+#define SDFB_MERGE_SYNC 0
+#endif
+constexpr bool MERGE = SDFB_MERGE_SYNC != 0 && !WG;
+constexpr int NTHREADS = WG ? 256 : (MERGE ? NSTEPPERS : NSTEPPERS + 32);     // + 1 sync warp (flag polling and progress publication)
 constexpr int EVAL_LANES = HALO_EVAL ? NSTEPPERS : NCOMPUTE;   // lanes that share the column-wide evaluation queue
 #ifndef SDFB_SYNC_SLEEP
 #define SDFB_SYNC_SLEEP 150
@@ -438,8 +446,14 @@ __device__ __forceinline__ void sync_column(const ColParams &P, ColShared &sh, i
 // lane of the J = 0 column that reads it anyway (b = the slab's last plane).
 template <bool CTA_QUEUE, bool LINK>
 __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, const TriRec *__restrict__ rec,
-                                            const ColParams &P, ColShared &sh, int h, int rj0, int rk0, unsigned &my_evals)
+                                            const ColParams &P, ColShared &sh, int h, int rj0, int rk0, unsigned &my_evals,
+                                            const uint32_t *prog_left = nullptr, const uint32_t *prog_down = nullptr, uint32_t *prog_mine = nullptr,
+                                            const unsigned long long *link_down = nullptr, unsigned long long *link_mine = nullptr)
 {
+    // SDFB_MERGE_SYNC: what this warp last read from its producers' progress words (all lanes hold the same values)
+    const uint32_t ebase = P.epoch << 16;
+    uint32_t seen_l = prog_left ? 0u : 0xffffffffu, seen_d = prog_down ? 0u : 0xffffffffu;
+    unsigned long long seen_link = (LINK && link_down) ? 0ull : ~0ull;
     const Grid &g = P.g;
     int a, b;
     if (h <= EK) { a = -1; b = h - 1; }                    // (-1,-1), (-1,0) .. (-1,EK-1)
@@ -465,7 +479,30 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
     uint64_t wA = ~0ull, wB = ~0ull;
     for (int s0 = 0, c = 0; s0 < P.steps; s0 += PUBLISH, ++c) {
         const int s1 = s0 + PUBLISH;                       // P.steps is a multiple of PUBLISH
-        bar_go_wait(c);                                    // until the sync warp has cleared chunk c
+        if (!MERGE) bar_go_wait(c);                        // until the sync warp has cleared chunk c
+        else {
+            // the same condition as sync_column's, polled here: the loads of this chunk (words of steps up to s1 + 1) may be
+            // issued once the producers have completed s1 - 1 + E + 3 steps.  Uniform over the warp; no fence (see sync_column).
+            const uint32_t need_l = ebase + (uint32_t)min(P.steps, s1 - 1 + EJ + 3), need_d = ebase + (uint32_t)min(P.steps, s1 - 1 + EK + 3);
+            const unsigned long long need_link = P.run_base + (unsigned long long)min(P.steps, s1 - 1 + EK + 3);
+            unsigned idle = 0;
+            unsigned long long t_wait = 0;
+            while (seen_l < need_l || seen_d < need_d || (LINK && seen_link < need_link)) {
+                if (prog_left) seen_l = *reinterpret_cast<const volatile uint32_t *>(prog_left);
+                if (prog_down) seen_d = *reinterpret_cast<const volatile uint32_t *>(prog_down);
+                if (LINK && link_down) seen_link = *reinterpret_cast<const volatile unsigned long long *>(link_down);
+                if (seen_l >= need_l && seen_d >= need_d && !(LINK && seen_link < need_link)) break;
+                __nanosleep(SDFB_SYNC_SLEEP);
+                if (LINK && P.link_timeout_ns && (++idle & 1023u) == 0) {
+                    const unsigned long long now = global_timer_ns();
+                    if (idle == 1024u) t_wait = now;
+                    else if (now - t_wait > P.link_timeout_ns) {
+                        if (h == 0) printf("sdfb: column wait timed out (sweep stamp %u, waiting for %s)\n", P.stamp, link_down ? "the neighbour GPU" : "a local column");
+                        __trap();
+                    }
+                }
+            }
+        }
         if (s0 == 0 && row_ok) {
             if ((unsigned)ri < (unsigned)g.ni) wA = __ldcg(ptr);
             if ((unsigned)(ri + 1) < (unsigned)g.ni) wB = __ldcg(ptr + si);
@@ -494,6 +531,16 @@ __device__ __forceinline__ void halo_column(const uint64_t *__restrict__ cells, 
             if (CTA_QUEUE) my_evals += halo_evaluate_share(rec, sh, h);
             TRACE(P, 8 + (h >> 5), s + 1, 7);
             bar_step();
+        }
+        if (MERGE && h == 0) {
+            // every lane's cell stores of this chunk precede its arrival at the step barrier this warp has just left: the
+            // RELEASE store (not fence + store, see sync_column) makes them visible before the progress word
+            if (LINK && link_mine) {
+                const unsigned long long v = P.run_base + (unsigned long long)s1;
+                if (P.link_gpu_fence) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(link_mine), "l"(v) : "memory");
+                else asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(link_mine), "l"(v) : "memory");
+            }
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_mine), "r"(ebase + (uint32_t)s1) : "memory");
         }
     }
 }
@@ -881,8 +928,14 @@ __device__ __forceinline__ void column_loop(uint64_t *__restrict__ cells, const 
         if (GROUP != 1 && tid < NCOMPUTE) {
             compute_column<CTA_QUEUE>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (GROUP != 0 && tid >= NCOMPUTE && tid < NSTEPPERS) {
-            halo_column<CTA_QUEUE, false>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
-        } else if (GROUP != 0 && tid >= NSTEPPERS && tid < NSTEPPERS + 32) {
+            if (MERGE) {
+                const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
+                const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
+                halo_column<CTA_QUEUE, false>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals, prog_left, prog_down, &progress[K * P.NJ + J]);
+            } else {
+                halo_column<CTA_QUEUE, false>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            }
+        } else if (!MERGE && GROUP != 0 && tid >= NSTEPPERS && tid < NSTEPPERS + 32) {
             const uint32_t *prog_left = (J > 0) ? &progress[K * P.NJ + (J - 1)] : nullptr;
             const uint32_t *prog_down = (K > 0) ? &progress[(K - 1) * P.NJ + J] : nullptr;
             sync_column<false>(P, sh, lane, prog_left, prog_down, &progress[K * P.NJ + J]);
@@ -1002,9 +1055,21 @@ k_sweep_columns_fused(uint64_t *__restrict__ cells, const TriRec *__restrict__ r
             if (P.cta_queue) compute_column<true, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
             else compute_column<false, true, LINK>(cells, rec, P, sh, tid, rj0, rk0, my_changed, my_evals);
         } else if (tid < NSTEPPERS) {
-            if (P.cta_queue) halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
-            else halo_column<false, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
-        } else if (tid < NSTEPPERS + 32) {
+            if (MERGE) {
+                // the halo warp is the sync warp too: previous sweep's prerequisites, release of the compute lanes, then the column
+                if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, tid - NCOMPUTE, J, K);
+                bar_start_arrive();
+                const uint32_t *prog_left = (J > 0) ? &flags[K * P.NJ + (J - 1)] : nullptr;
+                const uint32_t *prog_down = (K > 0) ? &flags[(K - 1) * P.NJ + J] : nullptr;
+                const unsigned long long *link_down = (LINK && K == 0 && P.link.flag_src) ? &P.link.flag_src[J] : nullptr;
+                unsigned long long *link_mine = (LINK && K == P.NK - 1 && P.link.flag_dst) ? &P.link.flag_dst[J] : nullptr;
+                if (P.cta_queue) halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals, prog_left, prog_down, &flags[K * P.NJ + J], link_down, link_mine);
+                else halo_column<false, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals, prog_left, prog_down, &flags[K * P.NJ + J], link_down, link_mine);
+            } else {
+                if (P.cta_queue) halo_column<true, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+                else halo_column<false, LINK>(cells, rec, P, sh, tid - NCOMPUTE, rj0, rk0, my_evals);
+            }
+        } else if (!MERGE && tid < NSTEPPERS + 32) {
             if (q > 0) wait_previous_sweep(P, FP.p[q - 1], progress + ((q - 1) & 1) * FP.flag_stride, lane, J, K);
             bar_start_arrive();
             const uint32_t *prog_left = (J > 0) ? &flags[K * P.NJ + (J - 1)] : nullptr;
