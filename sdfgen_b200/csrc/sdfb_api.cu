@@ -239,6 +239,39 @@ cudaError_t staged_d2h_sink(const void *src, size_t bytes, cudaStream_t st, Sink
     return e;
 }
 
+// Host -> device for a pageable source, through the same ring: the worker threads copy chunk i into a pinned buffer while
+// the DMA of chunk i-1 runs.  cudaMemcpyAsync from pageable memory lets the driver do this with one thread (24 MB of mesh:
+// 2.3 ms; this way 0.8 ms).
+cudaError_t staged_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    const size_t CH = STAGE_CHUNK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    StagingRing &g_staging = g_staging_dev[dev];
+    std::lock_guard<std::mutex> lock(g_staging.mtx);
+    char **ring = g_staging.ring;
+    cudaEvent_t *ev = g_staging.ev;
+    for (int b = 0; b < STAGE_BUFS && e == cudaSuccess; ++b) {
+        if (!ring[b]) e = cudaHostAlloc(reinterpret_cast<void **>(&ring[b]), CH, cudaHostAllocPortable);
+        if (e == cudaSuccess && !ev[b]) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    }
+    const size_t nch = (bytes + CH - 1) / CH;
+    for (size_t i = 0; i < nch && e == cudaSuccess; ++i) {
+        const size_t n = bytes - i * CH < CH ? bytes - i * CH : CH;
+        const int b = (int)(i % STAGE_BUFS);
+        if (i >= (size_t)STAGE_BUFS) e = cudaEventSynchronize(ev[b]);          // the DMA that last read this buffer
+        if (e != cudaSuccess) break;
+        parallel_for_bytes(ring[b], n, copy_bytes, static_cast<const char *>(src) + i * CH);
+        e = cudaMemcpyAsync(static_cast<char *>(dst) + i * CH, ring[b], n, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+    }
+    // the ring is shared: nothing may still be reading it when the lock goes (the copies are short; the kernels behind them are not waited for)
+    for (int b = 0; b < STAGE_BUFS && b < (int)nch; ++b) { const cudaError_t w = cudaEventSynchronize(ev[b]); if (e == cudaSuccess) e = w; }
+    return e;
+}
+
 cudaError_t staged_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st)
 {
     return staged_d2h_sink(src, bytes, st, [dst](const char *data, size_t n, size_t off) {
@@ -608,8 +641,12 @@ int sdfb_plan_set_mesh_host(sdfb_plan *p, const uint32_t *tri, uint64_t ntri, co
         CU(dev_alloc(&p->xyz_own, (nvert ? nvert : 1) * 3 * sizeof(float)));
         p->xyz_own_cap = nvert ? nvert : 1;
     }
-    if (ntri) CU(cudaMemcpyAsync(p->tri_own, tri, ntri * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    if (nvert) CU(cudaMemcpyAsync(p->xyz_own, xyz, nvert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    auto upload = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (bytes >= ((size_t)4 << 20) && is_pageable(src)) return staged_h2d(dst, src, bytes, st);
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    if (ntri) CU(upload(p->tri_own, tri, ntri * 3 * sizeof(uint32_t)));
+    if (nvert) CU(upload(p->xyz_own, xyz, nvert * 3 * sizeof(float)));
     return build_records(p, p->tri_own, p->xyz_own, ntri, nvert, st);
 }
 
