@@ -62,6 +62,7 @@ Tuning tuning_from_env()
     t.minb = env_int("SDFB_MINB", 0);
     t.max_occ = env_int("SDFB_MAX_OCC", 0);
     t.cta_queue = env_int("SDFB_CTA_QUEUE", -1);
+    t.cta_queue_until = env_int("SDFB_CTA_QUEUE_UNTIL", 8);
     t.relax_list_cap = env_int("SDFB_RELAX_LIST_CAP", 0);
     if (getenv("SDFB_RELAX_HEAVY_LIMIT")) t.relax_heavy_limit = (long long)strtoull(getenv("SDFB_RELAX_HEAVY_LIMIT"), nullptr, 10);
     t.relax_scan_from = env_int("SDFB_RELAX_SCAN_FROM", 13);

@@ -35,6 +35,7 @@ struct Tuning {
     int minb = 0;                 // SDFB_MINB: 3 / 4 = register bound (CTAs per SM) of the column kernels, 0 = by launch size
     int max_occ = 0;              // SDFB_MAX_OCC: cap on resident column CTAs per SM (experiments)
     int cta_queue = -1;           // SDFB_CTA_QUEUE: 0/1 force the warp-private / column-wide evaluation queue
+    int cta_queue_until = 8;      // SDFB_CTA_QUEUE_UNTIL: first sweep that uses warp-private queues (default: the second pass)
     int relax_list_cap = 0;       // SDFB_RELAX_LIST_CAP: work-list capacity (tests force the bitmap fallback)
     long long relax_heavy_limit = -1;   // SDFB_RELAX_HEAVY_LIMIT: work-list entries before a sweep is handed back to the columns
     int relax_scan_from = 13;     // SDFB_RELAX_SCAN_FROM: first sweep whose round 0 uses the lean scan kernel

@@ -1135,7 +1135,7 @@ int COLS_FN(launch_sweep_columns_fused)(uint64_t *cells, const TriRec *rec, cons
         if (!fill_col_params(P, g, first + q, *epoch + 1 + (uint32_t)q)) return 0;      // a sweep with nothing to update: do not fuse
         if ((size_t)P.NJ * P.NK > (size_t)FP.flag_stride) return 0;
         FP.col_begin[q + 1] = FP.col_begin[q] + P.NJ * P.NK;
-        P.cta_queue = tun.cta_queue >= 0 ? (tun.cta_queue != 0) : (first + q < 8);
+        P.cta_queue = tun.cta_queue >= 0 ? (tun.cta_queue != 0) : (first + q < tun.cta_queue_until);
         if (link) {
             // upstream side of this sweep: the slab below for dk > 0, above for dk < 0 (if there is one); downstream: the other
             const int s = first + q, up = P.sd.dk > 0 ? 0 : 1, down = 1 - up;
@@ -1222,7 +1222,7 @@ int COLS_FN(launch_sweep_columns)(uint64_t *cells, const TriRec *rec, const Grid
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // evaluation-heavy sweeps (the first pass) balance the distance evaluations over the whole column
-    const bool cta_queue = tun.cta_queue >= 0 ? tun.cta_queue != 0 : (sweep_index < 8);
+    const bool cta_queue = tun.cta_queue >= 0 ? tun.cta_queue != 0 : (sweep_index < tun.cta_queue_until);
     int occ = 1;
     // register bound by the amount of work per launch (see k_sweep_columns)
     int minb = ((int64_t)g.ni * (g.nj - 1) * (rk_hi - rk_lo + 1) >= ((int64_t)300 << 20)) ? 4 : MINB_SMALL;

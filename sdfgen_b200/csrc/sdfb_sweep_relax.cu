@@ -26,6 +26,7 @@
 // changed in this sweep -- recognised by their stamp, which is this sweep's; work lists are de-duplicated
 // with a bitmap (one bit per cell); a list that overflows falls back to scanning the bitmap.  The exact
 // pruning rules (own / duplicate triangle, stamp memo) are those of sdfb_sweep_columns.cu.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include "sdfb_kernels.cuh"
@@ -391,10 +392,10 @@ struct LookParams {
 };
 struct LookPend { uint32_t c; float px, py, pz, phi; };
 struct LookShared {
+    uint32_t priv[LK_WARPS][26 * 32];        // the candidates of each lane's voxel (triangle | q << 27), entry e of lane l at e*32 + l
     uint32_t q_ent[LK_WARPS][LK_QCAP];       // triangle | q << 27
     uint16_t q_own[LK_WARPS][LK_QCAP];       // index into pend
     LookPend pend[LK_WARPS][LK_PCAP];
-    uint32_t priv[LK_WARPS][26 * 32];        // table-driven path: the candidates of each lane's voxel, entry e of lane l at e*32 + l
 };
 
 // directions as compile-time functions of q (SweepDir::of(q), cpu_lib/makelevelset3.cpp:245-248)
@@ -517,17 +518,19 @@ template <> struct LookStep<-1> {
     static __device__ __forceinline__ void filter(const LookParams &, const uint32_t (&)[27], uint32_t, uint32_t *, int &) {}
 };
 
+// generic path: the live neighbours of direction Q go to the lane's private list, like the table-driven path's
+// (the list holds 26 entries -- every neighbour offset once; a voxel of an odd window that has more is put on the sweep's
+// list unevaluated instead)
 template <int Q>
-__device__ __forceinline__ void look_enqueue(const uint32_t (&w)[27], uint32_t live, uint32_t *q_ent, uint16_t *q_own, int &wq, int pidx)
+__device__ __forceinline__ void look_enqueue(const LookParams &P, uint32_t c, const uint32_t (&w)[27], uint32_t live, uint32_t *priv, int &cnt)
 {
     constexpr int di = look_di(Q), dj = look_dj(Q), dk = look_dk(Q);
     if (!live) return;
     #pragma unroll
     for (int m = 0; m < 7; ++m) if ((live >> m) & 1u) {
         const int ci = (m == 0 || m == 2 || m == 4 || m == 6) ? 1 : 0, cj = (m == 1 || m == 2 || m == 5 || m == 6) ? 1 : 0, ck = (m >= 3) ? 1 : 0;
-        q_ent[wq] = (w[(1 - dk * ck) * 9 + (1 - dj * cj) * 3 + (1 - di * ci)] & TRI_MASK) | ((uint32_t)Q << 27);
-        q_own[wq] = (uint16_t)pidx;
-        ++wq;
+        if (cnt < 26) { priv[cnt * 32] = (w[(1 - dk * ck) * 9 + (1 - dj * cj) * 3 + (1 - di * ci)] & TRI_MASK) | ((uint32_t)Q << 27); ++cnt; }
+        else { look_mark(P, c, Q); break; }
     }
 }
 
@@ -638,8 +641,11 @@ __global__ void __launch_bounds__(LK_THREADS, SDFB_LOOK_MINB) k_look_scan(const 
                     live[Q] = look_live<Q, false>(P, w, own, inb && !st, cls); }
                 SDFB_LOOK_Q(0) SDFB_LOOK_Q(1) SDFB_LOOK_Q(2) SDFB_LOOK_Q(3) SDFB_LOOK_Q(4) SDFB_LOOK_Q(5) SDFB_LOOK_Q(6) SDFB_LOOK_Q(7)
 #undef SDFB_LOOK_Q
-                #pragma unroll
-                for (int q = 0; q < 8; ++q) ncand += __popc(live[q]);
+                const uint32_t cc = (uint32_t)(row + i);
+                look_enqueue<0>(P, cc, w, live[0], priv, ncand); look_enqueue<1>(P, cc, w, live[1], priv, ncand);
+                look_enqueue<2>(P, cc, w, live[2], priv, ncand); look_enqueue<3>(P, cc, w, live[3], priv, ncand);
+                look_enqueue<4>(P, cc, w, live[4], priv, ncand); look_enqueue<5>(P, cc, w, live[5], priv, ncand);
+                look_enqueue<6>(P, cc, w, live[6], priv, ncand); look_enqueue<7>(P, cc, w, live[7], priv, ncand);
             }
             const uint32_t bp = __ballot_sync(0xffffffffu, ncand > 0);
             if (!bp) continue;
@@ -664,18 +670,7 @@ __global__ void __launch_bounds__(LK_THREADS, SDFB_LOOK_MINB) k_look_scan(const 
                     pe.px = lattice(i, g.dx, g.ox); pe.py = py; pe.pz = pz;
                     pe.phi = __uint_as_float(__ldg(base + 2 * i + 1));    // high word: the voxel's distance
                     int wq = nq + incl - ncand - done;
-                    if (fast) {
-                        for (int e = 0; e < ncand; ++e, ++wq) { sh.q_ent[warp][wq] = priv[e * 32]; sh.q_own[warp][wq] = (uint16_t)pidx; }
-                    } else {
-                        look_enqueue<0>(w, live[0], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<1>(w, live[1], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<2>(w, live[2], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<3>(w, live[3], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<4>(w, live[4], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<5>(w, live[5], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<6>(w, live[6], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                        look_enqueue<7>(w, live[7], sh.q_ent[warp], sh.q_own[warp], wq, pidx);
-                    }
+                    for (int e = 0; e < ncand; ++e, ++wq) { sh.q_ent[warp][wq] = priv[e * 32]; sh.q_own[warp][wq] = (uint16_t)pidx; }
                 }
                 const int upto = __shfl_sync(0xffffffffu, incl, end - 1);   // candidates of lanes [0, end)
                 nq += upto - done;
