@@ -96,7 +96,7 @@ struct RelaxParams {
 #define SDFB_RELAX_PCAP 96
 #endif
 #ifndef SDFB_RELAX_SOLOCAP
-#define SDFB_RELAX_SOLOCAP 2048
+#define SDFB_RELAX_SOLOCAP 1024
 #endif
 #ifndef SDFB_RELAX_PF
 #define SDFB_RELAX_PF 1
@@ -104,6 +104,12 @@ struct RelaxParams {
 constexpr int QCAP_B = SDFB_RELAX_QCAP;                  // queue entries per warp; a call adds at most 7 * 32
 constexpr int PCAP_B = SDFB_RELAX_PCAP;                   // pending voxels per warp; a call adds at most 32
 constexpr int SOLO_CAP = SDFB_RELAX_SOLOCAP;               // entries of the in-CTA work lists of the tail rounds
+// Single-CTA rounds of at most HASH_MAX entries de-duplicate their pushes in shared memory instead of with atomicOr on the
+// global bitmap: waiting for those seven atomics was 54 % of such a round (profiles/r2_lookahead.txt).  The table is emptied
+// at the start of the round and receives at most 7 * HASH_MAX of its HSET slots, so a probe always ends.
+constexpr int HSET = 2048;
+constexpr unsigned HASH_MAX = 256;
+constexpr uint32_t HSET_EMPTY = 0xffffffffu;               // no cell index (sweep_relax_supported: fewer than 2^32 cells)
 struct Pending {
     uint32_t c;                              // cell index
     float px, py, pz;                        // world position
@@ -111,6 +117,14 @@ struct Pending {
     uint32_t cur_lo, cur_hi;                 // the cell as the filter read it (nobody else writes it in this round)
     uint32_t base_lo, base_hi;               // the cell at the start of the sweep
 };
+// -DSDFB_RELAX_PHASES (measurement builds): cycles of the single-CTA rounds by phase, warp 0 of CTA 0, summed into
+// debug[300 ..]: 4 = list + cell loads, 0 = filter, 1 = evaluation, 2 = replay + pushes, 3 = CTA barrier + next length
+#ifdef SDFB_RELAX_PHASES
+#define RELAX_PHASE(k) do { if (solo && P.debug && warp == 0 && lane == 0) { const unsigned long long t_ = clock64(); \
+        atomicAdd(&P.debug[300 + (k)], t_ - sh.tprev); sh.tprev = t_; } } while (0)
+#else
+#define RELAX_PHASE(k) do { } while (0)
+#endif
 struct RelaxShared {
     uint32_t q_ent[RX_WARPS][QCAP_B];        // triangle
     float q_d[RX_WARPS][QCAP_B];             // owner (index into pend) until evaluated, then the distance
@@ -118,7 +132,9 @@ struct RelaxShared {
     uint32_t thr[8][8];
     uint32_t tmin[8];                        // lowest threshold of each class: the cheap "nothing is fresh" test
     uint32_t slist[2][SOLO_CAP];             // tail rounds (one CTA): the work lists live here
+    uint32_t hset[HSET];                     // ... and the set of cells already pushed in this round (open addressing)
     unsigned int scount[3];
+    unsigned long long tprev;                // SDFB_RELAX_PHASES
 };
 
 __device__ __forceinline__ uint64_t ld_cg64(const uint64_t *p) { return __ldcg(reinterpret_cast<const unsigned long long *>(p)); }
@@ -214,7 +230,8 @@ __device__ __forceinline__ void load_words_l2(const uint64_t *cp, int64_t si, in
 // solo = tail rounds run by one CTA: the next list and its length live in shared memory (entries beyond
 // SOLO_CAP spill to the global list).
 __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &sh, int warp, int lane, int &nq, int &np,
-                                            int push_parity, unsigned int *push_count, bool solo, int &net_changed, unsigned &evals)
+                                            int push_parity, unsigned int *push_count, bool solo, int &net_changed, unsigned &evals,
+                                            bool use_hash = false)
 {
     if (np == 0) return;
     const Grid &g = P.g;
@@ -223,6 +240,7 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
     const Pending *const pend = sh.pend[warp];
     const int64_t si = -(int64_t)P.sd.di, sj = -(int64_t)P.sd.dj * g.ni, sk = -(int64_t)P.sd.dk * g.plane();
     __syncwarp();
+    RELAX_PHASE(0);
     for (int q = lane; q < nq; q += 32) {
         const Pending &pe = pend[__float_as_int(q_d[q])];
         const F3 x0{pe.px, pe.py, pe.pz};
@@ -232,6 +250,7 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
         ++evals;
     }
     __syncwarp();
+    RELAX_PHASE(1);
     for (int pi = lane; pi < np; pi += 32) {
         const Pending &pe = pend[pi];
         const int64_t c = (int64_t)pe.c;
@@ -286,6 +305,16 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
                 const bool a = m & 1, b = m & 2, cc = m & 4;
                 if ((a && !pi_ok) || (b && !pj_ok) || (cc && !pk_ok)) continue;
                 const int64_t d = c - (a ? si : 0) - (b ? sj : 0) - (cc ? sk : 0);
+                if (use_hash) {
+                    uint32_t h = ((uint32_t)d * 2654435761u) >> 21;                   // 11 bits
+                    for (;;) {
+                        const uint32_t old = atomicCAS(&sh.hset[h], HSET_EMPTY, (uint32_t)d);
+                        if (old == HSET_EMPTY) { fresh |= 1u << m; break; }
+                        if (old == (uint32_t)d) break;
+                        h = (h + 1) & (HSET - 1);
+                    }
+                    continue;
+                }
                 const uint32_t bit = 1u << (d & 31);
                 const uint32_t prev = atomicOr(&P.bitmap[push_parity][d >> 5], bit);
                 fresh |= (prev & bit) ? 0u : (1u << m);
@@ -304,6 +333,7 @@ __device__ __forceinline__ void relax_flush(const RelaxParams &P, RelaxShared &s
         }
     }
     __syncwarp();
+    RELAX_PHASE(2);
     nq = 0; np = 0;
 }
 
@@ -374,8 +404,14 @@ __global__ void __launch_bounds__(SCAN_ROWS * 32) k_relax_scan(RelaxParams P)
 // ---- lookahead: one pass over the cells for up to eight consecutive sweeps (see LookState above) ---------------------
 constexpr int LK_WARPS = 8;
 constexpr int LK_THREADS = LK_WARPS * 32;
-constexpr int LK_QCAP = 512;                 // candidate queue entries per warp
-constexpr int LK_PCAP = 128;                 // pending voxels per warp
+#ifndef SDFB_LOOK_QCAP
+#define SDFB_LOOK_QCAP 512
+#endif
+#ifndef SDFB_LOOK_PCAP
+#define SDFB_LOOK_PCAP 128
+#endif
+constexpr int LK_QCAP = SDFB_LOOK_QCAP;      // candidate queue entries per warp
+constexpr int LK_PCAP = SDFB_LOOK_PCAP;      // pending voxels per warp
 struct LookParams {
     Grid g;
     const uint64_t *cells;
@@ -891,6 +927,7 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
         unsigned n = solo ? *reinterpret_cast<volatile unsigned int *>(&sh.scount[r % 3])
                           : *reinterpret_cast<volatile unsigned int *>(&P.count[r % 3]);
         if (n == 0) break;
+        RELAX_PHASE(3);
         work += n;
         // (not once the team or one CTA has taken over: the CTAs that left have already reported their change counts, and a
         // list of a few thousand entries is no longer the heavy case)
@@ -928,11 +965,20 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
             if (blockIdx.x != 0) break;
             for (unsigned t = tid; t < n; t += RX_THREADS) sh.slist[par][t] = __ldcg(&P.list[par][t]);     // import the list
             if (tid == 0) sh.scount[(r + 1) % 3] = 0;
+#ifdef SDFB_RELAX_PHASES
+            if (tid == 0) sh.tprev = clock64();
+#endif
             __syncthreads();
         }
         if (solo) { if (tid == 0) sh.scount[(r + 2) % 3] = 0; }
         else if (blockIdx.x == 0 && tid == 0) P.count[(r + 2) % 3] = 0;
         unsigned int *const push_count = solo ? &sh.scount[(r + 1) % 3] : &P.count[(r + 1) % 3];
+        // (only when every push is sure to fit the next list: a list that overflows is walked from the global bitmap)
+        const bool use_hash = solo && n <= HASH_MAX && 7u * n <= (unsigned)SOLO_CAP + P.list_cap;      // uniform over the CTA
+        if (use_hash) {
+            for (int t = tid; t < HSET; t += RX_THREADS) sh.hset[t] = HSET_EMPTY;
+            __syncthreads();
+        }
         // the bitmap is the work list when a list overflowed
         // (round 0 after the lean scan kernel walks the bitmap it filled; k_look_mark leaves a list like any other round's)
         const bool use_bitmap = (r == 0 && !look_on) || n > P.list_cap + (solo ? (unsigned)SOLO_CAP : 0u);
@@ -980,11 +1026,15 @@ __global__ void __launch_bounds__(RX_THREADS, SDFB_RELAX_MINB) k_relax_rounds(Re
                     was_changed = lo_stamp(cell_lo(wd.own)) == P.stamp;
                     base64 = was_changed ? old64 : wd.own;
                 }
+#ifdef SDFB_RELAX_PHASES
+                asm volatile("" ::"l"(base64), "r"(wd.nb[0] ^ wd.nb[1] ^ wd.nb[2] ^ wd.nb[3] ^ wd.nb[4] ^ wd.nb[5] ^ wd.nb[6]));
+                RELAX_PHASE(4);
+#endif
                 relax_filter(P, sh, warp, lane, valid, c, ri, rj, rk, wd.own, base64, wd.nb, was_changed, nq, np);
-                if (nq > QCAP_B - 7 * 32 || np > PCAP_B - 32) relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
+                if (nq > QCAP_B - 7 * 32 || np > PCAP_B - 32) relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals, use_hash);
             }
         }
-        relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals);
+        relax_flush(P, sh, warp, lane, nq, np, par ^ 1, push_count, solo, net_changed, evals, use_hash);
         if (solo) __syncthreads();                                    // orders the CTA's writes (global and shared) and reads
         else if (team) grid_barrier(&P.count[6], team_target, TEAM_CTAS);
         else grid_barrier(&P.count[4], bar_target, gridDim.x);
@@ -1127,6 +1177,10 @@ int launch_sweep_relax(uint64_t *cells, const TriRec *rec, const Grid &g, int sw
             for (int r = 1; r < 250 && h[4 + 2 * r]; ++r) fprintf(stderr, " %llu@%.0f", h[4 + 2 * r], h[5 + 2 * r] * 1e-3);
             fprintf(stderr, "\n");
         }
+#ifdef SDFB_RELAX_PHASES
+        fprintf(stderr, "[relax] sweep %2d single-CTA rounds, cycles of warp 0: loads %llu filter %llu eval %llu replay+push %llu barrier %llu\n", sweep_index,
+                h[304], h[300], h[301], h[302], h[303]);
+#endif
         fprintf(stderr, "[relax] sweep %2d: round 0 %.3f ms, total %.3f ms, first list %llu, rounds %llu, grid %d x %d\n", sweep_index,
                 h[0] * 1e-6, h[1] * 1e-6, h[2], h[3], grid, RX_THREADS);
     }
