@@ -804,7 +804,12 @@ __device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &ta
 
 // ---- the kernel: round 0 over all voxels, then the rounds ---------------------------------------------------------------------------------------
 constexpr int MAX_GRID_ROUNDS = 256;         // more grid-wide rounds than this cost as much as a column sweep
-constexpr unsigned SOLO_MAX = 512;           // lists this short are finished by one CTA (a CTA barrier per round
+// 256 = HASH_MAX: every single-CTA round is one batch per warp and de-duplicates in shared memory (512: second pass of C2
+// 12.9 ms, 256: 12.3, 128: 12.8, 64: 13.1 -- profiles/r2_lookahead.txt)
+#ifndef SDFB_RELAX_SOLO_MAX
+#define SDFB_RELAX_SOLO_MAX 256
+#endif
+constexpr unsigned SOLO_MAX = SDFB_RELAX_SOLO_MAX;   // lists this short are finished by one CTA (a CTA barrier per round
                                              // instead of a grid barrier)
 // In between, a TEAM of the first few CTAs carries on: a list of a few thousand entries is one batch for their warps, and a
 // barrier among 16 CTAs costs a fraction of one among all 444 (the rounds are pure latency: ~80 of them per sweep).
