@@ -16,11 +16,14 @@
 // pay the full dependency depth ni+nj+nk for them).  Round 0 is then a streaming pass over the cells plus the
 // distance evaluations the stamp memo could not exclude, all at full occupancy; the later rounds touch a few
 // thousand voxels.  One cooperative launch per sweep: round 0 (dense), then rounds over a work list with a
-// grid-wide barrier in between, until a round changes nothing; once a list is short, one CTA finishes alone with
-// the lists in shared memory.  For the last sweeps of the pass, which have almost no candidates, a lean scan
-// kernel marks the voxels that have one and round 0 starts from that bitmap instead of the dense pass.
+// grid-wide barrier in between, until a round changes nothing; lists of at most 4096 entries are run by a team of
+// 16 CTAs, lists of at most 256 by one CTA with the lists (and the set of cells already pushed) in shared memory.
 // Evaluations are batched per warp (filter as the voxels come, evaluate a full queue with all lanes, replay).
 // oracle/relax_emu.c runs the same rules on the CPU in random order against the serial oracle.
+//
+// Round 0 has two cheaper forms.  (1) The lookahead window (below; the default from sweep 8 on for whole grids): ONE scan
+// of the cells serves up to eight consecutive sweeps, each of which then starts from a short list.  (2) Without a
+// window, the last sweeps of a pass, which have almost no candidates, start from a bitmap that a lean scan kernel fills.
 //
 // Bookkeeping: `oldbuf` (8 B per cell, touched only where a cell changes) keeps old[v] for voxels already
 // changed in this sweep -- recognised by their stamp, which is this sweep's; work lists are de-duplicated
