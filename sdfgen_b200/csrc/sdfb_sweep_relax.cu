@@ -424,6 +424,7 @@ struct LookParams {
     uint32_t tmin;                           // lowest threshold of the window: the cheap "nothing is fresh" test
     uint32_t othr[26];                       // class-0 threshold of each neighbour offset in the order of kLookOrder (standard windows)
     int standard;                            // the window starts at a multiple of 8: kLookOrder is its order of first examination
+    int pass2;                               // ... and it is sweeps 8..15 with the thresholds of look_thr8 (compile-time filter)
     LookState *look;
     uint32_t *w_list;
     uint32_t cap_w;
@@ -537,23 +538,40 @@ template <int N, int U> struct LookDup {      // does any partner offset u <= U 
 };
 template <int N> struct LookDup<N, -1> { static __device__ __forceinline__ bool any(const uint32_t (&)[27], uint32_t) { return false; } };
 
-template <int N> struct LookStep {
+// The window that matters is the reference's second pass, sweeps 8..15 after sweeps 0..7: its thresholds are a function of
+// the direction table alone (memo_last_table), so they can be compile-time constants -- and the offsets that sweep 7 was the
+// last to examine (stamp threshold 9) cannot be fresh at all, because no cell carries a stamp above 8 before sweep 8.
+// look_thr8(q, m) = lowest stamp that makes neighbour m of sweep 8 + q fresh for an interior voxel.
+__host__ __device__ constexpr int look_thr8(int q, int m)
+{
+    const bool ci = (m == 0 || m == 2 || m == 4 || m == 6), cj = (m == 1 || m == 2 || m == 5 || m == 6), ck = (m >= 3);
+    for (int e = 8 + q - 1; e >= 0; --e) {
+        const int qe = e & 7;
+        if ((!ci || look_di(qe) == look_di(q)) && (!cj || look_dj(qe) == look_dj(q)) && (!ck || look_dk(qe) == look_dk(q))) return e + 2;
+    }
+    return 1;
+}
+
+template <int N, bool PASS2> struct LookStep {
     // Offsets 0..N in window order: a neighbour that names another triangle than the voxel's, whose cell is newer than the
     // memo entry of the sweep that examines it first and whose triangle no partner offset repeats goes to the lane's private
     // list (entry = triangle | q << 27).  A neighbour without a triangle carries stamp 0 and fails every threshold of a second
-    // pass (launch_look_scan checks that they are all >= 1 << 27).
+    // pass (launch_look_scan checks that they are all >= 1 << 27).  PASS2: the window is sweeps 8..15 (see look_thr8).
     static __device__ __forceinline__ void filter(const LookParams &P, const uint32_t (&w)[27], uint32_t own, uint32_t *priv, int &cnt)
     {
-        LookStep<N - 1>::filter(P, w, own, priv, cnt);
+        LookStep<N - 1, PASS2>::filter(P, w, own, priv, cnt);
         constexpr LookOfs o = kLookOrder[N];
+        constexpr int t8 = look_thr8(o.q, o.m);
+        if (PASS2 && t8 > 8) return;                                  // compile-time: this offset is never fresh in that window
         const uint32_t x = w[look_widx(o.oi, o.oj, o.ok)];
-        if ((((x ^ own) & TRI_MASK) != 0) && (x >= P.othr[N]) && !LookDup<N, N - 1>::any(w, x)) {
+        const uint32_t thr = PASS2 ? (uint32_t)t8 << 27 : P.othr[N];
+        if ((((x ^ own) & TRI_MASK) != 0) && (x >= thr) && !LookDup<N, N - 1>::any(w, x)) {
             priv[cnt * 32] = (x & TRI_MASK) | ((uint32_t)o.q << 27);
             ++cnt;
         }
     }
 };
-template <> struct LookStep<-1> {
+template <bool PASS2> struct LookStep<-1, PASS2> {
     static __device__ __forceinline__ void filter(const LookParams &, const uint32_t (&)[27], uint32_t, uint32_t *, int &) {}
 };
 
@@ -652,7 +670,8 @@ __global__ void __launch_bounds__(LK_THREADS, SDFB_LOOK_MINB) k_look_scan(const 
                 #pragma unroll
                 for (int t = 0; t < 27; ++t) if (t != 13) mx = max(mx, w[t]);
                 if (__any_sync(0xffffffffu, inb && mx >= P.tmin)) {
-                    LookStep<25>::filter(P, w, w[13], priv, ncand);
+                    if (P.pass2) LookStep<25, true>::filter(P, w, w[13], priv, ncand);
+                    else LookStep<25, false>::filter(P, w, w[13], priv, ncand);
                     if (!inb) ncand = 0;
                 }
             } else {
@@ -1250,6 +1269,10 @@ int launch_look_scan(const uint64_t *cells, const TriRec *rec, const Grid &g, in
         if (n != 26) P.standard = 0;
         // the table-driven filter leaves out the "names a triangle" test: a cell without one has stamp 0
         for (int t = 0; t < 26 && P.standard; ++t) if (P.othr[t] < (1u << 27)) P.standard = 0;
+        // the reference's second pass as a whole: thresholds as compile-time constants (checked against the table just built)
+        P.pass2 = (P.standard && s_lo == 8 && s_hi == 16) ? 1 : 0;
+        for (int t = 0; t < 26 && P.pass2; ++t)
+            if (P.othr[t] != (uint32_t)look_thr8(kLookOrderHost[t].q, kLookOrderHost[t].m) << 27) P.pass2 = 0;
     }
     cudaMemsetAsync(P.look, 0, sizeof(LookState), st);
     int dev = 0, sms = 148, occ = 1;
