@@ -716,8 +716,13 @@ int sdfb_plan_sweep(sdfb_plan *p, int32_t first, int32_t count, void *stream)
             if (has && !p->link.peer_halo[side]) return fail(SDFB_ERR_STATE, "linked plan: the slab %s this one has not been linked (sdfb_plan_link_import / _local)", side == 0 ? "below" : "above");
         }
         CU(reset_epoch_if_needed((uint32_t)count));
-        const int l = launch_sweep_columns_fused(p->cells, p->rec, p->g, first, count, p->changed, p->progress, p->progress_words,
-                                                 &p->epoch, st, tun, p->max_ctas, &p->link);
+        // (8 x 16 build unless SDFB_COL_SHAPE=12 is set -- on EVERY slab of the run: the hand-over is per J column and EJ is 8 in
+        // both builds, but a slab's lag behind its upstream neighbour is counted in that neighbour's EK)
+        const int l = tun.col_shape == 12
+            ? launch_sweep_columns_fused_ek12(p->cells, p->rec, p->g, first, count, p->changed, p->progress, p->progress_words,
+                                              &p->epoch, st, tun, p->max_ctas > 0 ? (p->max_ctas * 4 + 2) / 3 : 0, &p->link)
+            : launch_sweep_columns_fused(p->cells, p->rec, p->g, first, count, p->changed, p->progress, p->progress_words,
+                                         &p->epoch, st, tun, p->max_ctas, &p->link);
         if (!l) return fail(SDFB_ERR_STATE, "linked plan: the fused column launch declined sweeps %d..%d on slab [%d,%d)", first, first + count - 1, p->g.k_lo, p->g.k_hi);
         g_launches += l;
         if (first + count - 1 > p->last_sweep) p->last_sweep = first + count - 1;
