@@ -21,6 +21,13 @@ float sdfo_point_triangle_distance(const float *x0, const float *x1, const float
 
 static const int RDIRS[8][3] = { {+1,+1,+1}, {-1,-1,-1}, {+1,+1,-1}, {-1,-1,+1}, {+1,-1,+1}, {-1,+1,-1}, {+1,-1,-1}, {-1,+1,+1} };
 
+/* Design study ("what is next" for the rounds): with tile > 0 a push that stays inside the tile x tile x tile block
+ * of the voxel that changed is processed in the SAME round (as a CTA that keeps the block's cells in shared memory could do);
+ * only pushes that leave the block wait for the next round.  The result is the same -- any order is --; what changes is the
+ * number of grid-wide rounds, which rounds_out then reports. */
+static int emu_tile = 0;
+void sdfo_emu_set_tile(int t) { emu_tile = t > 0 ? t : 0; }
+
 static uint64_t rng_next(uint64_t *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return *s; }
 static void shuffle(int64_t *a, int64_t n, uint64_t *s)
 {
@@ -82,7 +89,7 @@ long sdfo_emu_sweep_relax_from(const uint32_t *tri, const float *x, float *cells
         int64_t nn = 0;
         for (int64_t q = 0; q < n; ++q) {
             const int64_t c = list[q];
-            if (rounds > 0) queued[c] = 0;                     /* popped; may be scheduled again for the next round */
+            queued[c] = 0;                                     /* popped; may be scheduled again */
             const int64_t p = c / plane, rem = c - p * plane;
             const int j = (int)(rem / ni), i = (int)(rem - (int64_t)j * ni), k = (int)p - 1 + k_lo;
             const int ri = di > 0 ? i : ni - 1 - i, rj = dj > 0 ? j : nj - 1 - j, rk = dk > 0 ? k : nk - 1 - k;
@@ -116,7 +123,13 @@ long sdfo_emu_sweep_relax_from(const uint32_t *tri, const float *x, float *cells
                     const int a = m & 1, b = (m >> 1) & 1, cc = (m >> 2) & 1;
                     if ((a && ri + 1 > ni - 1) || (b && rj + 1 > nj - 1) || (cc && rk + 1 > rk_last)) continue;
                     const int64_t d = c - (a ? si : 0) - (b ? sj : 0) - (cc ? sk : 0);
-                    if (!queued[d]) { queued[d] = 1; next[nn++] = d; }
+                    if (queued[d]) continue;
+                    queued[d] = 1;
+                    if (emu_tile > 0) {                        /* same block: this round (appended behind the entries still to come) */
+                        const int i2 = i + (a ? di : 0), j2 = j + (b ? dj : 0), k2 = k + (cc ? dk : 0);
+                        if (i2 / emu_tile == i / emu_tile && j2 / emu_tile == j / emu_tile && k2 / emu_tile == k / emu_tile && n < ncell) { list[n++] = d; continue; }
+                    }
+                    next[nn++] = d;
                 }
             }
         }

@@ -48,3 +48,25 @@ def test_lookahead_sweeps_start_from_few_voxels():
     _, _, evals_plain, _, _ = oracle.port.emu_sweep_mixed(*a, band.phi_band, band.tri_band, relax_from=8, seed=3)
     assert all(0 <= x < 0.1 * n ** 3 for x in r0[8:]), r0
     assert len(scan_evals) == 1 and scan_evals[0] + sum(evals[8:]) <= 1.05 * sum(evals_plain[8:]), (scan_evals, evals[8:], evals_plain[8:])
+
+
+def test_rounds_that_follow_a_front_inside_a_block_give_the_same_result_in_fewer_rounds():
+    """Design study behind DESIGN.md 4.6 (oracle/experiments/tile_rounds.py): pushes that stay inside a block of cells are
+    processed in the same round.  Same result, fewer rounds."""
+    import ctypes as C
+    n = 40
+    w = meshes.stacked_workload(1, n=n, level=4)
+    a = (w["vertices"], w["triangles"], w["origin"], w["dx"], n, n, n)
+    r = oracle.port.staged(*a)
+    L = oracle.port.lib()
+    L.sdfo_emu_set_tile.argtypes = [C.c_int]
+    totals = []
+    try:
+        for tile in (0, 8):
+            L.sdfo_emu_set_tile(tile)
+            phi, tri, evals, changed, rounds = oracle.port.emu_sweep_mixed(*a, r.phi_band, r.tri_band, relax_from=8, seed=5)
+            assert _same(phi, r.phi_swept) and _same(tri, r.tri_final), tile
+            totals.append(sum(rounds[8:]))
+    finally:
+        L.sdfo_emu_set_tile(0)
+    assert totals[1] <= totals[0], totals
