@@ -86,6 +86,9 @@ uint64_t sdfb_launch_count(void);
  * cpu_lib/makelevelset3.cpp:205); here it is SDFB_ERR_INVALID ("triangle T names a vertex index >= nvert"), found on the
  * device and reported by the calls that deliver results (this one, the batch call, sdfb_plan_download,
  * sdfb_plan_write_sdf); the CUDA context stays usable.
+ * Large phi-only calls (>= 64 MB of output) copy phi to the host while the last eight sweeps run and then patch the few
+ * values those sweeps changed; the result is the same as a copy after the last sweep.  While the call
+ * runs, up to 12 worker threads of the library touch / fill phi_out and stage the mesh.
  */
 int sdfb_make_level_set3(const uint32_t *tri, uint64_t ntri, const float *xyz, uint64_t nvert,
                          const float origin[3], float dx, int32_t ni, int32_t nj, int32_t nk,
