@@ -150,63 +150,47 @@ def generate_sdf_debug(vertices, triangles, origin, dx, nx, ny, nz, exact_band: 
     return phi, tri, cnt
 
 
+def _size_grid(extents, nx, ny, nz, dx):
+    """The reference's grid sizing rules in one place (python/sdfgen.py:101-112 and :219-247 state them twice):
+    without dx the spacing follows from the cell counts -- x extent / nx when a count is missing (proportional
+    sizing), the largest extent / count ratio when all three are given -- and every missing count is
+    ceil(extent / dx)."""
+    counts = (nx, ny, nz)
+    if dx is None:
+        if nx is None:
+            raise ValueError("Must specify either 'dx' or 'nx' (or 'nx', 'ny', 'nz') for grid sizing")
+        dx = extents[0] / nx if None in counts[1:] else max(e / n for e, n in zip(extents, counts))
+    return [int(np.ceil(e / dx)) if n is None else n for e, n in zip(extents, counts)], dx
+
+
+def _padded_sdf(vertices, triangles, min_box, max_box, nx, ny, nz, dx, padding, exact_band, backend, num_threads):
+    """Size the grid around the box, add `padding` cells on every side (python/sdfgen.py:114-121,249-255), run
+    generate_sdf and describe the grid with the reference's metadata keys (:137-142)."""
+    (nx, ny, nz), dx = _size_grid(max_box - min_box, nx, ny, nz, dx)
+    origin = min_box - padding * dx
+    sdf = generate_sdf(vertices, triangles, tuple(origin), dx, nx + 2 * padding, ny + 2 * padding, nz + 2 * padding,
+                       exact_band=exact_band, backend=backend, num_threads=num_threads)
+    return sdf, {"origin": tuple(origin), "dx": dx, "bounds": (tuple(min_box), tuple(max_box)), "backend": backend}
+
+
 def generate_from_mesh(vertices: np.ndarray, triangles: np.ndarray, nx: int, ny: Optional[int] = None,
                        nz: Optional[int] = None, dx: Optional[float] = None, padding: int = 1,
                        exact_band: int = 1, backend: str = "auto", num_threads: int = 0) -> Tuple[np.ndarray, dict]:
-    """Grid sizing wrapper, python/sdfgen.py:47-142 (same arithmetic, same metadata keys)."""
+    """SDF of an in-memory mesh on a grid sized from its bounding box, python/sdfgen.py:47-142 (same arguments,
+    same sizing, same metadata keys)."""
     vertices = np.asarray(vertices)
-    min_box = vertices.min(axis=0)
-    max_box = vertices.max(axis=0)
-    extents = max_box - min_box
-    if ny is None or nz is None:
-        if dx is None:
-            dx = extents[0] / nx
-        ny = int(np.ceil(extents[1] / dx)) if ny is None else ny
-        nz = int(np.ceil(extents[2] / dx)) if nz is None else nz
-    elif dx is None:
-        dx = max(extents[0] / nx, extents[1] / ny, extents[2] / nz)
-    nx += 2 * padding
-    ny += 2 * padding
-    nz += 2 * padding
-    origin = min_box - padding * dx
-    sdf = generate_sdf(vertices, triangles, tuple(origin), dx, nx, ny, nz, exact_band=exact_band,
-                       backend=backend, num_threads=num_threads)
-    metadata = {"origin": tuple(origin), "dx": dx, "bounds": (tuple(min_box), tuple(max_box)), "backend": backend}
-    return sdf, metadata
+    return _padded_sdf(vertices, triangles, vertices.min(axis=0), vertices.max(axis=0), nx, ny, nz, dx,
+                       padding, exact_band, backend, num_threads)
 
 
 def generate_from_file(filename: str, nx: Optional[int] = None, ny: Optional[int] = None, nz: Optional[int] = None,
                        dx: Optional[float] = None, padding: int = 1, exact_band: int = 1, backend: str = "auto",
                        num_threads: int = 0) -> Tuple[np.ndarray, dict]:
-    """Load a mesh file and generate its SDF, python/sdfgen.py:145-265 (same sizing modes)."""
+    """Load a mesh file and generate its SDF, python/sdfgen.py:145-265 (same sizing modes; the box is the loader's,
+    as float32)."""
     vertices, triangles, bounds = load_mesh(filename)
-    min_box = np.array(bounds[0], dtype=np.float32)
-    max_box = np.array(bounds[1], dtype=np.float32)
-    extents = max_box - min_box
-    if dx is not None:
-        if nx is None:
-            nx = int(np.ceil(extents[0] / dx))
-        if ny is None:
-            ny = int(np.ceil(extents[1] / dx))
-        if nz is None:
-            nz = int(np.ceil(extents[2] / dx))
-    elif nx is not None:
-        if ny is None or nz is None:
-            dx = extents[0] / nx
-            ny = int(np.ceil(extents[1] / dx)) if ny is None else ny
-            nz = int(np.ceil(extents[2] / dx)) if nz is None else nz
-        else:
-            dx = max(extents[0] / nx, extents[1] / ny, extents[2] / nz)
-    else:
-        raise ValueError("Must specify either 'dx' or 'nx' (or 'nx', 'ny', 'nz') for grid sizing")
-    nx += 2 * padding
-    ny += 2 * padding
-    nz += 2 * padding
-    origin = min_box - padding * dx
-    sdf = generate_sdf(vertices, triangles, tuple(origin), dx, nx, ny, nz, exact_band=exact_band,
-                       backend=backend, num_threads=num_threads)
-    metadata = {"origin": tuple(origin), "dx": dx, "bounds": (tuple(min_box), tuple(max_box)), "backend": backend}
-    return sdf, metadata
+    return _padded_sdf(vertices, triangles, np.array(bounds[0], dtype=np.float32), np.array(bounds[1], dtype=np.float32),
+                       nx, ny, nz, dx, padding, exact_band, backend, num_threads)
 
 
 def load_mesh(filename: str):

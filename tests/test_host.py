@@ -90,6 +90,65 @@ def test_generate_from_mesh_sizing(monkeypatch):
     assert seen["dims"] == (10, 10, 10) and abs(seen["dx"] - 0.25) < 1e-7
 
 
+def test_sizing_wrappers_call_generate_sdf_like_the_reference_wrappers(monkeypatch, tmp_path):
+    """generate_from_mesh / generate_from_file against the reference's own python/sdfgen.py (imported here with a stub in
+    place of its compiled extension, which cannot be built offline): for every sizing mode both must hand generate_sdf the
+    same grid, spacing, origin and options, and return the same metadata.  Runs only where /root/reference exists."""
+    import importlib.util
+    import sys
+    import types
+    ref_py = "/root/reference/python/sdfgen.py"
+    if not os.path.exists(ref_py):
+        pytest.skip("reference sources not present")
+    calls = []
+
+    def fake(vertices, triangles, origin, dx, nx, ny, nz, exact_band=1, backend="auto", num_threads=0):
+        calls.append((tuple(float(x) for x in origin), float(dx), type(dx).__name__, int(nx), int(ny), int(nz), exact_band, backend, num_threads))
+        return np.zeros((nx, ny, nz), np.float32)
+
+    from sdfgen_b200 import mesh_io
+    ext = types.ModuleType("refpkg.sdfgen_ext")
+    ext.load_mesh, ext.generate_sdf, ext.save_sdf, ext.load_sdf = mesh_io.load_mesh, fake, mesh_io.save_sdf, mesh_io.load_sdf
+    ext.is_gpu_available = lambda: True
+    pkg = types.ModuleType("refpkg")
+    pkg.__path__ = []
+    monkeypatch.setitem(sys.modules, "refpkg", pkg)
+    monkeypatch.setitem(sys.modules, "refpkg.sdfgen_ext", ext)
+    spec = importlib.util.spec_from_file_location("refpkg.sdfgen", ref_py)
+    ref = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, "refpkg.sdfgen", ref)
+    spec.loader.exec_module(ref)
+    monkeypatch.setattr(sdfgen_b200, "generate_sdf", fake)
+
+    v, t = meshes.unit_cube(-0.3, 1.9)
+    v = (v * np.array([1.0, 0.61, 1.37], np.float32)).astype(np.float32)
+    obj = tmp_path / "box.obj"
+    obj.write_text("".join(f"v {x!r} {y!r} {z!r}\n" for x, y, z in v.tolist()) + "".join(f"f {a + 1} {b + 1} {c + 1}\n" for a, b, c in t.tolist()))
+
+    def same(kind, **kw):
+        calls.clear()
+        if kind == "mesh":
+            _, m_ref = ref.generate_from_mesh(v, t, **kw)
+            _, m_own = sdfgen_b200.generate_from_mesh(v, t, **kw)
+        else:
+            _, m_ref = ref.generate_from_file(str(obj), **kw)
+            _, m_own = sdfgen_b200.generate_from_file(str(obj), **kw)
+        assert len(calls) == 2 and calls[0] == calls[1], (kind, kw, calls)
+        assert set(m_ref) == set(m_own)
+        assert m_ref["origin"] == m_own["origin"] and m_ref["dx"] == m_own["dx"] and type(m_ref["dx"]) is type(m_own["dx"])
+        assert m_ref["bounds"] == m_own["bounds"] and m_ref["backend"] == m_own["backend"]
+
+    for kw in (dict(nx=16), dict(nx=16, padding=3, exact_band=2), dict(nx=10, ny=7), dict(nx=10, nz=9), dict(nx=8, ny=9, nz=10),
+               dict(nx=12, dx=0.2), dict(nx=12, ny=5, nz=6, dx=0.15, backend="gpu", num_threads=3), dict(nx=9, padding=0)):
+        same("mesh", **kw)
+    for kw in (dict(nx=16), dict(dx=0.1), dict(dx=0.13, padding=2), dict(dx=0.1, nx=7), dict(dx=0.1, ny=5, nz=6), dict(nx=8, ny=9, nz=10),
+               dict(nx=11, ny=4), dict(nx=11, nz=4, padding=0, exact_band=3), dict(nx=6, ny=6, nz=6, dx=0.4, backend="gpu")):
+        same("file", **kw)
+    for mod in (ref, sdfgen_b200):
+        with pytest.raises(ValueError, match="Must specify either 'dx' or 'nx'"):
+            mod.generate_from_file(str(obj), ny=4, nz=4)
+
+
 def test_repository_name_alias_is_the_same_package():
     """`sdfgenfast_b200` (the repository's name) resolves to the very same module objects as `sdfgen_b200`."""
     import sdfgenfast_b200
