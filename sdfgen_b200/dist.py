@@ -1,24 +1,32 @@
-"""Multi-GPU make_level_set3: z-slab sharding, one process per GPU (torch.distributed for the plumbing).
+"""Multi-GPU make_level_set3: z-slab sharding, one process per GPU (torch.distributed for the plumbing only).
 
 The reference is single-device (no communication backend at all); its only
 decomposition is the racy k-slab threading of the CPU sweep (cpu_lib/makelevelset3.cpp:261-290).
-Here the grid's k range is cut into contiguous slabs, the mesh is replicated, and
+Here the grid's k range is cut into contiguous slabs, the triangle records are replicated, and
 
   * phase A (exact band + x-ray crossing counts) and phase C (sign) are local to a slab: the band box
-    and the lattice range are clamped with the GLOBAL nk and then clipped to the slab, x-rays run along
-    i and never leave it.  Bit-exact, no communication.
-  * phase B (sweeps) has one dependency per slab face.  Each pass of 8 direction sweeps runs on every
-    slab concurrently against halo planes (a copy of the neighbour's boundary plane of {phi, closest_tri}
-    cells, exchanged point-to-point over NVLink with NCCL send/recv); passes repeat until no cell changes
-    anywhere (one int all-reduce per pass), at least the reference's 2 passes.  This is the
-    "exchange halos and iterate to a fixed point" scheme of BASELINE.json's north_star; it is NOT
-    bit-identical to the single-device Gauss-Seidel order (values can differ where information crosses a
-    slab face; every value is still the exact distance to some triangle).  tests/ and bench.py report the
-    divergence from the single-device result.  With one rank there are no halos and the result is
-    bit-exact.
+    and the lattice range are clamped with the GLOBAL nk (cpu_lib/makelevelset3.cpp:210-212,222-225)
+    and then clipped to the slab, x-rays run along i and never leave it.  Bit-exact, no communication.
+  * phase B (sweeps) has one dependency per slab face: a sweep reads k offsets 0 and -dk only (:143-149).
 
-`run_sharded` only needs the small SlabEngine interface, so the orchestration is exercised on CPU
-(gloo, world_size 2) with an oracle-backed engine in tests/test_dist_cpu.py; CudaSlabEngine is the product.
+Three transports for that dependency, all behind the small SlabEngine interface:
+
+  linked (DEFAULT; `link_slabs` + `run_sharded_linked`; what bench.py --gpus N and the tests' equality checks run)
+      the slabs' plans are linked (sdfb_plan_link_export / _import: a CUDA IPC handle, 128 bytes through
+      torch.distributed) and every rank enqueues band -> sweep(0, 16) -> sign.  The sweep kernel itself hands
+      the boundary plane to the downstream GPU column by column (peer stores over NVLink + system-scope flags).
+      Bit-identical to one GPU; no collective, no NCCL and no host synchronisation in the data path.
+  `run_sharded_exact` (kept as a cross-check)
+      the same serial order with the whole boundary plane sent by NCCL send/recv after each sweep;
+      bit-identical, parallel efficiency 2 / (world + 1).
+  `run_sharded` (kept as the north_star's "exchange halos, iterate" scheme; APPROXIMATE, used by no default path)
+      every pass of 8 sweeps runs on all slabs at once against stale halo planes; passes repeat until nothing
+      changes or `max_passes` is reached.  Not the single-device Gauss-Seidel order: values differ where
+      information crosses a slab face (every value is still the exact distance to some triangle).
+
+The orchestration of the last two is exercised on CPU (gloo, world_size 2) with an oracle-backed engine in
+tests/test_dist_cpu.py; the linked protocol is emulated on CPU in tests/test_linked_emu.py; CudaSlabEngine is
+the product.
 """
 from __future__ import annotations
 
