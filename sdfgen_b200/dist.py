@@ -323,6 +323,45 @@ def _gather_sum_u64(value, world):
     return sum(vals) & ((1 << 64) - 1), vals
 
 
+def _one_gpu_run(w, device, stream, columns_only):
+    """The whole grid of workload `w` as ONE plan on `device`: per-step time (second of two runs), phase times and the
+    verification checksums.  Default schedule mix first (unless `columns_only`), then the column schedule for all 16
+    sweeps -- what the linked slabs run, which separates the cost of the schedule from the cost of the cross-GPU
+    pipeline.  For 2048^3 the column run is the only one that fits one GPU: 16 B per voxel = 137 of the 180 GB; the
+    relaxation schedule's scratch would not."""
+    import sdfgen_b200
+    from . import _lib
+    ni, nj, nk = w["ni"], w["nj"], w["nk"]
+    sh = stream.cuda_stream
+    one = {}
+
+    def measured(flags):
+        plan = _lib.Plan(ni, nj, nk, device=device, flags=flags)
+        try:
+            plan.set_mesh_host(w["vertices"], w["triangles"], stream=sh)
+            for _ in range(2):
+                plan.run(w["origin"], w["dx"], 1, stream=sh)
+            ph = plan.phase_ms()
+            return ph, plan.verify(stream=sh)
+        finally:
+            plan.close()
+
+    sdfgen_b200.trim_memory()
+    try:
+        if not columns_only:
+            ph, chk = measured(0)
+            one.update(ms_per_step=ph["total"], phase_ms=ph, checksum_values=chk["checksum_values"],
+                       checksum_cells=chk["checksum_cells"], inconsistent=chk["inconsistent"])
+        ph, chk = measured(_lib.SWEEP_COLUMNS)
+        one["all_columns_ms_per_step"] = ph["total"]
+        if columns_only:
+            one.update(ms_per_step=ph["total"], phase_ms=ph, checksum_values=chk["checksum_values"],
+                       checksum_cells=chk["checksum_cells"], inconsistent=chk["inconsistent"])
+    finally:
+        sdfgen_b200.trim_memory()
+    return one
+
+
 def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
     """N > 1: BASELINE configs[3] (5.0 M-triangle torus at 1024^3) cut into N linked k-slabs -- strong scaling, every
     number from the exact mode -- plus, on 8 GPUs, configs[4] (10 M triangles at 2048^3).  One rank per GPU."""
@@ -392,44 +431,32 @@ def bench_main(args, METRIC, UNIT, measured_peaks, ClockSampler):
         eng.close()
         if with_one_gpu:
             # the same grid as ONE plan on rank 0's GPU: the 1-GPU figure of the strong-scaling line and the
-            # 1-GPU-vs-N-GPU equality check of SURVEY.md 8(c)(iii), by checksum over every cell
+            # 1-GPU-vs-N-GPU equality check of SURVEY.md 8(c)(iii), by checksum over every cell.  A comparison run:
+            # if it fails (a 2048^3 plan needs 137 of the 180 GB) the N-GPU figures above still get reported.
             one = {}
             if rank == 0:
-                sdfgen_b200.trim_memory()
-                if not one_gpu_columns_only:
-                    p1 = _lib.Plan(ni, nj, nk, device=local)
-                    p1.set_mesh_host(w["vertices"], w["triangles"], stream=stream.cuda_stream)
-                    for _ in range(2):
-                        p1.run(w["origin"], w["dx"], 1, stream=stream.cuda_stream)
-                    one = {"ms_per_step": p1.phase_ms()["total"], "phase_ms": p1.phase_ms()}
-                    c1 = p1.verify(stream=stream.cuda_stream)
-                    one["checksum_values"], one["checksum_cells"], one["inconsistent"] = c1["checksum_values"], c1["checksum_cells"], c1["inconsistent"]
-                    p1.close()
-                # the same with the column schedule for all 16 sweeps (what the linked slabs run): separates the cost of the
-                # schedule from the cost of the cross-GPU pipeline.  For 2048^3 it is the only one-GPU run that fits: 16 B per
-                # voxel = 137 GB of the 180 GB; the relaxation schedule's scratch would not
-                p2 = _lib.Plan(ni, nj, nk, device=local, flags=_lib.SWEEP_COLUMNS)
-                p2.set_mesh_host(w["vertices"], w["triangles"], stream=stream.cuda_stream)
-                for _ in range(2):
-                    p2.run(w["origin"], w["dx"], 1, stream=stream.cuda_stream)
-                one["all_columns_ms_per_step"] = p2.phase_ms()["total"]
-                if one_gpu_columns_only:
-                    one["ms_per_step"], one["phase_ms"] = one["all_columns_ms_per_step"], p2.phase_ms()
-                    c1 = p2.verify(stream=stream.cuda_stream)
-                    one["checksum_values"], one["checksum_cells"], one["inconsistent"] = c1["checksum_values"], c1["checksum_cells"], c1["inconsistent"]
-                p2.close()
-                sdfgen_b200.trim_memory()
+                try:
+                    one = _one_gpu_run(w, local, stream, one_gpu_columns_only)
+                except Exception as e:
+                    one = {"error": repr(e)[:300]}
+                    try:
+                        sdfgen_b200.trim_memory()
+                    except Exception:
+                        pass
             box = [one]
             dist.broadcast_object_list(box, src=0)
             one = box[0]
-            res["one_gpu_ms_per_step"] = one["ms_per_step"]
-            res["one_gpu_phase_ms"] = one["phase_ms"]
-            res["one_gpu_all_columns_ms_per_step"] = one["all_columns_ms_per_step"]
-            res["one_gpu_value"] = V / (one["ms_per_step"] * 1e-3) / 1e9
-            res["speedup_vs_one_gpu"] = one["ms_per_step"] / dev_ms
-            res["parallel_efficiency"] = one["ms_per_step"] / dev_ms / world
-            res["equal_to_one_gpu"] = bool(one["checksum_values"] == sum_vals and one["inconsistent"] == 0)
-            res["equal_to_one_gpu_with_stamps"] = bool(one["checksum_cells"] == sum_cells)
+            if "ms_per_step" in one:
+                res["one_gpu_ms_per_step"] = one["ms_per_step"]
+                res["one_gpu_phase_ms"] = one["phase_ms"]
+                res["one_gpu_all_columns_ms_per_step"] = one["all_columns_ms_per_step"]
+                res["one_gpu_value"] = V / (one["ms_per_step"] * 1e-3) / 1e9
+                res["speedup_vs_one_gpu"] = one["ms_per_step"] / dev_ms
+                res["parallel_efficiency"] = one["ms_per_step"] / dev_ms / world
+                res["equal_to_one_gpu"] = bool(one["checksum_values"] == sum_vals and one["inconsistent"] == 0)
+                res["equal_to_one_gpu_with_stamps"] = bool(one["checksum_cells"] == sum_cells)
+            else:
+                res["one_gpu_error"] = one.get("error", "no result")
         torch.cuda.synchronize()
         sdfgen_b200.trim_memory()
         return res, (ni, nj, nk, V, T, NV, k_lo, k_hi)

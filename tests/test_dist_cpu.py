@@ -146,3 +146,55 @@ def test_sweep_dk_table_matches_the_reference_order():
     # cpu_lib/makelevelset3.cpp:245-248
     dirs = [(+1, +1, +1), (-1, -1, -1), (+1, +1, -1), (-1, -1, +1), (+1, -1, +1), (-1, +1, -1), (+1, -1, -1), (-1, +1, +1)]
     assert sdist.SWEEP_DK == tuple(d[2] for d in dirs)
+
+
+def test_one_gpu_comparison_run_of_the_bench_closes_its_plans(monkeypatch):
+    """dist._one_gpu_run (the 1-GPU leg of bench.py --gpus N) with a recording stand-in for the plan: which schedules it
+    runs, what it reports, and that a failing run still closes its plan and trims the pool (a 2048^3 plan is 137 GB)."""
+    import types
+    import sdfgen_b200
+    from sdfgen_b200 import _lib, dist as sdist
+    log = []
+
+    class FakePlan:
+        fail_on = None
+
+        def __init__(self, ni, nj, nk, device=0, flags=0):
+            self.flags = flags
+            log.append(("create", flags))
+
+        def set_mesh_host(self, v, t, stream=0):
+            log.append(("mesh", self.flags))
+
+        def run(self, origin, dx, band, stream=0):
+            if FakePlan.fail_on == self.flags:
+                raise MemoryError("out of memory")
+            log.append(("run", self.flags))
+
+        def phase_ms(self):
+            return dict(band=1.0, sweeps=10.0 + self.flags, sign=0.5, total=11.5 + self.flags)
+
+        def verify(self, stream=0):
+            return dict(inconsistent=0, without_triangle=0, checksum_cells=7 + self.flags, checksum_values=9)
+
+        def close(self):
+            log.append(("close", self.flags))
+
+    monkeypatch.setattr(_lib, "Plan", FakePlan)
+    monkeypatch.setattr(sdfgen_b200, "trim_memory", lambda: log.append(("trim",)))
+    w = dict(ni=8, nj=8, nk=8, vertices=None, triangles=None, origin=(0, 0, 0), dx=0.1)
+    stream = types.SimpleNamespace(cuda_stream=0)
+    one = sdist._one_gpu_run(w, 0, stream, False)
+    assert one["ms_per_step"] == 11.5 and one["all_columns_ms_per_step"] == 11.5 + _lib.SWEEP_COLUMNS
+    assert one["checksum_cells"] == 7 and one["checksum_values"] == 9 and one["inconsistent"] == 0
+    assert [x for x in log if x[0] in ("create", "close")] == [("create", 0), ("close", 0), ("create", _lib.SWEEP_COLUMNS), ("close", _lib.SWEEP_COLUMNS)]
+    assert log[0] == ("trim",) and log[-1] == ("trim",) and log.count(("run", 0)) == 2
+    log.clear()
+    one = sdist._one_gpu_run(w, 0, stream, True)
+    assert one["ms_per_step"] == one["all_columns_ms_per_step"] == 11.5 + _lib.SWEEP_COLUMNS and one["checksum_cells"] == 7 + _lib.SWEEP_COLUMNS
+    assert ("create", 0) not in log
+    log.clear()
+    FakePlan.fail_on = _lib.SWEEP_COLUMNS
+    with pytest.raises(MemoryError):
+        sdist._one_gpu_run(w, 0, stream, True)
+    assert log[-2:] == [("close", _lib.SWEEP_COLUMNS), ("trim",)]
