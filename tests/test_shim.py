@@ -132,3 +132,41 @@ def test_generate_from_file_on_the_reference_stl(tmp_path, golden_dir):
     assert sdf3.shape == (18, 22, 26)
     with pytest.raises(ValueError):
         sdfgen_b200.generate_from_file(str(stl))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "gpu_lib", "makelevelset3_gpu.h")), reason="reference headers not present")
+def test_integration_md_replacement_of_the_gpu_slot_compiles_against_the_reference(tmp_path):
+    """INTEGRATION.md section 1 tells a maintainer to replace the body of gpu_lib/makelevelset3_gpu.cu by a C++ file that
+    forwards to sdfb_make_level_set3.  Take that file from the document as written, compile it against the reference's OWN
+    declaration of the slot (gpu_lib/makelevelset3_gpu.h:40-42) and headers, link it with libsdfb.so and call it the way
+    common/sdfgen_unified.cpp:56-58 does: with a B200 it fills phi, without one it must throw (no CPU fallback)."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```cpp\n(.*?)```", doc, flags=re.S) if b.lstrip().startswith("// gpu_lib/makelevelset3_gpu.cpp") and "#include" in b]
+    assert len(blocks) == 1
+    (tmp_path / "makelevelset3_gpu.cpp").write_text(blocks[0])
+    (tmp_path / "main.cpp").write_text(r'''
+#include <cstdio>
+#include <stdexcept>
+#include "makelevelset3_gpu.h"
+int main() {
+    std::vector<Vec3f> x = {Vec3f(0,0,0), Vec3f(1,0,0), Vec3f(0,1,0), Vec3f(0,0,1)};
+    std::vector<Vec3ui> tri = {Vec3ui(0,2,1), Vec3ui(0,1,3), Vec3ui(0,3,2), Vec3ui(1,2,3)};
+    Array3f phi;
+    try {
+        sdfgen::gpu::make_level_set3(tri, x, Vec3f(-0.5f,-0.5f,-0.5f), 0.125f, 16, 12, 8, phi, 1);
+        std::printf("filled %d %d %d\n", phi.ni, phi.nj, phi.nk);
+    } catch (const std::runtime_error& e) { std::printf("threw: %s\n", e.what()); }
+    return 0;
+}
+''')
+    exe = tmp_path / "slot"
+    lib_dir = os.path.join(ROOT, "sdfgen_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", f"-I{ROOT}/include", f"-I{REF}/common", f"-I{REF}/gpu_lib",
+           str(tmp_path / "makelevelset3_gpu.cpp"), str(tmp_path / "main.cpp"), "-o", str(exe),
+           f"-L{lib_dir}", "-lsdfb", f"-Wl,-rpath,{lib_dir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "filled 16 12 8" in r.stdout or ("threw:" in r.stdout and "no CPU fallback" in r.stdout), r.stdout
