@@ -99,3 +99,47 @@ def test_batch_item_layout_matches_the_header():
         out = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
     assert out[0] == ctypes.sizeof(_lib.BatchItem)
     assert out[1:] == [getattr(_lib.BatchItem, f).offset for f in fields]
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype in include/sdfb.h against what sdfgen_b200/_lib.py tells ctypes: same number of parameters, and per
+    parameter the same class (pointer / 64-bit integer / 32-bit integer / float) -- a drifted binding would pass garbage
+    through the C ABI without any error."""
+    hdr = open(os.path.join(ROOT, "include", "sdfb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = re.findall(r"\b(int|uint64_t|const char \*)\s*(sdfb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) >= 30
+
+    def c_class(param):
+        p = " ".join(param.split())
+        if p == "void":
+            return None
+        if "*" in p or "[" in p:
+            return "ptr"
+        if p.startswith(("uint64_t", "int64_t")):
+            return "i64"
+        if p.startswith(("int32_t", "uint32_t", "int ")):
+            return "i32"
+        if p.startswith("float"):
+            return "f32"
+        raise AssertionError("unclassified parameter: " + p)
+
+    def ct_class(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_uint64: "i64", ctypes.c_int64: "i64", ctypes.c_int32: "i32", ctypes.c_uint32: "i32",
+                ctypes.c_int: "i32", ctypes.c_float: "f32"}[t]
+
+    L = _lib.lib()
+    checked = 0
+    for ret, name, params in protos:
+        want = [c for c in (c_class(x) for x in params.split(",")) if c]
+        f = getattr(L, name)
+        if f.argtypes is None:
+            assert not want or name in ("sdfb_version", "sdfb_last_error", "sdfb_device_count", "sdfb_launch_count"), name
+            continue
+        assert [ct_class(t) for t in f.argtypes] == want, (name, want, f.argtypes)
+        want_ret = {"int": ctypes.c_int, "uint64_t": ctypes.c_uint64, "const char *": ctypes.c_char_p}[ret]
+        assert f.restype is want_ret, (name, f.restype)
+        checked += 1
+    assert checked >= 28
