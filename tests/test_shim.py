@@ -170,3 +170,54 @@ int main() {
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "filled 16 12 8" in r.stdout or ("threw:" in r.stdout and "no CPU fallback" in r.stdout), r.stdout
+
+
+def test_integration_md_plan_api_snippets_compile():
+    """The plan-API examples printed in INTEGRATION.md (streaming loop, CLI replacement, batch call, one process per GPU)
+    are compiled against include/sdfb.h inside functions that declare the variables the text assumes -- a renamed entry
+    point or a changed parameter list breaks the document here, not at a maintainer's desk."""
+    import re
+    import tempfile
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    cpp = re.findall(r"```cpp\n(.*?)```", doc, flags=re.S)
+    c = re.findall(r"```c\n(.*?)```", doc, flags=re.S)
+    stream = [b for b in cpp if "sdfb_plan_download_phi_async" in b]
+    cli = [b for b in cpp if "sdfb_plan_write_sdf" in b]
+    batch = [b for b in cpp if "sdfb_make_level_set3_batch" in b]
+    ranks = [b for b in c if "sdfb_plan_link_export" in b]
+    assert len(stream) == 1 and len(cli) == 1 and len(batch) == 1 and len(ranks) == 1
+    pre = '''
+#include <cstdint>
+#include <cstddef>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "sdfb.h"
+typedef struct CUstream_st* cudaStream_t;
+static int cudaStreamCreate(cudaStream_t*) { return 0; }
+static int cudaStreamSynchronize(cudaStream_t) { return 0; }
+struct V3 { float v[3]; float& operator[](int i) { return v[i]; } };
+struct U3 { uint32_t v[3]; uint32_t& operator[](int i) { return v[i]; } };
+'''
+    src = pre + '''
+void streaming(int dev, int nx, int ny, int nz, std::vector<int>& meshes, const uint32_t** tri, const uint64_t* ntri,
+               const float** xyz, const uint64_t* nvert, const float* origin, float dx, float** phi_host) {
+''' + stream[0] + '''}
+int cli(int dev, int nx, int ny, int nz, std::vector<U3>& faceList, std::vector<V3>& vertList, V3 min_box, float dx,
+        int exact_band, std::string outname) {
+''' + cli[0] + '''  return 0; }
+void batch(int n, const uint32_t** tri, const uint64_t* ntri, const float** xyz, const uint64_t* nvert, float ox, float oy,
+           float oz, float dx, int nx, int ny, int nz, float** phi_out) {
+''' + batch[0] + '''}
+void ranks(int nk, int world, int rank, int local_device, int ni, int nj, const uint32_t* tri, uint64_t ntri, const float* xyz,
+           uint64_t nvert, const float* origin, float dx, int exact_band, cudaStream_t stream, float* phi_of_the_whole_grid) {
+  int32_t k_lo, k_hi; sdfb_plan* plan;
+''' + ranks[0] + '''}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "snippets.cpp")
+        open(path, "w").write(src)
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused", f"-I{ROOT}/include", path],
+                           capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
