@@ -88,3 +88,28 @@ def load_golden(golden_dir):
         c["ref"] = {f: z[n + "/" + f] for f in FIELDS}
         out.append(c)
     return out
+
+
+def nasty_case(seed):
+    """A small random problem built to hit the corners of the arithmetic: an open triangle soup (signs are 'wrong' the same
+    way on both sides), vertices ON lattice points and lattice planes (orientation ties, SOS rules, ceil/floor of exact
+    integers), repeated and degenerate triangles (zero-length edges: NaN segment parameters), triangles partly or wholly
+    outside the grid, thin grids, bands 1-3, origins far from zero (coarse float spacing)."""
+    rng = np.random.default_rng(seed)
+    ni, nj, nk = (int(x) for x in rng.integers(1, 14, 3))
+    dx = np.float32(rng.choice([0.125, 0.1, 0.37, 1.0]))
+    origin = (rng.choice([0.0, -1.0, 1000.0, -3.3]) + rng.uniform(-1, 1, 3) * rng.choice([0.0, 1.0])).astype(np.float32)
+    nv = int(rng.integers(3, 24))
+    span = np.array([ni, nj, nk], np.float32) * dx
+    v = (origin + rng.uniform(-0.3, 1.3, (nv, 3)).astype(np.float32) * span).astype(np.float32)
+    on_lattice = rng.random(nv) < 0.4                                  # snap some vertices to lattice points / planes
+    cells = rng.integers(-1, 15, (nv, 3)).astype(np.float32)
+    snapped = (cells * dx + origin).astype(np.float32)
+    axes = rng.random((nv, 3)) < 0.7
+    v = np.where(on_lattice[:, None] & axes, snapped, v).astype(np.float32)
+    nt = int(rng.integers(1, 40))
+    t = rng.integers(0, nv, (nt, 3)).astype(np.uint32)                 # repeated indices = degenerate triangles
+    if nt > 3:
+        t[nt // 2] = t[0]                                              # an exact duplicate: the lower index must win
+        t[nt - 1] = t[0][[1, 2, 0]]                                    # the same triangle, rotated
+    return v, t, origin, float(dx), ni, nj, nk, int(rng.integers(1, 4))
