@@ -41,3 +41,20 @@ def test_emulated_columns_per_sweep():
         r = oracle.port.staged(*a, nsweeps=ns)
         phi, tri, _, _, viol = oracle.port.emu_sweep_columns(*a, band.phi_band, band.tri_band, nsweeps=ns)
         assert viol == 0 and _same(phi, r.phi_swept) and _same(tri, r.tri_final), ns
+
+
+def test_emulated_schedules_on_nasty_random_cases():
+    """The column emulator (both builds) and the relaxation emulator (second pass, and every sweep) on the seeded corner-case
+    problems of tests/cases.py::nasty_case -- thin grids, lattice-aligned soups, duplicate and degenerate triangles, bands
+    1-3 -- against the serial oracle: no halo load outruns its wait condition, results bit-identical."""
+    from cases import nasty_case
+    for seed in range(60):
+        v, t, origin, dx, ni, nj, nk, band = nasty_case(seed)
+        a = (v, t, origin, dx, ni, nj, nk)
+        r = oracle.port.staged(*a, band)
+        for shape in ((8, 16), (8, 12)):
+            phi, tri, _, _, viol = oracle.port.emu_sweep_columns(*a, r.phi_band, r.tri_band, shape=shape)
+            assert viol == 0 and _same(phi, r.phi_swept) and _same(tri, r.tri_final), (seed, shape, (ni, nj, nk))
+        for relax_from in (8, 0):
+            phi, tri, _, _, _ = oracle.port.emu_sweep_mixed(*a, r.phi_band, r.tri_band, relax_from=relax_from, seed=seed + 1)
+            assert _same(phi, r.phi_swept) and _same(tri, r.tri_final), (seed, relax_from, (ni, nj, nk))
