@@ -176,3 +176,33 @@ def test_c_slab_bounds_match_the_python_side():
         assert prev == nk
     a, b = C.c_int32(), C.c_int32()
     assert L.sdfb_slab_bounds(4, 5, 0, C.byref(a), C.byref(b)) == _lib.ERR_INVALID      # more slabs than planes
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference (the reference's CPU path on the host cores): one JSON line with the arm's keys, rank 0
+    only under torchrun; and the GPU arm refuses to run without a B200 instead of falling back to anything."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bench = os.path.join(root, "bench.py")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "c1_blob_256", "--grid", "24", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sdf_gvoxels_per_s" and d["unit"] == "Gvoxel/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["gpu_launches"] == 0 and d["value"] > 0
+    assert d["config"]["workload"] == "c1_blob_256" and d["config"]["grid"] == [24, 24, 24] and d["config"]["same_config_as_gpu_arm"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert abs(d["value"] - 24 ** 3 / (d["ms_per_step"] * 1e-3) / 1e9) < 1e-9 * max(1.0, d["value"])
+    # under torchrun only rank 0 measures; the other ranks leave without output
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--gpus", "2", "--grid", "24"], capture_output=True, text=True,
+                       env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    if not sdfgen_b200.is_gpu_available():
+        r = subprocess.run([sys.executable, bench, "--steps", "1"], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
