@@ -139,7 +139,13 @@ def exchange_halos(engine, rank, world, group=None):
 
 
 def run_sharded(engine, rank, world, origin, dx, exact_band=1, min_passes=2, max_passes=3, group=None) -> ShardStats:
-    """Phases A, B (halo exchange + passes of 8 sweeps until nothing changes), C on one rank's slab."""
+    """APPROXIMATE transport (kept for comparison; no default path and no bench number uses it): phases A, B, C on one
+    rank's slab with every pass of 8 sweeps run against stale halo planes.  Passes repeat until no cell changed anywhere
+    OR `max_passes` is reached, whichever comes first -- with the default cap of 3 the loop usually stops while cells
+    are still changing (stats.changed_per_pass[-1] > 0), so the result is neither the reference's 16 sweeps nor a fixed
+    point: measured 0.16 % of the voxels off by up to 0.03 dx at 2 x 512^3 (profiles/r1_exact_mode_2gpu_fullsize.txt).
+    Counts and signs are exact.  Plan indices beyond 30 lose the stamp memo (5-bit stamps), which is why the cap is low.
+    Use link_slabs + run_sharded_linked (bit-identical to one GPU) for results."""
     import torch.distributed as dist
     stats = ShardStats()
     engine.band(origin, dx, exact_band)
