@@ -198,3 +198,62 @@ def test_one_gpu_comparison_run_of_the_bench_closes_its_plans(monkeypatch):
     with pytest.raises(MemoryError):
         sdist._one_gpu_run(w, 0, stream, True)
     assert log[-2:] == [("close", _lib.SWEEP_COLUMNS), ("trim",)]
+
+
+# ---- linked mode: the handle exchange of link_slabs / unlink_slabs (gloo; the device side is tests/test_linked_emu.py) ----
+
+class _RecordingPlan:
+    """Stand-in for _lib.Plan in link_slabs: exports a handle that names its rank, records what it imports and when."""
+    def __init__(self, rank):
+        self.rank, self.log = rank, []
+
+    def link_export(self):
+        self.log.append("export")
+        return bytes([self.rank]) * 128
+
+    def link_import(self, side, handle):
+        assert len(handle) == 128 and len(set(handle)) == 1
+        self.log.append(("import", side, handle[0]))
+
+    def unlink(self):
+        self.log.append("unlink")
+
+
+def _worker_link(rank, world, port, out_dir):
+    import json
+    import types
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = types.SimpleNamespace(plan=_RecordingPlan(rank))
+    sdist.link_slabs(eng, rank, world)
+    stats = sdist.run_sharded_linked(types.SimpleNamespace(band=lambda *a: eng.plan.log.append("band"),
+                                                           sweep=lambda f, c: eng.plan.log.append(("sweep", f, c)),
+                                                           sign=lambda: eng.plan.log.append("sign")), (0, 0, 0), 0.1, 1)
+    orig_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda *a, **k: None            # unlink_slabs waits for the device first; none here
+    try:
+        sdist.unlink_slabs(eng)
+    finally:
+        torch.cuda.synchronize = orig_sync
+    json.dump({"log": eng.plan.log, "passes": stats.passes}, open(os.path.join(out_dir, f"r{rank}.json"), "w"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_link_slabs_wires_each_rank_to_its_two_neighbours(tmp_path, world):
+    """Every rank exports once, imports the handle of rank-1 as side 0 (the slab below) and of rank+1 as side 1 (the slab
+    above) -- the faces of the grid import nothing on their outer side --, runs band -> sweep(0, 16) -> sign, unlinks once."""
+    import json
+    port = 29900 + world + (os.getpid() % 1000)
+    mp.spawn(_worker_link, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = json.load(open(os.path.join(str(tmp_path), f"r{r}.json")))
+        want = ["export"]
+        if r > 0:
+            want.append(["import", 0, r - 1])
+        if r < world - 1:
+            want.append(["import", 1, r + 1])
+        want += ["band", ["sweep", 0, 16], "sign", "unlink"]
+        assert d["log"] == want, (r, d["log"])
+        assert d["passes"] == 2
