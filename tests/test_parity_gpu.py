@@ -464,45 +464,6 @@ def test_edge_shapes_and_reuse():
             p.close()
 
 
-def test_plan_call_order_is_checked():
-    """The plan API refuses calls out of order with SDFB_ERR_STATE instead of computing from stale state: phases before a
-    mesh / before the band, and a sweep index that skips sweeps (the stamp memo assumes every earlier sweep has looked at
-    the cells, include/sdfb.h).  Bad arguments are SDFB_ERR_INVALID.  The plan stays usable afterwards."""
-    v, t = meshes.icosphere(2, 0.3)
-    o, dx, n = np.array([-0.5, -0.5, -0.5], np.float32), 1.0 / 24, 24
-    p = _lib.Plan(n, n, n)
-    try:
-        for call in (lambda: p.band(o, dx, 1), lambda: p.sweep(0, 1), lambda: p.sign()):
-            with pytest.raises(_lib.SdfbError) as e:
-                call()
-            assert e.value.code == _lib.ERR_STATE
-        p.set_mesh_host(v, t)
-        for call in (lambda: p.sweep(0, 16), lambda: p.sign()):              # still no band
-            with pytest.raises(_lib.SdfbError) as e:
-                call()
-            assert e.value.code == _lib.ERR_STATE
-        with pytest.raises(ValueError):
-            p.band(o, 0.0, 1)
-        with pytest.raises(ValueError):
-            p.band(o, dx, -1)
-        p.band(o, dx, 1)
-        with pytest.raises(_lib.SdfbError) as e:
-            p.sweep(5, 1)                                                     # sweeps 0..4 have not run
-        assert e.value.code == _lib.ERR_STATE and "in order" in str(e.value)
-        with pytest.raises(ValueError):
-            p.sweep(-1, 1)
-        p.sweep(0, 8)
-        with pytest.raises(_lib.SdfbError):
-            p.sweep(10, 1)                                                    # 8 and 9 are missing
-        p.sweep(8, 8)
-        p.sign()
-        phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
-        r = oracle.best().staged(v, t, o, dx, n, n, n, 1)
-        assert _same(phi, r.phi) and _same(tri, r.tri_final) and _same(cnt, r.counts)
-    finally:
-        p.close()
-
-
 def test_slab_plans_band_and_sign_match_full_grid():
     """Phases A and C are local in k: slab plans reproduce the matching window of the full grid."""
     w = meshes.workload("c1_blob_256", n=48)
@@ -706,3 +667,42 @@ def test_more_than_2_31_voxels_on_one_gpu():
     far = np.abs(exact) > float(dx)
     assert np.array_equal(ph[far] < 0, exact[far] < 0)
     assert np.abs(ph - exact).max() < 0.75 * float(dx)
+
+
+def test_plan_call_order_is_checked():
+    """The plan API refuses calls out of order with SDFB_ERR_STATE instead of computing from stale state: phases before a
+    mesh / before the band, and a sweep index that skips sweeps (the stamp memo assumes every earlier sweep has looked at
+    the cells, include/sdfb.h).  Bad arguments are SDFB_ERR_INVALID.  The plan stays usable afterwards."""
+    v, t = meshes.icosphere(2, 0.3)
+    o, dx, n = np.array([-0.5, -0.5, -0.5], np.float32), 1.0 / 24, 24
+    p = _lib.Plan(n, n, n)
+    try:
+        for call in (lambda: p.band(o, dx, 1), lambda: p.sweep(0, 1), lambda: p.sign()):
+            with pytest.raises(_lib.SdfbError) as e:
+                call()
+            assert e.value.code == _lib.ERR_STATE
+        p.set_mesh_host(v, t)
+        for call in (lambda: p.sweep(0, 16), lambda: p.sign()):              # still no band
+            with pytest.raises(_lib.SdfbError) as e:
+                call()
+            assert e.value.code == _lib.ERR_STATE
+        with pytest.raises(ValueError):
+            p.band(o, 0.0, 1)
+        with pytest.raises(ValueError):
+            p.band(o, dx, -1)
+        p.band(o, dx, 1)
+        with pytest.raises(_lib.SdfbError) as e:
+            p.sweep(5, 1)                                                     # sweeps 0..4 have not run
+        assert e.value.code == _lib.ERR_STATE and "in order" in str(e.value)
+        with pytest.raises(ValueError):
+            p.sweep(-1, 1)
+        p.sweep(0, 8)
+        with pytest.raises(_lib.SdfbError):
+            p.sweep(10, 1)                                                    # 8 and 9 are missing
+        p.sweep(8, 8)
+        p.sign()
+        phi, tri, cnt = p.download(phi=True, tri=True, counts=True)
+        r = oracle.best().staged(v, t, o, dx, n, n, n, 1)
+        assert _same(phi, r.phi) and _same(tri, r.tri_final) and _same(cnt, r.counts)
+    finally:
+        p.close()
