@@ -143,3 +143,30 @@ def test_ctypes_prototypes_match_the_header():
         assert f.restype is want_ret, (name, f.restype)
         checked += 1
     assert checked >= 28
+
+
+def test_missing_library_fails_loudly():
+    """Without libsdfb.so the package must not compute anything: the first call is an ImportError that says how to build
+    the extension, from every public entry (there is no Python, torch or oracle fallback behind it)."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, sdfgen_b200\n"
+        "from sdfgen_b200 import meshes\n"
+        "v, t = meshes.unit_cube()\n"
+        "calls = [lambda: sdfgen_b200.is_gpu_available(), lambda: sdfgen_b200.generate_sdf(v, t, (0, 0, 0), 0.1, 8, 8, 8),\n"
+        "         lambda: sdfgen_b200.generate_from_mesh(v, t, nx=8), lambda: sdfgen_b200.Plan(8, 8, 8),\n"
+        "         lambda: sdfgen_b200.generate_sdf_batch([dict(vertices=v, triangles=t, origin=(0, 0, 0), dx=0.1, nx=4, ny=4, nz=4)])]\n"
+        "for c in calls:\n"
+        "    try:\n"
+        "        c()\n"
+        "    except ImportError as e:\n"
+        "        assert 'no CPU fallback' in str(e) and 'make -C sdfgen_b200/csrc' in str(e)\n"
+        "    else:\n"
+        "        raise SystemExit('a call succeeded without the library')\n"
+        "import sys\n"
+        "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'the product imported the oracle'\n"
+        "print('LOUD')\n")
+    env = dict(os.environ, SDFB_LIB_PATH="/nonexistent/libsdfb.so", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and "LOUD" in r.stdout, r.stdout + r.stderr
