@@ -170,3 +170,26 @@ def test_missing_library_fails_loudly():
     env = dict(os.environ, SDFB_LIB_PATH="/nonexistent/libsdfb.so", PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and "LOUD" in r.stdout, r.stdout + r.stderr
+
+
+def test_product_sources_never_reach_into_the_oracle():
+    """Static side of the same rule: no module under sdfgen_b200/ (or its alias package) imports `oracle`, the library's
+    build does not compile or link anything from oracle/, and libsdfb.so does not depend on the checkers' shared objects."""
+    import ast
+    import subprocess
+    for pkg in ("sdfgen_b200", "sdfgenfast_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                path = os.path.join(dirpath, f)
+                if f.endswith(".py"):
+                    for node in ast.walk(ast.parse(open(path).read())):
+                        names = [a.name for a in node.names] if isinstance(node, ast.Import) else \
+                                [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+                        assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+                elif f.endswith((".cu", ".cuh", ".h", ".hpp")) or f == "Makefile":
+                    text = open(path).read()
+                    assert not re.search(r'#include\s*[<"][^>"]*oracle', text), path
+                    assert "liboracle" not in text and "libsdfgen_ref" not in text, path
+    r = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode == 0:
+        assert "oracle" not in r.stdout and "sdfgen_ref" not in r.stdout and "libtorch" not in r.stdout and "libcudart" not in r.stdout, r.stdout
